@@ -1,0 +1,108 @@
+/* qmprs_b200 -- C ABI of the B200 (sm_100a) kernels behind the qmprs MPS hot path.
+ *
+ * Conventions
+ *   - every matrix is row-major complex128 (interleaved re,im; 16 bytes per element),
+ *     leading dimensions are in elements;
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 on success, a cudaError_t (>0) on a CUDA failure, <0 on a
+ *     workspace/argument error.  The Python host maps non-zero to RuntimeError.
+ *
+ * Each entry point names the reference interface it replaces.  The reference
+ * (Qualition/qmprs) is pure Python: the "FFI" it binds today is numpy/scipy LAPACK and
+ * quimb's tensor routines, reached from the cited lines.
+ */
+#ifndef QMPRS_B200_H
+#define QMPRS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- dense linear algebra ------------------------------------------------------ */
+
+/* C = alpha*A*B + beta*C (NN).  Replaces quimb tensordot/tensor_contract reached from
+ * qmprs/primitives/mps.py:270 (to_dense), :451-453 (compress), :968-971 (gate_split_).
+ * batch > 1 strides the three operands. */
+int qm_zgemm(int m, int n, int k, double alpha_re, double alpha_im, const void* A, long long lda,
+             const void* B, long long ldb, double beta_re, double beta_im, void* C, long long ldc,
+             int batch, long long strideA, long long strideB, long long strideC, void* stream);
+
+/* Thin SVD A = U diag(S) Vh by blocked one-sided Jacobi.  Replaces numpy/LAPACK zgesdd
+ * behind quimb tensor_split: mps.py:242 (from_dense), :451-453, :928-931, :968-971;
+ * sequential.py:443.  S is double[k], sorted descending, k = min(m,n).  U/Vh may be NULL.
+ * info_host: host int[2] = {sweeps, converged} (may be NULL). */
+long long qm_svd_work_bytes(int m, int n);
+int qm_svd(int m, int n, const void* A, long long lda, void* U, long long ldu, void* S, void* Vh,
+           long long ldvh, void* work, long long work_bytes, double tol, int max_sweeps, int* info_host,
+           void* stream);
+
+/* Householder QR (LAPACK zgeqr2 layout), explicit thin Q, and R with non-negative
+ * diagonal.  Replaces quimb qr_stabilized behind left_canonize / right_canonize /
+ * tensor_compress_bond: mps.py:396-398, :451-453. */
+int qm_qr(int m, int n, void* A, long long lda, void* tau, void* stream);
+int qm_qr_formq(int m, int k, const void* A, long long lda, const void* tau, void* Q, long long ldq, void* stream);
+int qm_qr_finish(int m, int n, const void* A, long long lda, void* R, long long ldr, void* Q, long long ldq,
+                 void* stream);
+
+/* ---- MPS bookkeeping ----------------------------------------------------------- */
+
+/* Rank selection of quimb _trim_and_renorm_svd_result: mode 0 'rel', 1 'rsum2' (+renorm).
+ * out_rank: int[1], out_f: double[1] (renormalisation factor). */
+int qm_trim(const void* S, int k, double cutoff, int mode, int max_bond, void* out_rank, void* out_f, void* stream);
+
+/* out = in with rows (mode 1) or columns (mode 2) scaled by (S*f)^(half_power ? 1/2 : 1);
+ * mode 0 copies.  absorb='both' / 'left' of tensor_split.  f may be NULL. */
+int qm_scale_copy(void* out, long long ldo, const void* in, long long ldi, int rows, int cols, const void* S,
+                  const void* f, int mode, int half_power, void* stream);
+
+/* theta[(l,oi),(oj,r)] = sum M[(oi,oj),(pi,pj)] X[(l,pi),(pj,r)], M = G or G^H, in place
+ * on the (2l x 2r) matrix X.  gate_split_ contraction, mps.py:928-931, :968-971. */
+int qm_theta_gate(void* X, int l, int r, const void* G, int dagger, void* stream);
+
+/* B[l,o,r] = sum_p M[o,p] B[l,p,r] in place.  gate_(contract=True), mps.py:913-917, :953-957. */
+int qm_site_gate(void* B, int l, int r, const void* G, int dagger, void* stream);
+
+/* chi=2 truncation bookkeeping for one bond (mps.py:881): picks n <= 2 by the 'rel'
+ * cutoff, applies the canonical row-phase rule, writes the site tensor rows Csite[2][4],
+ * the projector Vsel[4][2] and bond[0] = n. */
+int qm_chi2_select(const void* S, const void* Vh, long long ldvh, double cutoff, double tie, void* Csite,
+                   void* Vsel, void* bond, void* stream);
+int qm_chi2_first(const void* T0, void* Csite, void* stream);
+
+/* Isometry -> unitary completion for all sites of a chi=2 MPS
+ * (_generate_{first,two,last}_site_unitary + generate_unitary_layer, mps.py:565-847).
+ * C: [N][8] padded site tensors, bond: int[N-1]; gates: [N][16], kinds: int[N]
+ * (2 = two-qubit gate on (i,i+1), 1 = one-qubit gate), bad: int[1] unitarity flag. */
+int qm_complete_unitaries(const void* C, const void* bond, int n_sites, void* gates, void* kinds, void* bad,
+                          double sign_tol, void* stream);
+
+/* ---- vectors ------------------------------------------------------------------- */
+int qm_conj_scale_copy(void* out, const void* in, long long n, int conj, double scale, void* stream);
+int qm_vdot(const void* a, const void* b, long long n, void* out2 /* double[2] */, void* stream);
+int qm_div_sqrt(void* x, long long n, const void* nrm2 /* double[1] */, void* stream);
+
+/* ---- dense statevector path (optimisation sweeps) -------------------------------- */
+
+/* x <- op(G) x on site (kind 1) or sites (site,site+1) (kind 2); op 0 G, 1 G^H, 2 G^T.
+ * quimb `TensorNetwork @ Tensor`, sequential.py:460, :496. */
+int qm_apply_gate(void* x, int n_sites, int site, int kind, const void* G, int op, void* stream);
+
+/* c <- gates applied in order to |0..0>.  sites/kinds: HOST int arrays.
+ * sequential.py:215-292 + to_dense :443-447. */
+int qm_circuit_state(void* c, int n_sites, const void* gates, const int* sites, const int* kinds, int n_gates,
+                     void* stream);
+
+/* One environment sweep, gates updated in place (sequential.py:452-505).
+ * work: qm_sweep_work_bytes() bytes.  envs: optional [n_gates][16] record of each E. */
+long long qm_sweep_work_bytes(void);
+int qm_sweep(void* c, void* tbar, int n_sites, void* gates, const int* sites, const int* kinds, int n_gates,
+             void* work, void* envs, void* stream);
+
+/* Library identification: returns the compiled architecture number (100 for sm_100a). */
+int qm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMPRS_B200_H */

@@ -299,7 +299,14 @@ def first_site_unitary(a, gauge):
 def two_site_unitary(a, gauge):
     """mps.py:653-683.  ``a``: (2,2,2) tensor of an interior site of a block."""
     K = null_space(np.conj(a.reshape(2, 4)), gauge)            # 4 x 2
-    K = K / np.exp(1j * np.angle(K[0]))                        # mps.py:661-662
+    if gauge == "verbatim":
+        K = K / np.exp(1j * np.angle(K[0]))                    # mps.py:661-662
+    else:
+        # same rule, but a first entry that is zero up to rounding (structural zeros are
+        # common after a disentangling layer) has no meaningful phase: leave that vector
+        mag = np.abs(K[0])
+        ph = np.where(mag > SIGN_TOL, K[0] / np.where(mag > 0, mag, 1.0), 1.0)
+        K = K / ph
     u = np.zeros((2, 2, 2, 2), dtype=np.complex128)
     u[0] = a
     u[1] = K.reshape(2, 2, 2, 1).transpose(3, 2, 0, 1)

@@ -1,0 +1,70 @@
+// Shared device helpers for the qmprs_b200 kernels (complex128 arithmetic on double2).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef double2 cplx;
+
+#define QM_CHECK_LAUNCH()                                  \
+    do {                                                   \
+        cudaError_t e__ = cudaGetLastError();              \
+        if (e__ != cudaSuccess) return (int)e__;           \
+    } while (0)
+
+#define QM_CUDA(call)                                      \
+    do {                                                   \
+        cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return (int)e__;           \
+    } while (0)
+
+__host__ __device__ __forceinline__ cplx mk(double re, double im) { cplx z; z.x = re; z.y = im; return z; }
+__host__ __device__ __forceinline__ cplx cconj(cplx a) { return mk(a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return mk(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// a * conj(b)
+__host__ __device__ __forceinline__ cplx cmulc(cplx a, cplx b) { return mk(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+// conj(a) * b
+__host__ __device__ __forceinline__ cplx ccmul(cplx a, cplx b) { return mk(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
+__host__ __device__ __forceinline__ cplx cscale(cplx a, double s) { return mk(a.x * s, a.y * s); }
+__host__ __device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
+// acc += a*b
+__host__ __device__ __forceinline__ void cfma(cplx& acc, cplx a, cplx b) {
+    acc.x += a.x * b.x - a.y * b.y;
+    acc.y += a.x * b.y + a.y * b.x;
+}
+// acc += a*conj(b)
+__host__ __device__ __forceinline__ void cfmac(cplx& acc, cplx a, cplx b) {
+    acc.x += a.x * b.x + a.y * b.y;
+    acc.y += a.y * b.x - a.x * b.y;
+}
+// acc += conj(a)*b
+__host__ __device__ __forceinline__ void ccfma(cplx& acc, cplx a, cplx b) {
+    acc.x += a.x * b.x + a.y * b.y;
+    acc.y += a.x * b.y - a.y * b.x;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; result valid in every thread.  `red` must hold >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = (lane < nw) ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

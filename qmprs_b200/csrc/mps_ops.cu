@@ -1,0 +1,398 @@
+// Small MPS kernels: rank selection, singular-value absorption, gate application on
+// site tensors, chi=2 gauge fixing and isometry->unitary completion.
+//
+// Reference call sites (qmprs/primitives/mps.py unless noted):
+//   qm_trim               quimb _trim_and_renorm_svd_result behind :242, :451-453, :928-931, :968-971
+//   qm_scale_copy         absorb='both' / 'left' of the same splits
+//   qm_theta_gate         gate_split_ contraction with the 4x4 gate            :968-971
+//   qm_site_gate          gate_(..., contract=True)                            :953-957
+//   qm_chi2_select        compress(mode="right", max_bond=2) bookkeeping       :881  (+ canonical phase rule)
+//   qm_complete_unitaries _generate_{first,two,last}_site_unitary, generate_unitary_layer  :565-847
+#include "common.cuh"
+#include "qmprs_b200.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------
+// rank selection.  mode 0 = 'rel' (s_j > cutoff*s_0), 1 = 'rsum2' (+ Frobenius renorm).
+// out_rank[0] = n, out_f[0] = renormalisation factor.
+// ---------------------------------------------------------------------------------
+__global__ void k_trim(const double* __restrict__ S, int k, double cutoff, int mode, int max_bond,
+                       int* __restrict__ out_rank, double* __restrict__ out_f) {
+    __shared__ double red[33];
+    const int tid = threadIdx.x;
+    double part = 0.0;
+    for (int i = tid; i < k; i += blockDim.x) part += S[i] * S[i];
+    double tot = block_sum(part, red);
+    if (tid == 0) {
+        int n;
+        if (mode == 0) {
+            double thr = cutoff * S[0];
+            n = 0;
+            for (int i = 0; i < k; i++) n += (S[i] > thr) ? 1 : 0;
+        } else {
+            double target = cutoff * tot, ssum = 0.0;
+            n = k;
+            for (int i = k - 1; i >= 0; i--) {
+                ssum += S[i] * S[i];
+                if (ssum > target) break;
+                n--;
+            }
+        }
+        if (n < 1) n = 1;
+        if (max_bond > 0 && n > max_bond) n = max_bond;
+        double f = 1.0;
+        if (mode == 1 && n < k) {
+            double keep = 0.0;
+            for (int i = 0; i < n; i++) keep += S[i] * S[i];
+            double lose = 0.0;
+            for (int i = n; i < k; i++) lose += S[i] * S[i];
+            f = sqrt((keep + lose) / keep);
+        }
+        out_rank[0] = n;
+        out_f[0] = f;
+    }
+}
+
+// out[r][c] = in[r][c] * w(r or c),  w(j) = (S[j]*f)^power ; mode 0 none, 1 scale rows, 2 scale cols
+__global__ void k_scale_copy(cplx* __restrict__ out, long long ldo, const cplx* __restrict__ in, long long ldi,
+                             int rows, int cols, const double* __restrict__ S, const double* __restrict__ f,
+                             int mode, int half_power) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * cols) return;
+    int r = (int)(idx / cols), c = (int)(idx % cols);
+    cplx v = in[(long long)r * ldi + c];
+    if (mode) {
+        double s = S[mode == 1 ? r : c];
+        if (f) s *= f[0];
+        if (half_power) s = sqrt(s);
+        v = cscale(v, s);
+    }
+    out[(long long)r * ldo + c] = v;
+}
+
+// X viewed as (l, 2, 2, r): theta[(l,oi),(oj,r)] = sum M[(oi,oj),(pi,pj)] X[(l,pi),(pj,r)],
+// M = G (dagger = 0) or G^H (dagger = 1).  In place.
+__global__ void k_theta_gate(cplx* __restrict__ X, int l, int r, const cplx* __restrict__ G, int dagger) {
+    __shared__ cplx M[16];
+    if (threadIdx.x < 16) {
+        int a = threadIdx.x / 4, b = threadIdx.x % 4;
+        M[threadIdx.x] = dagger ? cconj(G[b * 4 + a]) : G[a * 4 + b];
+    }
+    __syncthreads();
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)l * r) return;
+    int li = (int)(idx / r), ri = (int)(idx % r);
+    long long ld = 2LL * r;
+    cplx* base = X + (long long)(2 * li) * ld + ri;
+    cplx x[4];
+    x[0] = base[0];            // pi=0,pj=0
+    x[1] = base[r];            // pi=0,pj=1
+    x[2] = base[ld];           // pi=1,pj=0
+    x[3] = base[ld + r];       // pi=1,pj=1
+    cplx y[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        cplx s = mk(0.0, 0.0);
+#pragma unroll
+        for (int b = 0; b < 4; b++) cfma(s, M[a * 4 + b], x[b]);
+        y[a] = s;
+    }
+    base[0] = y[0]; base[r] = y[1]; base[ld] = y[2]; base[ld + r] = y[3];
+}
+
+// B viewed as (l, 2, r): B[l,o,r] = sum_p M[o,p] B[l,p,r].  In place.
+__global__ void k_site_gate(cplx* __restrict__ B, int l, int r, const cplx* __restrict__ G, int dagger) {
+    cplx M[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int a = i / 2, b = i % 2;
+        M[i] = dagger ? cconj(G[b * 2 + a]) : G[a * 2 + b];
+    }
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)l * r) return;
+    int li = (int)(idx / r), ri = (int)(idx % r);
+    cplx* base = B + (long long)(2 * li) * r + ri;
+    cplx x0 = base[0], x1 = base[r];
+    base[0] = cadd(cmul(M[0], x0), cmul(M[1], x1));
+    base[r] = cadd(cmul(M[2], x0), cmul(M[3], x1));
+}
+
+// ---------------------------------------------------------------------------------
+// chi=2 truncation bookkeeping for one bond (single thread).
+//   S[4], Vh[4][4] (ld) : SVD of the padded (k x 4) matrix R_{i-1} T_i
+//   n = #{ S_j > cutoff*S_0 } capped at 2.  Canonical phase rule: each kept row of Vh is
+//   divided by the phase of its first entry with |x|^2 >= (1-tie)*max|x|^2.
+//   Csite[2][4]  <- kept rows (zero padded);  Vsel[4][2] <- conj-transposed kept rows
+//   (zero padded);  bond[0] <- n.
+// ---------------------------------------------------------------------------------
+__global__ void k_chi2_select(const double* __restrict__ S, const cplx* __restrict__ Vh, long long ldvh,
+                              double cutoff, double tie, cplx* __restrict__ Csite, cplx* __restrict__ Vsel,
+                              int* __restrict__ bond) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n = 0;
+    double thr = cutoff * S[0];
+    for (int j = 0; j < 4; j++) n += (S[j] > thr) ? 1 : 0;
+    if (n < 1) n = 1;
+    if (n > 2) n = 2;
+    for (int j = 0; j < 2; j++) {
+        cplx row[4];
+        for (int c = 0; c < 4; c++) row[c] = (j < n) ? Vh[(long long)j * ldvh + c] : mk(0.0, 0.0);
+        if (j < n) {
+            double mx = 0.0;
+            for (int c = 0; c < 4; c++) { double a = cabs2(row[c]); mx = a > mx ? a : mx; }
+            int pick = 0;
+            for (int c = 0; c < 4; c++) if (cabs2(row[c]) >= (1.0 - tie) * mx) { pick = c; break; }
+            double a = sqrt(cabs2(row[pick]));
+            cplx ph = (a > 0.0) ? mk(row[pick].x / a, row[pick].y / a) : mk(1.0, 0.0);
+            for (int c = 0; c < 4; c++) row[c] = cmulc(row[c], ph);      // row / ph
+        }
+        for (int c = 0; c < 4; c++) {
+            Csite[j * 4 + c] = row[c];
+            Vsel[c * 2 + j] = cconj(row[c]);
+        }
+    }
+    bond[0] = n;
+}
+
+// site 0 of the chi=2 MPS: C0 = T0 / ||T0||  (T0 is 1 x 2 x 2 padded -> 4 entries)
+__global__ void k_chi2_first(const cplx* __restrict__ T0, cplx* __restrict__ Csite) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s = 0.0;
+    for (int c = 0; c < 4; c++) s += cabs2(T0[c]);
+    double inv = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
+    for (int c = 0; c < 4; c++) { Csite[c] = cscale(T0[c], inv); Csite[4 + c] = mk(0.0, 0.0); }
+}
+
+// ---------------------------------------------------------------------------------
+// Isometry completion.  Null space of an m x n matrix (m < n <= 4) by Householder LQ
+// with LAPACK zgelq2/zlarfg conventions and the rounding-robust sign rule of the
+// canonical oracle.  Q (n x n, row-major) accumulates H_0 H_1 ... from the right; its
+// columns m.. span the null space.
+// ---------------------------------------------------------------------------------
+__device__ void null_space_hh(cplx M[2][4], int m, int n, cplx Q[4][4], double sign_tol) {
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) Q[i][j] = mk(i == j ? 1.0 : 0.0, 0.0);
+    for (int i = 0; i < m; i++) {
+        cplx x[4];
+        for (int c = i; c < n; c++) x[c] = cconj(M[i][c]);
+        cplx alpha = x[i];
+        double xn2 = 0.0;
+        for (int c = i + 1; c < n; c++) xn2 += cabs2(x[c]);
+        if (xn2 == 0.0 && alpha.y == 0.0) continue;
+        double nrm = sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xn2);
+        double beta = (alpha.x >= -sign_tol * nrm) ? -nrm : nrm;
+        cplx tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
+        cplx d = mk(alpha.x - beta, alpha.y);
+        double d2 = cabs2(d);
+        cplx dinv = mk(d.x / d2, -d.y / d2);
+        cplx v[4];
+        v[i] = mk(1.0, 0.0);
+        for (int c = i + 1; c < n; c++) v[c] = cmul(x[c], dinv);
+        // rows of M and Q:  row <- row - tau * (row . v) * v^H
+        for (int r = 0; r < m; r++) {
+            cplx dot = mk(0.0, 0.0);
+            for (int c = i; c < n; c++) cfma(dot, M[r][c], v[c]);
+            cplx td = cmul(tau, dot);
+            for (int c = i; c < n; c++) M[r][c] = csub(M[r][c], cmulc(td, v[c]));
+        }
+        for (int r = 0; r < n; r++) {
+            cplx dot = mk(0.0, 0.0);
+            for (int c = i; c < n; c++) cfma(dot, Q[r][c], v[c]);
+            cplx td = cmul(tau, dot);
+            for (int c = i; c < n; c++) Q[r][c] = csub(Q[r][c], cmulc(td, v[c]));
+        }
+    }
+}
+
+// One thread per site.  C: N x 8 (site tensor (l=2,p=2,r=2) zero padded, index l*4+p*2+r),
+// bond: N-1 ints.  gates: N x 16 (2x2 gates use the first 4 entries), kinds: N ints
+// (2 = two-qubit gate on sites (i,i+1), 1 = one-qubit gate on site i), bad: set to 1
+// if any generated matrix fails the unitarity check (mps.py:837-839).
+__global__ void k_complete_unitaries(const cplx* __restrict__ C, const int* __restrict__ bond, int N,
+                                     cplx* __restrict__ gates, int* __restrict__ kinds, int* __restrict__ bad,
+                                     double sign_tol) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const cplx* A = C + (long long)i * 8;
+    int dl = (i == 0) ? 1 : bond[i - 1];
+    int dr = (i == N - 1) ? 1 : bond[i];
+    cplx G[16];
+    for (int k = 0; k < 16; k++) G[k] = mk(0.0, 0.0);
+    int dim;
+    cplx M[2][4], Q[4][4];
+    if (dr < 2) {
+        dim = 2;
+        if (dl < 2) {
+            // isolated site: G = [a ; null(conj a)]^T  -> col 0 = a, col 1 = null vector
+            // padded layout: A[0, p, 0] at index p*2
+            cplx a0 = A[0], a1 = A[2];
+            M[0][0] = cconj(a0); M[0][1] = cconj(a1);
+            null_space_hh(M, 1, 2, Q, sign_tol);
+            G[0] = a0; G[2] = a1;          // G[p][0]
+            G[1] = Q[0][1]; G[3] = Q[1][1];  // G[p][1] = K[p]
+        } else {
+            // last site of a block: G[p][l] = A[l, p, 0]
+            for (int p = 0; p < 2; p++)
+                for (int l = 0; l < 2; l++) G[p * 2 + l] = A[l * 4 + p * 2];
+        }
+    } else {
+        dim = 4;
+        if (dl < 2) {
+            // first site of a block: m = A.reshape(1,4) over (p,r); K = null(conj m) (4x3)
+            for (int c = 0; c < 4; c++) M[0][c] = cconj(A[c]);
+            null_space_hh(M, 1, 4, Q, sign_tol);
+            // G[(p,r), col]: col0 = A, col1 = K_1, col2 = K_0, col3 = K_2   (K_k = Q[:, 1+k])
+            for (int row = 0; row < 4; row++) {
+                G[row * 4 + 0] = A[row];
+                G[row * 4 + 1] = Q[row][2];
+                G[row * 4 + 2] = Q[row][1];
+                G[row * 4 + 3] = Q[row][3];
+            }
+        } else {
+            // interior site: M = A.reshape(2,4) rows l, cols (p,r); K = null(conj M) (4x2),
+            // each column divided by the phase of its first entry (mps.py:661-662)
+            for (int l = 0; l < 2; l++)
+                for (int c = 0; c < 4; c++) M[l][c] = cconj(A[l * 4 + c]);
+            null_space_hh(M, 2, 4, Q, sign_tol);
+            for (int l = 0; l < 2; l++) {
+                cplx k0 = Q[0][2 + l];
+                double a = sqrt(cabs2(k0));
+                // a first entry that is zero up to rounding carries no phase (canonical rule)
+                cplx ph = (a > sign_tol) ? mk(k0.x / a, k0.y / a) : mk(1.0, 0.0);
+                for (int row = 0; row < 4; row++) {
+                    G[row * 4 + 2 * l + 0] = A[l * 4 + row];                 // j = 0: A[l,p,r]
+                    G[row * 4 + 2 * l + 1] = cmulc(Q[row][2 + l], ph);       // j = 1: K[(p,r), l] / phase
+                }
+            }
+        }
+    }
+    // unitarity check  G G^H = I  (atol 1e-8)
+    int isbad = 0;
+    for (int a = 0; a < dim; a++)
+        for (int b = 0; b < dim; b++) {
+            cplx s = mk(0.0, 0.0);
+            for (int k = 0; k < dim; k++) cfmac(s, G[a * dim + k], G[b * dim + k]);
+            double er = s.x - (a == b ? 1.0 : 0.0);
+            if (!(fabs(er) <= 1e-8 && fabs(s.y) <= 1e-8)) isbad = 1;
+        }
+    if (isbad) atomicExch(bad, 1);
+    for (int k = 0; k < 16; k++) gates[(long long)i * 16 + k] = G[k];
+    kinds[i] = (dim == 4) ? 2 : 1;
+}
+
+// ---------------------------------------------------------------------------------
+// vector utilities
+// ---------------------------------------------------------------------------------
+__global__ void k_conj_scale_copy(cplx* __restrict__ out, const cplx* __restrict__ in, long long n, int conj,
+                                  double scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        cplx v = in[i];
+        if (conj) v.y = -v.y;
+        out[i] = cscale(v, scale);
+    }
+}
+
+// out[0] += sum conj(a_i) b_i   (out must be zeroed by the caller); a == b gives the squared norm
+__global__ void k_vdot(const cplx* __restrict__ a, const cplx* __restrict__ b, long long n, double* __restrict__ out) {
+    __shared__ double red[33];
+    cplx acc = mk(0.0, 0.0);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        ccfma(acc, a[i], b[i]);
+    double re = block_sum(acc.x, red);
+    double im = block_sum(acc.y, red);
+    if (threadIdx.x == 0) { atomicAdd(&out[0], re); atomicAdd(&out[1], im); }
+}
+
+// x <- x / sqrt(nrm2[0])
+__global__ void k_div_sqrt(cplx* __restrict__ x, long long n, const double* __restrict__ nrm2) {
+    double s = nrm2[0];
+    double inv = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        x[i] = cscale(x[i], inv);
+}
+
+int grid_for(long long n) {
+    long long g = (n + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+extern "C" int qm_trim(const void* S, int k, double cutoff, int mode, int max_bond, void* out_rank, void* out_f,
+                       void* stream) {
+    k_trim<<<1, 256, 0, (cudaStream_t)stream>>>((const double*)S, k, cutoff, mode, max_bond, (int*)out_rank,
+                                                (double*)out_f);
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_scale_copy(void* out, long long ldo, const void* in, long long ldi, int rows, int cols,
+                             const void* S, const void* f, int mode, int half_power, void* stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    k_scale_copy<<<ceil_div((long long)rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
+        (cplx*)out, ldo, (const cplx*)in, ldi, rows, cols, (const double*)S, (const double*)f, mode, half_power);
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_theta_gate(void* X, int l, int r, const void* G, int dagger, void* stream) {
+    k_theta_gate<<<ceil_div((long long)l * r, 256), 256, 0, (cudaStream_t)stream>>>((cplx*)X, l, r, (const cplx*)G,
+                                                                                   dagger);
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_site_gate(void* B, int l, int r, const void* G, int dagger, void* stream) {
+    k_site_gate<<<ceil_div((long long)l * r, 256), 256, 0, (cudaStream_t)stream>>>((cplx*)B, l, r, (const cplx*)G,
+                                                                                  dagger);
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_chi2_select(const void* S, const void* Vh, long long ldvh, double cutoff, double tie, void* Csite,
+                              void* Vsel, void* bond, void* stream) {
+    k_chi2_select<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)S, (const cplx*)Vh, ldvh, cutoff, tie,
+                                                      (cplx*)Csite, (cplx*)Vsel, (int*)bond);
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_chi2_first(const void* T0, void* Csite, void* stream) {
+    k_chi2_first<<<1, 32, 0, (cudaStream_t)stream>>>((const cplx*)T0, (cplx*)Csite);
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_complete_unitaries(const void* C, const void* bond, int n_sites, void* gates, void* kinds,
+                                     void* bad, double sign_tol, void* stream) {
+    k_complete_unitaries<<<ceil_div(n_sites, 64), 64, 0, (cudaStream_t)stream>>>(
+        (const cplx*)C, (const int*)bond, n_sites, (cplx*)gates, (int*)kinds, (int*)bad, sign_tol);
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_conj_scale_copy(void* out, const void* in, long long n, int conj, double scale, void* stream) {
+    if (n <= 0) return 0;
+    k_conj_scale_copy<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((cplx*)out, (const cplx*)in, n, conj, scale);
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_vdot(const void* a, const void* b, long long n, void* out2, void* stream) {
+    QM_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), (cudaStream_t)stream));
+    k_vdot<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const cplx*)a, (const cplx*)b, n, (double*)out2);
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_div_sqrt(void* x, long long n, const void* nrm2, void* stream) {
+    k_div_sqrt<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((cplx*)x, n, (const double*)nrm2);
+    QM_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,319 @@
+"""Host orchestration of the MPS hot path on top of the C-ABI kernels.
+
+Every function mirrors one row of SURVEY.md section 8(a) and cites the reference lines
+it replaces (paths relative to the reference repo).  An MPS is a python list of N
+device tensors ``A[i]`` of shape (l, 2, r) (quimb's 'lpr' layout, edge bonds of size 1);
+site 0 is the most significant bit of the dense index.
+
+``K`` is the kernel handle (:class:`qmprs_b200.kernels.CudaKernels`).  All arithmetic is
+done by its kernels; this module only sequences launches, reshapes views and reads the
+few scalars that decide shapes (ranks, block structure, the early-break overlap).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .kernels import CUTOFF, MODE_REL, MODE_RSUM2
+
+
+# --------------------------------------------------------------------------------------
+# A1  statevector -> exact MPS        qmprs/primitives/mps.py:242 (quimb from_dense)
+# --------------------------------------------------------------------------------------
+def from_dense(K, psi, n_sites, spectra=None):
+    """Right-to-left TT-SVD, cutoff 1e-10 'rsum2', sqrt(s) absorbed on both sides."""
+    N = int(n_sites)
+    A = [None] * N
+    T = psi.reshape(-1, 1)
+    r = 1
+    for i in range(N - 1, 0, -1):
+        M = T.reshape(2 ** i, 2 * r)
+        U, S, Vh = K.svd(M)
+        k = S.shape[0]
+        if spectra is not None:
+            spectra.append(S)
+        rank, f = K.trim(S, k, CUTOFF, MODE_RSUM2)
+        n = K.read_int(rank)
+        A[i] = K.scale_copy(Vh[:n], S, f, mode=1, half_power=True).reshape(n, 2, r)
+        T = K.scale_copy(U[:, :n], S, f, mode=2, half_power=True)
+        r = n
+    A[0] = T.reshape(1, 2, r)
+    return A
+
+
+def to_dense(K, A):
+    """Full contraction to a 2^N vector (mps.py:270)."""
+    x = A[0].reshape(-1, A[0].shape[2])
+    for i in range(1, len(A)):
+        l, _, r = A[i].shape
+        x = K.gemm(x, A[i].reshape(l, 2 * r)).reshape(-1, r)
+    return x.reshape(-1)
+
+
+def bond_dims(A):
+    return [int(a.shape[2]) for a in A[:-1]]
+
+
+def copy_mps(K, A):
+    return [K.scale_copy(a.reshape(a.shape[0] * 2, a.shape[2])).reshape(a.shape) for a in A]
+
+
+# --------------------------------------------------------------------------------------
+# A2/A3  canonical forms and truncation   mps.py:247, :396-398, :451-453
+# --------------------------------------------------------------------------------------
+def left_canon(K, A):
+    """QR sweep left->right with non-negative diag(R) (quimb left_canonize)."""
+    A = list(A)
+    for i in range(len(A) - 1):
+        l, _, r = A[i].shape
+        Q, R = K.qr(A[i].reshape(l * 2, r))
+        k = Q.shape[1]
+        A[i] = Q.reshape(l, 2, k)
+        r2 = A[i + 1].shape[2]
+        A[i + 1] = K.gemm(R, A[i + 1].reshape(r, 2 * r2)).reshape(k, 2, r2)
+    return A
+
+
+def right_compress(K, A, max_bond=None, spectra=None):
+    """Right->left truncation sweep on a LEFT-canonical MPS: SVD of each site matrix,
+    cutoff 1e-10 'rel' (+ max_bond), singular values absorbed to the left, no renorm
+    (quimb right_compress / tensor_compress_bond; the QR/LQ reduction of the reference
+    is an identity on a left-canonical input)."""
+    A = list(A)
+    for i in range(len(A) - 1, 0, -1):
+        b, _, r = A[i].shape
+        l0 = A[i - 1].shape[0]
+        U, S, Vh = K.svd(A[i].reshape(b, 2 * r))
+        k = S.shape[0]
+        if spectra is not None:
+            spectra.append(S)
+        rank, _ = K.trim(S, k, CUTOFF, MODE_REL, max_bond or 0)
+        n = K.read_int(rank)
+        US = K.scale_copy(U[:, :n], S, None, mode=2, half_power=False)
+        A[i] = K.scale_copy(Vh[:n]).reshape(n, 2, r)
+        A[i - 1] = K.gemm(A[i - 1].reshape(l0 * 2, b), US).reshape(l0, 2, n)
+    return A
+
+
+def canonicalize_truncate(K, A, max_bond=None, spectra=None):
+    """``tensor_network_1d_compress(max_bond)`` (mps.py:247) and ``compress(form='right')``
+    (mps.py:451/453): right-canonical MPS with the norm on site 0."""
+    return right_compress(K, left_canon(K, A), max_bond, spectra)
+
+
+def normalize_site0(K, A):
+    """``right_canonize(normalize=True)`` on an already right-canonical MPS (mps.py:398)."""
+    a0 = A[0]
+    K.div_sqrt(a0, K.vdot(a0, a0))
+    return A
+
+
+# --------------------------------------------------------------------------------------
+# A4 + A5  chi=2 truncation and unitary completion   mps.py:849-891, :565-847
+# --------------------------------------------------------------------------------------
+def chi2_layer(K, B, debug=None):
+    """Returns (gates [N,16] device, kinds list[int] host).  ``B`` is not modified
+    (the reference works on a deepcopy, mps.py:878).
+
+    The reference left-canonises the copy and then truncates bond by bond from the right
+    (QR, LQ, SVD of R.L keeping <= 2 values).  Here only the R factors of the left
+    sweep are formed (R_i with  B_0..B_i = Q R_i), and every truncation step is the SVD
+    of the (k x 4) matrix R_{i-1} T_i, T_i being site i contracted with the already
+    truncated right part; bonds are zero-padded to 2 so that all shapes are static and
+    the bond dimensions stay on the device until the block structure is read back.
+    """
+    N = len(B)
+    # left sweep, R factors only
+    Rs = [None] * (N - 1)
+    Rprev = None
+    for i in range(N - 1):
+        l, _, r = B[i].shape
+        if Rprev is None:
+            M = B[i].reshape(l * 2, r)
+        else:
+            M = K.gemm(Rprev, B[i].reshape(l, 2 * r)).reshape(-1, r)
+        _, Rprev = K.qr(M, want_q=False)
+        Rs[i] = Rprev
+    # right->left truncation with padded bond 2
+    C = K.zeros((N, 8))
+    bond = K.zeros((max(N - 1, 1),), dtype=_i32(K))
+    b_last = B[N - 1].shape[0]
+    T = K.zeros((b_last, 4))
+    K.scale_copy(B[N - 1].reshape(b_last * 2, 1), out=T.reshape(b_last * 2, 2)[:, 0:1])
+    S4 = K.zeros((4,), dtype=_f64(K))
+    Vh4 = K.zeros((4, 4))
+    Vsel = K.zeros((4, 2))
+    for i in range(N - 1, 0, -1):
+        M = K.gemm(Rs[i - 1], T)                       # (k x 4)
+        if M.shape[0] < 4:
+            S4.zero_()
+            Vh4.zero_()
+        K.svd(M, want_u=False, out_s=S4, out_vh=Vh4)
+        K.chi2_select(S4, Vh4, C[i], Vsel, bond[i - 1:i])
+        W = K.gemm(T, Vsel)                            # (b x 2)
+        l0, _, b = B[i - 1].shape
+        T = K.gemm(B[i - 1].reshape(l0 * 2, b), W).reshape(l0, 4)
+    K.chi2_first(T, C[0])
+    gates, kinds, bad = K.complete_unitaries(C, bond, N)
+    kinds_h = [int(x) for x in K.to_host(kinds)]
+    if K.read_int(bad):
+        raise ValueError("All the generated unitaries must be unitary.")     # mps.py:838-839
+    if debug is not None:
+        debug["C"] = C
+        debug["bond"] = bond
+    return gates, kinds_h
+
+
+def _i32(K):
+    import torch
+    return torch.int32
+
+
+def _f64(K):
+    import torch
+    return torch.float64
+
+
+def blocks_from_kinds(kinds):
+    """[(start, end)] : a block ends at the site carrying the one-qubit gate."""
+    out = []
+    s = 0
+    for i, k in enumerate(kinds):
+        if k == 1:
+            out.append((s, i))
+            s = i + 1
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# A6  inverse layer application       mps.py:933-971 (quimb gate_ / gate_split_)
+# --------------------------------------------------------------------------------------
+def apply_inverse_layer(K, B, gates, kinds, spectra=None):
+    """In place on the list ``B``.  theta = G^H (A_i A_{i+1}); SVD, cutoff 1e-10 'rsum2'
+    with Frobenius renorm, sqrt(s) to both sides, no max_bond."""
+    for s, e in blocks_from_kinds(kinds):
+        for i in range(e, s - 1, -1):
+            G = gates[i]
+            if i == e:
+                l, _, r = B[i].shape
+                K.site_gate(B[i], l, r, G, dagger=True)
+            else:
+                l, _, b = B[i].shape
+                _, _, r = B[i + 1].shape
+                X = K.gemm(B[i].reshape(l * 2, b), B[i + 1].reshape(b, 2 * r))
+                K.theta_gate(X, l, r, G, dagger=True)
+                U, S, Vh = K.svd(X)
+                k = S.shape[0]
+                if spectra is not None:
+                    spectra.append(S)
+                rank, f = K.trim(S, k, CUTOFF, MODE_RSUM2)
+                n = K.read_int(rank)
+                B[i] = K.scale_copy(U[:, :n], S, f, mode=2, half_power=True).reshape(l, 2, n)
+                B[i + 1] = K.scale_copy(Vh[:n], S, f, mode=1, half_power=True).reshape(n, 2, r)
+    return B
+
+
+# --------------------------------------------------------------------------------------
+# A7  overlap with |0..0>             mps.py:1020-1039
+# --------------------------------------------------------------------------------------
+def zero_overlap(K, B):
+    """conj(psi[0]) as a product of the p=0 slices (only element 0 of the dense vector is used)."""
+    v = B[0][:, 0, :]
+    for i in range(1, len(B)):
+        v = K.gemm(v, B[i][:, 0, :])
+    z = K.to_host(v).reshape(-1)[0]
+    return complex(np.conj(z))
+
+
+# --------------------------------------------------------------------------------------
+# A8/A9  dense optimisation sweeps    sequential.py:400-541
+# --------------------------------------------------------------------------------------
+def flat_schedule(kinds_per_layer, n_sites):
+    sites, kinds = [], []
+    for kl in kinds_per_layer:
+        sites.extend(range(n_sites))
+        kinds.extend(kl)
+    return sites, kinds
+
+
+def optimize_layers(K, target, gates_all, kinds_per_layer, n_sites, num_sweeps, envs=None):
+    """``_optimize_unitary_layers``: per sweep rebuild the dense circuit state from the
+    current gates (sequential.py:533, 443-447; the reference's full-rank re-compression
+    of that state into an MPS is an identity and is skipped) and run one environment
+    sweep (sequential.py:452-505).  ``gates_all``: [L*N, 16] in application order."""
+    sites, kinds = flat_schedule(kinds_per_layer, n_sites)
+    c = None
+    for _ in range(num_sweeps):
+        c = K.circuit_state(n_sites, gates_all, sites, kinds, out=c)
+        tbar = K.conj_scale_copy(target, conj=True)
+        K.sweep(c, tbar, n_sites, gates_all, sites, kinds, envs)
+    return gates_all
+
+
+# --------------------------------------------------------------------------------------
+# A0  top level                       base.py:96-104, sequential.py:330-398, 543-600
+# --------------------------------------------------------------------------------------
+def build_mps(K, psi, n_sites, chi, record=None):
+    """``MPS.from_statevector`` (mps.py:218-249).  Returns the chi-truncated
+    right-canonical MPS (norm on site 0, not renormalised)."""
+    rec = record if record is not None else {}
+    A = from_dense(K, psi, n_sites, rec.setdefault("tt_svd", []))
+    return canonicalize_truncate(K, A, chi, rec.setdefault("truncate", []))
+
+
+def disentangle(K, A, num_layers, threshold, record=None):
+    """``_get_unitary_layers`` (sequential.py:330-398).  Returns (gates_all [L*N,16] in
+    application order, kinds_per_layer, overlaps)."""
+    import torch
+    rec = record if record is not None else {}
+    N = len(A)
+    # sequential.py:360-376: copy, normalize, compress(mode="right"), permute, canonicalize.
+    # On the right-canonical Schmidt-gauge MPS built above this is the same tensors with
+    # site 0 normalised (the gauge is unique up to bond phases).
+    B = copy_mps(K, A)
+    normalize_site0(K, B)
+    layer_gates, layer_kinds, overlaps = [], [], []
+    for _ in range(num_layers):
+        gates, kinds = chi2_layer(K, B)                               # mps.py:849-891
+        sp = []
+        apply_inverse_layer(K, B, gates, kinds, sp)                   # sequential.py:326
+        rec.setdefault("gate_split", []).append(sp)
+        layer_gates.append(gates)
+        layer_kinds.append(kinds)
+        f = zero_overlap(K, B)
+        overlaps.append(f)
+        if np.isclose(f, 1 + 0j, atol=1 - threshold):                 # sequential.py:390
+            break
+    layer_gates.reverse()                                             # sequential.py:396
+    layer_kinds.reverse()
+    gates_all = torch.cat(layer_gates, dim=0).contiguous()
+    return gates_all, layer_kinds, overlaps
+
+
+def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 - 1e-6, record=None,
+            mps=None):
+    """Whole path on the device.  ``psi_host``: normalised complex128 numpy vector.
+    Returns dict(gates [L,N,16] numpy, kinds [L][N], n_layers, overlaps, fidelity)."""
+    N = int(n_sites)
+    psi = K.from_host(np.asarray(psi_host, dtype=np.complex128).reshape(-1))
+    if mps is None:
+        K.div_sqrt(psi, K.vdot(psi, psi))                             # quick Ket normalisation
+        A = build_mps(K, psi, N, chi, record)
+    else:
+        A = mps
+    gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record)
+    if num_sweeps > 0:
+        target = to_dense(K, A)                                       # sequential.py:440 (mps.mps)
+        optimize_layers(K, target, gates_all, layer_kinds, N, num_sweeps)
+    sites, kinds = flat_schedule(layer_kinds, N)
+    c = K.circuit_state(N, gates_all, sites, kinds)
+    ov = K.to_host(K.vdot(psi, c))
+    L = len(layer_kinds)
+    return {
+        "gates": K.to_host(gates_all).reshape(L, N, 16),
+        "kinds": layer_kinds,
+        "n_layers": L,
+        "overlaps": overlaps,
+        "fidelity": float(np.hypot(ov[0], ov[1])),
+        "n_sites": N,
+        "mps": A,
+    }

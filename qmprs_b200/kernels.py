@@ -1,0 +1,208 @@
+"""Thin Python binding of the C ABI (include/qmprs_b200.h) on torch CUDA tensors.
+
+PyTorch is used for device memory and streams only; every arithmetic step is one of
+the hand-written sm_100a kernels in ``csrc/``.  There is no CPU path: constructing
+:class:`CudaKernels` without CUDA or without the built library raises.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+C128 = torch.complex128
+F64 = torch.float64
+I32 = torch.int32
+
+CUTOFF = 1e-10
+TIE_REL = 1e-6
+SIGN_TOL = 1e-12
+MODE_REL, MODE_RSUM2 = 0, 1
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class CudaKernels:
+    """One instance per device.  Methods take/return torch tensors on that device."""
+
+    def __init__(self, device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("qmprs_b200 requires a CUDA device (B200, sm_100a); there is no CPU fallback.")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self._svd_work = None
+        self._sweep_work = None
+        self.launches = 0          # C-ABI calls issued (each launches >= 1 kernel)
+        self.svd_sweeps = 0
+        self.svd_tol = 1e-14
+        self.svd_max_sweeps = 30
+
+    # ---- memory / plumbing --------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, shape, dtype=C128):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype=C128):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def from_host(self, arr, dtype=C128):
+        return torch.as_tensor(np.ascontiguousarray(arr)).to(dtype).to(self.device)
+
+    def to_host(self, t):
+        return t.detach().cpu().numpy()
+
+    def read_int(self, t):
+        return int(t.item())
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.device)
+
+    def _check(self, code, name):
+        self.launches += 1
+        if code != 0:
+            raise RuntimeError(f"{name} failed with status {code}")
+
+    @staticmethod
+    def _ld(t):
+        assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), "matrix views must have unit column stride"
+        return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+    # ---- dense linear algebra -----------------------------------------------------
+    def gemm(self, A, B, out=None):
+        m, k = A.shape
+        k2, n = B.shape
+        assert k == k2
+        if out is None:
+            out = self.empty((m, n))
+        self._check(self.lib.qm_zgemm(m, n, k, 1.0, 0.0, _p(A), self._ld(A), _p(B), self._ld(B), 0.0, 0.0,
+                                      _p(out), self._ld(out), 1, 0, 0, 0, self._stream()), "qm_zgemm")
+        return out
+
+    def svd(self, A, want_u=True, want_vh=True, out_s=None, out_vh=None):
+        m, n = A.shape
+        k = min(m, n)
+        need = int(self.lib.qm_svd_work_bytes(m, n))
+        if self._svd_work is None or self._svd_work.numel() < need:
+            self._svd_work = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=self.device)
+        U = self.empty((m, k)) if want_u else None
+        S = out_s if out_s is not None else self.empty((k,), F64)
+        Vh = out_vh if out_vh is not None else (self.empty((k, n)) if want_vh else None)
+        info = (ctypes.c_int * 2)()
+        self._check(self.lib.qm_svd(m, n, _p(A), self._ld(A), _p(U), k, _p(S), _p(Vh),
+                                    (self._ld(Vh) if Vh is not None else n), _p(self._svd_work),
+                                    self._svd_work.numel(), self.svd_tol, self.svd_max_sweeps, info,
+                                    self._stream()), "qm_svd")
+        self.svd_sweeps += info[0]
+        return U, S, Vh
+
+    def qr(self, A, want_q=True):
+        """Reduced QR with non-negative diag(R).  Returns (Q or None, R)."""
+        m, n = A.shape
+        k = min(m, n)
+        F = self.empty((m, n))
+        self._check(self.lib.qm_scale_copy(_p(F), n, _p(A), self._ld(A), m, n, None, None, 0, 0, self._stream()),
+                    "qm_scale_copy")
+        tau = self.empty((k,))
+        self._check(self.lib.qm_qr(m, n, _p(F), n, _p(tau), self._stream()), "qm_qr")
+        Q = None
+        if want_q:
+            Q = self.empty((m, k))
+            self._check(self.lib.qm_qr_formq(m, k, _p(F), n, _p(tau), _p(Q), k, self._stream()), "qm_qr_formq")
+        R = self.empty((k, n))
+        self._check(self.lib.qm_qr_finish(m, n, _p(F), n, _p(R), n, _p(Q), k, self._stream()), "qm_qr_finish")
+        return Q, R
+
+    # ---- MPS bookkeeping ----------------------------------------------------------
+    def trim(self, S, k, cutoff, mode, max_bond=0):
+        rank = self.empty((1,), I32)
+        f = self.empty((1,), F64)
+        self._check(self.lib.qm_trim(_p(S), k, cutoff, mode, int(max_bond or 0), _p(rank), _p(f), self._stream()),
+                    "qm_trim")
+        return rank, f
+
+    def scale_copy(self, inp, S=None, f=None, mode=0, half_power=False, out=None):
+        rows, cols = inp.shape
+        if out is None:
+            out = self.empty((rows, cols))
+        self._check(self.lib.qm_scale_copy(_p(out), self._ld(out), _p(inp), self._ld(inp), rows, cols, _p(S), _p(f),
+                                           mode, 1 if half_power else 0, self._stream()), "qm_scale_copy")
+        return out
+
+    def theta_gate(self, X, l, r, G, dagger):
+        self._check(self.lib.qm_theta_gate(_p(X), l, r, _p(G), 1 if dagger else 0, self._stream()), "qm_theta_gate")
+
+    def site_gate(self, B, l, r, G, dagger):
+        self._check(self.lib.qm_site_gate(_p(B), l, r, _p(G), 1 if dagger else 0, self._stream()), "qm_site_gate")
+
+    def chi2_select(self, S4, Vh4, Csite, Vsel, bond_slot):
+        self._check(self.lib.qm_chi2_select(_p(S4), _p(Vh4), 4, CUTOFF, TIE_REL, _p(Csite), _p(Vsel), _p(bond_slot),
+                                            self._stream()), "qm_chi2_select")
+
+    def chi2_first(self, T0, Csite):
+        self._check(self.lib.qm_chi2_first(_p(T0), _p(Csite), self._stream()), "qm_chi2_first")
+
+    def complete_unitaries(self, C, bond, n_sites):
+        gates = self.empty((n_sites, 16))
+        kinds = self.empty((n_sites,), I32)
+        bad = self.zeros((1,), I32)
+        self._check(self.lib.qm_complete_unitaries(_p(C), _p(bond), n_sites, _p(gates), _p(kinds), _p(bad), SIGN_TOL,
+                                                   self._stream()), "qm_complete_unitaries")
+        return gates, kinds, bad
+
+    # ---- vectors --------------------------------------------------------------------
+    def conj_scale_copy(self, inp, conj=False, scale=1.0):
+        out = self.empty(inp.shape)
+        self._check(self.lib.qm_conj_scale_copy(_p(out), _p(inp), inp.numel(), 1 if conj else 0, float(scale),
+                                                self._stream()), "qm_conj_scale_copy")
+        return out
+
+    def vdot(self, a, b):
+        out = self.empty((2,), F64)
+        self._check(self.lib.qm_vdot(_p(a), _p(b), a.numel(), _p(out), self._stream()), "qm_vdot")
+        return out
+
+    def div_sqrt(self, x, nrm2):
+        self._check(self.lib.qm_div_sqrt(_p(x), x.numel(), _p(nrm2), self._stream()), "qm_div_sqrt")
+
+    # ---- dense statevector path -----------------------------------------------------
+    def apply_gate(self, x, n_sites, site, kind, G, op=0):
+        self._check(self.lib.qm_apply_gate(_p(x), n_sites, site, kind, _p(G), op, self._stream()), "qm_apply_gate")
+
+    @staticmethod
+    def _int_array(v):
+        arr = (ctypes.c_int * len(v))(*[int(x) for x in v])
+        return arr
+
+    def circuit_state(self, n_sites, gates, sites, kinds, out=None):
+        c = out if out is not None else self.empty((1 << n_sites,))
+        self._check(self.lib.qm_circuit_state(_p(c), n_sites, _p(gates), self._int_array(sites),
+                                              self._int_array(kinds), len(sites), self._stream()), "qm_circuit_state")
+        self.launches += len(sites)
+        return c
+
+    def sweep(self, c, tbar, n_sites, gates, sites, kinds, envs=None):
+        if self._sweep_work is None:
+            self._sweep_work = torch.empty(int(self.lib.qm_sweep_work_bytes()), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.qm_sweep(_p(c), _p(tbar), n_sites, _p(gates), self._int_array(sites),
+                                      self._int_array(kinds), len(sites), _p(self._sweep_work), _p(envs),
+                                      self._stream()), "qm_sweep")
+        self.launches += 3 * len(sites)
+
+
+_instances = {}
+
+
+def get_kernels(device="cuda:0"):
+    """Process-wide kernel handle for ``device`` (fails loudly without CUDA / the .so)."""
+    key = str(device)
+    if key not in _instances:
+        _instances[key] = CudaKernels(device)
+    return _instances[key]
