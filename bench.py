@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the qmprs MPS hot path on B200:  Sequential.prepare_state at the
+BASELINE.json headline configuration (20 qubits, chi=512, 15 layers, 50 sweeps).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1]
+
+A "step" is one prepare_state of a fresh synthetic random state (reference distribution,
+README.md:52-53).  Prints ONE JSON line (see the task contract): `value` = whole-job
+states/s with the input resident in HBM, `e2e` = the same through the public
+Sequential.prepare_state call with host buffers, `roofline` for the dominant kernel
+(timed live with CUDA events in one extra instrumented step), `cpu_baseline` = the numpy
+oracle on the host cores on a bounded sample.  `--impl reference` times the CPU path only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c1": dict(n=10, chi=512, layers=15, sweeps=50, name="10q chi=512(32) 15 layers 50 sweeps (README)"),
+    "c2": dict(n=16, chi=256, layers=15, sweeps=50, name="16q chi=256 15 layers 50 sweeps"),
+    "c3": dict(n=20, chi=512, layers=15, sweeps=50, name="20q chi=512 15 layers 50 sweeps (headline)"),
+}
+METRIC = "prepare_state_throughput"
+UNIT = "states/s"
+
+
+def rand_state(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.random(2 ** n) + 1j * rng.random(2 ** n)
+    return v / np.linalg.norm(v)
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores, bounded sample extrapolated to the full workload
+# ----------------------------------------------------------------------------------------
+def cpu_sample(wl, seed, setup=None):
+    """Times one disentangling layer and one layer's worth (N gates) of sweep gate-steps of
+    the verbatim oracle on the real workload shapes; the MPS build is timed once in
+    ``setup``.  Returns (seconds per state extrapolated, breakdown, setup)."""
+    from oracle import qmprs_oracle as O
+    n, chi, L, S = wl["n"], wl["chi"], wl["layers"], wl["sweeps"]
+    if setup is None:
+        psi = rand_state(n, seed)
+        t0 = time.perf_counter()
+        A = O.compress_right(O.from_dense(psi, n), max_bond=chi)
+        target = O.to_dense(A)
+        B = [a.copy() for a in A]
+        nrm = O.mps_norm(B)
+        if not np.isclose(nrm, 1.0):
+            B[-1] = B[-1] / nrm
+        B = O.right_canon(O.compress_right(B), normalize=True)
+        t_mps = time.perf_counter() - t0
+        setup = dict(B=B, target=target, t_mps=t_mps)
+    B = [b.copy() for b in setup["B"]]
+    t0 = time.perf_counter()
+    C = O.chi2_truncate(B, "verbatim")
+    layer = O.generate_unitary_layer(C, "verbatim")
+    O.apply_inverse_layer(B, layer)
+    O.zero_overlap(B)
+    t_layer = time.perf_counter() - t0
+    setup["B"] = B                      # next sample continues from the disentangled MPS
+    layers = [layer]
+    t0 = time.perf_counter()
+    O.sweep(setup["target"], layers, n)   # builds the 1-layer circuit state + N gate-steps
+    t_sweep_layer = time.perf_counter() - t0
+    total = setup["t_mps"] + L * t_layer + S * L * t_sweep_layer
+    return total, dict(t_mps=setup["t_mps"], t_layer=t_layer, t_sweep_layer=t_sweep_layer), setup
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    setup = None
+    totals = []
+    for i in range(args.warmup + args.steps):
+        tot, br, setup = cpu_sample(wl, 1000 + i, setup)
+        if i >= args.warmup:
+            totals.append(tot)
+    sec = float(np.mean(totals))
+    val = 1.0 / sec
+    sample = ("per step: 1 disentangling layer + 1 layer of sweep gate-steps of the numpy oracle at full size; "
+              "MPS build timed once; extrapolated t_mps + L*t_layer + S*L*t_sweep_layer "
+              f"(last: {br['t_mps']:.2f}s, {br['t_layer']:.2f}s, {br['t_sweep_layer']:.2f}s); "
+              "the reference's per-sweep from_dense (sequential.py:443) is not charged")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": {"workload": wl["name"], "n_qubits": wl["n"], "chi": wl["chi"], "layers": wl["layers"],
+                   "sweeps": wl["sweeps"]},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measure_fp64_peak(torch, dev):
+    """cuBLAS ZGEMM 4096^3 burst (8*n^3 real flops), best of 5: the FP64 roofline denominator."""
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.complex128, device=dev)
+    b = torch.randn(n, n, dtype=torch.complex128, device=dev)
+    torch.matmul(a, b)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 8.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from qmprs_b200 import GateListCircuit, host
+    from qmprs_b200.kernels import get_kernels
+    from qmprs.synthesis.mps_encoding import Sequential
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    K = get_kernels(str(dev))
+    n, chi, L, S = wl["n"], wl["chi"], wl["layers"], wl["sweeps"]
+    W, Ksteps = args.warmup, args.steps
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    states = [rand_state(n, rank * 100003 + i) for i in range(W + Ksteps)]
+    dev_states = [K.from_host(s) for s in states]
+
+    # ---- device-resident value ----
+    fid = []
+    for i in range(W):
+        flush.fill_(i)
+        fid.append(host.prepare(K, dev_states[i], n, chi, L, S)["fidelity"])
+    clocks = ClockSampler(local)
+    sync_all()
+    clocks.start()
+    l0 = K.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + Ksteps):
+        flush.fill_(i)
+        fid.append(host.prepare(K, dev_states[i], n, chi, L, S)["fidelity"])
+    e1.record()
+    sync_all()
+    launches = K.launch_count() - l0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop()
+    value = world * Ksteps / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers ----
+    enc = Sequential(GateListCircuit)
+    pinned = [torch.from_numpy(s).pin_memory().numpy() for s in states[W:]]
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    d2h = 0
+    for p in pinned:
+        flush.fill_(1)
+        circ = enc.prepare_state(p, chi, num_layers=L, num_sweeps=S)
+        d2h = sum(m.nbytes for m, _ in circ.gates)
+    e1.record()
+    sync_all()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e = world * Ksteps / (ms_e2e * 1e-3)
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel: one extra instrumented step (CUDA events per launch) ----
+        peak_tf = measure_fp64_peak(torch, dev)
+        K.prof_begin()
+        host.prepare(K, dev_states[-1], n, chi, L, S)
+        prof = K.prof_end()
+        tot_ms = sum(v[0] for v in prof.values())
+        dom = max(prof, key=lambda k: prof[k][0])
+        d_ms, d_cnt, d_work = prof[dom]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        if dom in ("gate", "env_polar"):
+            hbm = peaks.get("hbm_gbs", 6650.0)
+            ach = d_work / (d_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}
+        else:
+            ach = d_work / (d_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    "traffic": None,
+                    "peak_source": "FP64: cuBLAS ZGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)"}
+        roof.update({"kernel": dom, "launches": d_cnt, "avg_launch_us": 1e3 * d_ms / max(d_cnt, 1),
+                     "share_of_kernel_time": d_ms / tot_ms,
+                     "classes": {k: {"ms": round(v[0], 3), "launches": v[1], "work": v[2]} for k, v in prof.items()}})
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            tot, br, _ = cpu_sample(wl, 4242)
+            cpu = {"value": 1.0 / tot, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                   "sample": ("numpy oracle at full size: MPS build + 1 disentangling layer + 1 layer of sweep gate-steps, "
+                              f"extrapolated t_mps + L*t_layer + S*L*t_sweep_layer = {br['t_mps']:.2f} + {L}*{br['t_layer']:.2f}"
+                              f" + {S}*{L}*{br['t_sweep_layer']:.2f} s")}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Ksteps, "warmup": W,
+            "ms_per_step": ms / Ksteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "c128", "data": "synthetic",
+            "config": {"workload": wl["name"], "n_qubits": n, "chi": chi, "layers": L, "sweeps": S,
+                       "states_per_step_per_gpu": 1, "l2": "256 MiB buffer rewritten between steps",
+                       "parallelism": f"{world} independent states (one per GPU), no data-path collective"},
+            "s_per_state": ms * 1e-3 / Ksteps,
+            "fidelity_mean": float(np.mean(fid[W:])),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(16 * 2 ** n), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -77,6 +77,10 @@ int qm_chi2_first(const void* T0, void* Csite, void* stream);
 int qm_complete_unitaries(const void* C, const void* bond, int n_sites, void* gates, void* kinds, void* bad,
                           double sign_tol, void* stream);
 
+/* out (r,2,l) = in (l,2,r) with the bond axes swapped: mirror image of a site tensor, used
+ * for the left-handed canonicalize/compress variants (mps.py:396, :451-453 with mode="left"). */
+int qm_reverse3(void* out, const void* in, int l, int r, void* stream);
+
 /* ---- vectors ------------------------------------------------------------------- */
 int qm_conj_scale_copy(void* out, const void* in, long long n, int conj, double scale, void* stream);
 int qm_vdot(const void* a, const void* b, long long n, void* out2 /* double[2] */, void* stream);
@@ -101,6 +105,19 @@ int qm_sweep(void* c, void* tbar, int n_sites, void* gates, const int* sites, co
 
 /* Library identification: returns the compiled architecture number (100 for sm_100a). */
 int qm_version(void);
+
+/* Kernel launches issued by this library since load (every launch is counted). */
+long long qm_launch_count(void);
+
+/* Optional per-kernel-class CUDA-event profiler (bench.py roofline leg): between begin
+ * and end every launch is bracketed by events on its stream.  total_ms / count: host
+ * arrays of qm_prof_num_classes() entries. */
+int qm_prof_num_classes(void);
+const char* qm_prof_class_name(int cls);
+int qm_prof_begin(void);
+int qm_prof_end(double* total_ms, long long* count);
+/* algorithmic work per class since qm_prof_begin: flops (zgemm, svd_*, qr_apply) or bytes (gate, env_polar) */
+int qm_prof_work_get(double* work);
 
 #ifdef __cplusplus
 }

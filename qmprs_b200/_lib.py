@@ -32,6 +32,7 @@ SIGNATURES = {
     "qm_chi2_select": (_i, [_vp, _vp, _ll, _d, _d, _vp, _vp, _vp, _vp]),
     "qm_chi2_first": (_i, [_vp, _vp, _vp]),
     "qm_complete_unitaries": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _vp]),
+    "qm_reverse3": (_i, [_vp, _vp, _i, _i, _vp]),
     "qm_conj_scale_copy": (_i, [_vp, _vp, _ll, _i, _d, _vp]),
     "qm_vdot": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "qm_div_sqrt": (_i, [_vp, _ll, _vp, _vp]),
@@ -40,6 +41,12 @@ SIGNATURES = {
     "qm_sweep_work_bytes": (_ll, []),
     "qm_sweep": (_i, [_vp, _vp, _i, _vp, _ip, _ip, _i, _vp, _vp, _vp]),
     "qm_version": (_i, []),
+    "qm_launch_count": (_ll, []),
+    "qm_prof_num_classes": (_i, []),
+    "qm_prof_class_name": (ctypes.c_char_p, [_i]),
+    "qm_prof_begin": (_i, []),
+    "qm_prof_end": (_i, [ctypes.POINTER(_d), ctypes.POINTER(_ll)]),
+    "qm_prof_work_get": (_i, [ctypes.POINTER(_d)]),
 }
 
 _lib = None

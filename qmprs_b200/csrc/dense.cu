@@ -255,12 +255,13 @@ int grid_groups(long long ngroups) {
 }
 
 int launch_gate(cplx* x, int nbits, int site, int kind, const cplx* G, int op, cudaStream_t st) {
+    qm_prof_work(QM_CLS_GATE, 32.0 * (double)(1LL << nbits));      // read + write every amplitude
     if (kind == 2) {
         int q = nbits - 2 - site;
-        k_gate2<<<grid_groups(1LL << (nbits - 2)), NT, 0, st>>>(x, nbits, q, G, op);
+        QM_LAUNCH(QM_CLS_GATE, st, k_gate2<<<grid_groups(1LL << (nbits - 2)), NT, 0, st>>>(x, nbits, q, G, op));
     } else {
         int q = nbits - 1 - site;
-        k_gate1<<<grid_groups(1LL << (nbits - 1)), NT, 0, st>>>(x, nbits, q, G, op);
+        QM_LAUNCH(QM_CLS_GATE, st, k_gate1<<<grid_groups(1LL << (nbits - 1)), NT, 0, st>>>(x, nbits, q, G, op));
     }
     return (int)cudaGetLastError();
 }
@@ -277,7 +278,7 @@ extern "C" int qm_circuit_state(void* c, int n_sites, const void* gates, const i
                                 int n_gates, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const long long n = 1LL << n_sites;
-    k_basis_state<<<grid_groups(n), NT, 0, st>>>((cplx*)c, n);
+    QM_LAUNCH(QM_CLS_GATE, st, k_basis_state<<<grid_groups(n), NT, 0, st>>>((cplx*)c, n));
     for (int g = 0; g < n_gates; g++) {
         int e = launch_gate((cplx*)c, n_sites, sites[g], kinds[g], (const cplx*)gates + (long long)g * 16, 0, st);
         if (e) return e;
@@ -307,13 +308,14 @@ extern "C" int qm_sweep(void* c_, void* tbar_, int n_sites, void* gates_, const 
         if (e) return e;
         if (kinds[g] == 2) {
             int q = n_sites - 2 - sites[g];
-            k_env_polar<4><<<grid_groups(1LL << (n_sites - 2)), NT, 0, st>>>(tbar, c, n_sites, q, partials, counter,
-                                                                             G, envs ? envs + (long long)g * 16 : nullptr);
+            QM_LAUNCH(QM_CLS_ENV, st, (k_env_polar<4><<<grid_groups(1LL << (n_sites - 2)), NT, 0, st>>>(
+                tbar, c, n_sites, q, partials, counter, G, envs ? envs + (long long)g * 16 : nullptr)));
         } else {
             int q = n_sites - 1 - sites[g];
-            k_env_polar<2><<<grid_groups(1LL << (n_sites - 1)), NT, 0, st>>>(tbar, c, n_sites, q, partials, counter,
-                                                                             G, envs ? envs + (long long)g * 16 : nullptr);
+            QM_LAUNCH(QM_CLS_ENV, st, (k_env_polar<2><<<grid_groups(1LL << (n_sites - 1)), NT, 0, st>>>(
+                tbar, c, n_sites, q, partials, counter, G, envs ? envs + (long long)g * 16 : nullptr)));
         }
+        qm_prof_work(QM_CLS_ENV, 32.0 * (double)(1LL << n_sites));               // read tbar and c
         e = launch_gate(tbar, n_sites, sites[g], kinds[g], G, 2, st);           // tbar <- G_new^T tbar
         if (e) return e;
     }

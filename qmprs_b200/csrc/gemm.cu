@@ -118,9 +118,10 @@ extern "C" int qm_zgemm(int m, int n, int k, double alpha_re, double alpha_im, c
                         int batch, long long strideA, long long strideB, long long strideC, void* stream) {
     if (m <= 0 || n <= 0 || batch <= 0) return 0;
     dim3 grid(ceil_div(n, BN), ceil_div(m, BM), batch);
-    k_zgemm_nn<<<grid, 256, 0, (cudaStream_t)stream>>>(m, n, k, mk(alpha_re, alpha_im), (const cplx*)A, lda,
+    QM_LAUNCH(QM_CLS_GEMM, (cudaStream_t)stream, k_zgemm_nn<<<grid, 256, 0, (cudaStream_t)stream>>>(m, n, k, mk(alpha_re, alpha_im), (const cplx*)A, lda,
                                                         (const cplx*)B, ldb, mk(beta_re, beta_im), (cplx*)C, ldc,
-                                                        strideA, strideB, strideC);
+                                                        strideA, strideB, strideC));
+    qm_prof_work(QM_CLS_GEMM, 8.0 * m * n * (double)k * batch);
     QM_CHECK_LAUNCH();
     return 0;
 }

@@ -315,6 +315,15 @@ __global__ void k_div_sqrt(cplx* __restrict__ x, long long n, const double* __re
         x[i] = cscale(x[i], inv);
 }
 
+// out[c][p][a] = in[a][p][c]  (site tensor (l,2,r) -> (r,2,l))
+__global__ void k_reverse3(cplx* __restrict__ out, const cplx* __restrict__ in, int l, int r) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 2LL * l * r) return;
+    int a = (int)(idx / (2 * r)), rem = (int)(idx % (2 * r));
+    int p = rem / r, c = rem % r;
+    out[((long long)c * 2 + p) * l + a] = in[idx];
+}
+
 int grid_for(long long n) {
     long long g = (n + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
@@ -326,8 +335,8 @@ int grid_for(long long n) {
 
 extern "C" int qm_trim(const void* S, int k, double cutoff, int mode, int max_bond, void* out_rank, void* out_f,
                        void* stream) {
-    k_trim<<<1, 256, 0, (cudaStream_t)stream>>>((const double*)S, k, cutoff, mode, max_bond, (int*)out_rank,
-                                                (double*)out_f);
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_trim<<<1, 256, 0, (cudaStream_t)stream>>>((const double*)S, k, cutoff, mode, max_bond, (int*)out_rank,
+                                                (double*)out_f));
     QM_CHECK_LAUNCH();
     return 0;
 }
@@ -335,64 +344,70 @@ extern "C" int qm_trim(const void* S, int k, double cutoff, int mode, int max_bo
 extern "C" int qm_scale_copy(void* out, long long ldo, const void* in, long long ldi, int rows, int cols,
                              const void* S, const void* f, int mode, int half_power, void* stream) {
     if (rows <= 0 || cols <= 0) return 0;
-    k_scale_copy<<<ceil_div((long long)rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
-        (cplx*)out, ldo, (const cplx*)in, ldi, rows, cols, (const double*)S, (const double*)f, mode, half_power);
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_scale_copy<<<ceil_div((long long)rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
+        (cplx*)out, ldo, (const cplx*)in, ldi, rows, cols, (const double*)S, (const double*)f, mode, half_power));
     QM_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int qm_theta_gate(void* X, int l, int r, const void* G, int dagger, void* stream) {
-    k_theta_gate<<<ceil_div((long long)l * r, 256), 256, 0, (cudaStream_t)stream>>>((cplx*)X, l, r, (const cplx*)G,
-                                                                                   dagger);
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_theta_gate<<<ceil_div((long long)l * r, 256), 256, 0, (cudaStream_t)stream>>>((cplx*)X, l, r, (const cplx*)G,
+                                                                                   dagger));
     QM_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int qm_site_gate(void* B, int l, int r, const void* G, int dagger, void* stream) {
-    k_site_gate<<<ceil_div((long long)l * r, 256), 256, 0, (cudaStream_t)stream>>>((cplx*)B, l, r, (const cplx*)G,
-                                                                                  dagger);
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_site_gate<<<ceil_div((long long)l * r, 256), 256, 0, (cudaStream_t)stream>>>((cplx*)B, l, r, (const cplx*)G,
+                                                                                  dagger));
     QM_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int qm_chi2_select(const void* S, const void* Vh, long long ldvh, double cutoff, double tie, void* Csite,
                               void* Vsel, void* bond, void* stream) {
-    k_chi2_select<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)S, (const cplx*)Vh, ldvh, cutoff, tie,
-                                                      (cplx*)Csite, (cplx*)Vsel, (int*)bond);
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_chi2_select<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)S, (const cplx*)Vh, ldvh, cutoff, tie,
+                                                      (cplx*)Csite, (cplx*)Vsel, (int*)bond));
     QM_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int qm_chi2_first(const void* T0, void* Csite, void* stream) {
-    k_chi2_first<<<1, 32, 0, (cudaStream_t)stream>>>((const cplx*)T0, (cplx*)Csite);
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_chi2_first<<<1, 32, 0, (cudaStream_t)stream>>>((const cplx*)T0, (cplx*)Csite));
     QM_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int qm_complete_unitaries(const void* C, const void* bond, int n_sites, void* gates, void* kinds,
                                      void* bad, double sign_tol, void* stream) {
-    k_complete_unitaries<<<ceil_div(n_sites, 64), 64, 0, (cudaStream_t)stream>>>(
-        (const cplx*)C, (const int*)bond, n_sites, (cplx*)gates, (int*)kinds, (int*)bad, sign_tol);
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_complete_unitaries<<<ceil_div(n_sites, 64), 64, 0, (cudaStream_t)stream>>>(
+        (const cplx*)C, (const int*)bond, n_sites, (cplx*)gates, (int*)kinds, (int*)bad, sign_tol));
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_reverse3(void* out, const void* in, int l, int r, void* stream) {
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_reverse3<<<ceil_div(2LL * l * r, 256), 256, 0, (cudaStream_t)stream>>>((cplx*)out, (const cplx*)in, l, r));
     QM_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int qm_conj_scale_copy(void* out, const void* in, long long n, int conj, double scale, void* stream) {
     if (n <= 0) return 0;
-    k_conj_scale_copy<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((cplx*)out, (const cplx*)in, n, conj, scale);
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_conj_scale_copy<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((cplx*)out, (const cplx*)in, n, conj, scale));
     QM_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int qm_vdot(const void* a, const void* b, long long n, void* out2, void* stream) {
     QM_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), (cudaStream_t)stream));
-    k_vdot<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const cplx*)a, (const cplx*)b, n, (double*)out2);
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_vdot<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const cplx*)a, (const cplx*)b, n, (double*)out2));
     QM_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int qm_div_sqrt(void* x, long long n, const void* nrm2, void* stream) {
-    k_div_sqrt<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((cplx*)x, n, (const double*)nrm2);
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_div_sqrt<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((cplx*)x, n, (const double*)nrm2));
     QM_CHECK_LAUNCH();
     return 0;
 }

@@ -136,10 +136,11 @@ extern "C" int qm_qr(int m, int n, void* A_, long long lda, void* tau_, void* st
     cplx* tau = (cplx*)tau_;
     int k = m < n ? m : n;
     for (int j = 0; j < k; j++) {
-        k_house_vec<<<1, NT, 0, st>>>(A, lda, m, j, tau);
+        QM_LAUNCH(QM_CLS_QR_VEC, st, k_house_vec<<<1, NT, 0, st>>>(A, lda, m, j, tau));
         int ntrail = n - (j + 1);
+        qm_prof_work(QM_CLS_QR_APPLY, 16.0 * (double)(m - j) * (ntrail > 0 ? ntrail : 0));   // dot + axpy
         if (ntrail > 0)
-            k_house_apply<<<ceil_div(ntrail, CT), NT, 0, st>>>(A, lda, m, n, j + 1, A, lda, j, tau, 1);
+            QM_LAUNCH(QM_CLS_QR_APPLY, st, k_house_apply<<<ceil_div(ntrail, CT), NT, 0, st>>>(A, lda, m, n, j + 1, A, lda, j, tau, 1));
     }
     QM_CHECK_LAUNCH();
     return 0;
@@ -150,12 +151,12 @@ extern "C" int qm_qr_formq(int m, int k, const void* A_, long long lda, const vo
                            void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     cplx* Q = (cplx*)Q_;
-    k_set_eye<<<ceil_div((long long)m * k, 256), 256, 0, st>>>(Q, ldq, m, k);
+    QM_LAUNCH(QM_CLS_SMALL, st, k_set_eye<<<ceil_div((long long)m * k, 256), 256, 0, st>>>(Q, ldq, m, k));
     for (int j = k - 1; j >= 0; j--) {
         // H_j only touches rows >= j; columns < j of the accumulated product are still e_c there (zero)
         int c0 = j;
-        k_house_apply<<<ceil_div(k - c0, CT), NT, 0, st>>>(Q, ldq, m, k, c0, (const cplx*)A_, lda, j,
-                                                            (const cplx*)tau_, 0);
+        QM_LAUNCH(QM_CLS_QR_APPLY, st, k_house_apply<<<ceil_div(k - c0, CT), NT, 0, st>>>(Q, ldq, m, k, c0, (const cplx*)A_, lda, j,
+                                                            (const cplx*)tau_, 0));
     }
     QM_CHECK_LAUNCH();
     return 0;
@@ -166,9 +167,9 @@ extern "C" int qm_qr_finish(int m, int n, const void* A_, long long lda, void* R
                             long long ldq, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     int k = m < n ? m : n;
-    k_extract_r<<<ceil_div((long long)k * n, 256), 256, 0, st>>>((const cplx*)A_, lda, k, n, (cplx*)R_, ldr);
+    QM_LAUNCH(QM_CLS_SMALL, st, k_extract_r<<<ceil_div((long long)k * n, 256), 256, 0, st>>>((const cplx*)A_, lda, k, n, (cplx*)R_, ldr));
     if (Q_)
-        k_q_signs<<<ceil_div((long long)m * k, 256), 256, 0, st>>>((cplx*)Q_, ldq, m, k, (const cplx*)A_, lda);
+        QM_LAUNCH(QM_CLS_SMALL, st, k_q_signs<<<ceil_div((long long)m * k, 256), 256, 0, st>>>((cplx*)Q_, ldq, m, k, (const cplx*)A_, lda));
     QM_CHECK_LAUNCH();
     return 0;
 }

@@ -416,19 +416,19 @@ extern "C" int qm_svd(int m, int n, const void* A_, long long lda, void* U_, lon
     // --- build Wext = [W | I] ---
     if (m < n) {
         dim3 grid(ceil_div(n, 256) > 4096 ? 4096 : ceil_div(n, 256), m);
-        k_rowcopy<<<grid, 256, 0, st>>>(w.W, g.ldw, A, lda, nullptr, nullptr, 0, m, n);
+        QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_rowcopy<<<grid, 256, 0, st>>>(w.W, g.ldw, A, lda, nullptr, nullptr, 0, m, n));
     } else {
         // W[j][a] = A[a][j]: transpose of the m x n input
         // k_transpose maps in[perm[j]][a] -> out[a][j]; here "in" = A, out = W (n x m):
         // W[c][r] = A[r][c]  =>  nsel = m (rows of A), len = n (cols of A)
         int na = ceil_div(n, 32);
-        k_transpose<<<(unsigned)((long long)na * ceil_div(m, 32)), dim3(32, 8), 0, st>>>(
-            w.W, g.ldw, A, lda, nullptr, nullptr, 0, m, n, na);
+        QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose<<<(unsigned)((long long)na * ceil_div(m, 32)), dim3(32, 8), 0, st>>>(
+            w.W, g.ldw, A, lda, nullptr, nullptr, 0, m, n, na));
     }
     QM_CHECK_LAUNCH();
     {
         dim3 grid(ceil_div(g.nvp > 256 ? g.nvp : 256, 256), g.nvp);
-        k_init_ext<<<grid, 256, 0, st>>>(w.W, g.ldw, g.nv, g.nvp, g.len);
+        QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_init_ext<<<grid, 256, 0, st>>>(w.W, g.ldw, g.nv, g.nvp, g.len));
         QM_CHECK_LAUNCH();
     }
     QM_CUDA(cudaMemsetAsync(w.G, 0, (size_t)g.npairs * PMAX * PMAX * 2 * sizeof(double), st));
@@ -452,13 +452,16 @@ extern "C" int qm_svd(int m, int n, const void* A_, long long lda, void* U_, lon
     for (; sweeps < max_sweeps;) {
         QM_CUDA(cudaMemsetAsync(w.notconv, 0, sizeof(int), st));
         for (int r = 0; r < g.rounds; r++) {
-            k_gram<<<dim3(ncg, g.npairs), NT, 0, st>>>(w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, g.single,
-                                                        g.nrows, w.G);
-            k_eig<<<g.npairs, NT, 0, st>>>(w.G, w.Q, g.nrows, tol2, 12, r, g.nbp, g.single, w.notconv,
-                                           w.rotated, w.sig2);
-            k_apply<<<dim3(nca, g.npairs), NT, 0, st>>>(w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, g.single,
-                                                         g.nrows, w.Q, w.rotated);
+            QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram<<<dim3(ncg, g.npairs), NT, 0, st>>>(w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, g.single,
+                                                        g.nrows, w.G));
+            QM_LAUNCH(QM_CLS_SVD_EIG, st, k_eig<<<g.npairs, NT, 0, st>>>(w.G, w.Q, g.nrows, tol2, 12, r, g.nbp, g.single, w.notconv,
+                                           w.rotated, w.sig2));
+            QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply<<<dim3(nca, g.npairs), NT, 0, st>>>(w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, g.single,
+                                                         g.nrows, w.Q, w.rotated));
         }
+        // complex MAC = 8 flops: Gram nrows^2 x len, update nrows^2 x lenx, per pair and round
+        qm_prof_work(QM_CLS_SVD_GRAM, 8.0 * g.nrows * g.nrows * (double)g.len * g.npairs * g.rounds);
+        qm_prof_work(QM_CLS_SVD_APPLY, 8.0 * g.nrows * g.nrows * (double)lenx * g.npairs * g.rounds);
         QM_CHECK_LAUNCH();
         sweeps++;
         int h = 0;
@@ -469,7 +472,7 @@ extern "C" int qm_svd(int m, int n, const void* A_, long long lda, void* U_, lon
     if (info_host) { info_host[0] = sweeps; info_host[1] = converged; }
 
     // --- sort, emit ---
-    k_sort<<<1, 1024, (size_t)g.nv * sizeof(double), st>>>(w.sig2, g.nv, S, w.perm);
+    QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_sort<<<1, 1024, (size_t)g.nv * sizeof(double), st>>>(w.sig2, g.nv, S, w.perm));
     QM_CHECK_LAUNCH();
     const int k = g.nv;
     cplx* U = (cplx*)U_;
@@ -477,20 +480,20 @@ extern "C" int qm_svd(int m, int n, const void* A_, long long lda, void* U_, lon
     if (m < n) {
         // U[a][j] = conj(J[perm[j]][a]);  Vh[j][c] = W[perm[j]][c] / S[j]
         if (U)
-            k_transpose<<<(unsigned)((long long)ceil_div(m, 32) * ceil_div(k, 32)), dim3(32, 8), 0, st>>>(
-                U, ldu, w.W + g.len, g.ldw, w.perm, nullptr, 1, k, m, ceil_div(m, 32));
+            QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose<<<(unsigned)((long long)ceil_div(m, 32) * ceil_div(k, 32)), dim3(32, 8), 0, st>>>(
+                U, ldu, w.W + g.len, g.ldw, w.perm, nullptr, 1, k, m, ceil_div(m, 32)));
         if (Vh) {
             dim3 grid(ceil_div(n, 256) > 4096 ? 4096 : ceil_div(n, 256), k);
-            k_rowcopy<<<grid, 256, 0, st>>>(Vh, ldvh, w.W, g.ldw, w.perm, S, 0, k, n);
+            QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_rowcopy<<<grid, 256, 0, st>>>(Vh, ldvh, w.W, g.ldw, w.perm, S, 0, k, n));
         }
     } else {
         // U[a][j] = W[perm[j]][a] / S[j];  Vh[j][c] = conj(J[perm[j]][c])
         if (U)
-            k_transpose<<<(unsigned)((long long)ceil_div(m, 32) * ceil_div(k, 32)), dim3(32, 8), 0, st>>>(
-                U, ldu, w.W, g.ldw, w.perm, S, 0, k, m, ceil_div(m, 32));
+            QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose<<<(unsigned)((long long)ceil_div(m, 32) * ceil_div(k, 32)), dim3(32, 8), 0, st>>>(
+                U, ldu, w.W, g.ldw, w.perm, S, 0, k, m, ceil_div(m, 32)));
         if (Vh) {
             dim3 grid(ceil_div(n, 256), k);
-            k_rowcopy<<<grid, 256, 0, st>>>(Vh, ldvh, w.W + g.len, g.ldw, w.perm, nullptr, 1, k, n);
+            QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_rowcopy<<<grid, 256, 0, st>>>(Vh, ldvh, w.W + g.len, g.ldw, w.perm, nullptr, 1, k, n));
         }
     }
     QM_CHECK_LAUNCH();

@@ -73,7 +73,7 @@ def left_canon(K, A):
     return A
 
 
-def right_compress(K, A, max_bond=None, spectra=None):
+def right_compress(K, A, max_bond=None, spectra=None, cutoff=CUTOFF):
     """Right->left truncation sweep on a LEFT-canonical MPS: SVD of each site matrix,
     cutoff 1e-10 'rel' (+ max_bond), singular values absorbed to the left, no renorm
     (quimb right_compress / tensor_compress_bond; the QR/LQ reduction of the reference
@@ -86,7 +86,7 @@ def right_compress(K, A, max_bond=None, spectra=None):
         k = S.shape[0]
         if spectra is not None:
             spectra.append(S)
-        rank, _ = K.trim(S, k, CUTOFF, MODE_REL, max_bond or 0)
+        rank, _ = K.trim(S, k, cutoff, MODE_REL, max_bond or 0)
         n = K.read_int(rank)
         US = K.scale_copy(U[:, :n], S, None, mode=2, half_power=False)
         A[i] = K.scale_copy(Vh[:n]).reshape(n, 2, r)
@@ -94,10 +94,16 @@ def right_compress(K, A, max_bond=None, spectra=None):
     return A
 
 
-def canonicalize_truncate(K, A, max_bond=None, spectra=None):
+def canonicalize_truncate(K, A, max_bond=None, spectra=None, cutoff=CUTOFF):
     """``tensor_network_1d_compress(max_bond)`` (mps.py:247) and ``compress(form='right')``
     (mps.py:451/453): right-canonical MPS with the norm on site 0."""
-    return right_compress(K, left_canon(K, A), max_bond, spectra)
+    return right_compress(K, left_canon(K, A), max_bond, spectra, cutoff)
+
+
+def mirror(K, A):
+    """Site-reversed MPS: tensors (l,2,r) -> (r,2,l) in reverse order (used to run the
+    left-handed variants of canonicalize/compress through the right-handed kernels)."""
+    return [K.reverse3(a) for a in reversed(A)]
 
 
 def normalize_site0(K, A):
@@ -187,20 +193,22 @@ def blocks_from_kinds(kinds):
 # --------------------------------------------------------------------------------------
 # A6  inverse layer application       mps.py:933-971 (quimb gate_ / gate_split_)
 # --------------------------------------------------------------------------------------
-def apply_inverse_layer(K, B, gates, kinds, spectra=None):
+def apply_inverse_layer(K, B, gates, kinds, spectra=None, inverse=True):
     """In place on the list ``B``.  theta = G^H (A_i A_{i+1}); SVD, cutoff 1e-10 'rsum2'
-    with Frobenius renorm, sqrt(s) to both sides, no max_bond."""
+    with Frobenius renorm, sqrt(s) to both sides, no max_bond.  ``inverse=False`` is the
+    forward application (mps.py:893-931): G itself, sites in ascending order."""
     for s, e in blocks_from_kinds(kinds):
-        for i in range(e, s - 1, -1):
+        order = range(e, s - 1, -1) if inverse else range(s, e + 1)
+        for i in order:
             G = gates[i]
             if i == e:
                 l, _, r = B[i].shape
-                K.site_gate(B[i], l, r, G, dagger=True)
+                K.site_gate(B[i], l, r, G, dagger=inverse)
             else:
                 l, _, b = B[i].shape
                 _, _, r = B[i + 1].shape
                 X = K.gemm(B[i].reshape(l * 2, b), B[i + 1].reshape(b, 2 * r))
-                K.theta_gate(X, l, r, G, dagger=True)
+                K.theta_gate(X, l, r, G, dagger=inverse)
                 U, S, Vh = K.svd(X)
                 k = S.shape[0]
                 if spectra is not None:
@@ -294,7 +302,10 @@ def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 -
     """Whole path on the device.  ``psi_host``: normalised complex128 numpy vector.
     Returns dict(gates [L,N,16] numpy, kinds [L][N], n_layers, overlaps, fidelity)."""
     N = int(n_sites)
-    psi = K.from_host(np.asarray(psi_host, dtype=np.complex128).reshape(-1))
+    if hasattr(psi_host, "data_ptr"):                 # already a device tensor (bench: inputs resident in HBM)
+        psi = K.scale_copy(psi_host.reshape(-1, 1)).reshape(-1)
+    else:
+        psi = K.from_host(np.asarray(psi_host, dtype=np.complex128).reshape(-1))
     if mps is None:
         K.div_sqrt(psi, K.vdot(psi, psi))                             # quick Ket normalisation
         A = build_mps(K, psi, N, chi, record)

@@ -157,6 +157,12 @@ class CudaKernels:
                                                    self._stream()), "qm_complete_unitaries")
         return gates, kinds, bad
 
+    def reverse3(self, a):
+        l, _, r = a.shape
+        out = self.empty((r, 2, l))
+        self._check(self.lib.qm_reverse3(_p(out), _p(a), l, r, self._stream()), "qm_reverse3")
+        return out
+
     # ---- vectors --------------------------------------------------------------------
     def conj_scale_copy(self, inp, conj=False, scale=1.0):
         out = self.empty(inp.shape)
@@ -195,6 +201,28 @@ class CudaKernels:
                                       self._int_array(kinds), len(sites), _p(self._sweep_work), _p(envs),
                                       self._stream()), "qm_sweep")
         self.launches += 3 * len(sites)
+
+
+    # ---- instrumentation ------------------------------------------------------------
+    def launch_count(self):
+        """Kernel launches issued by the library since load (counted in QM_LAUNCH)."""
+        return int(self.lib.qm_launch_count())
+
+    def prof_begin(self):
+        self.lib.qm_prof_begin()
+
+    def prof_end(self):
+        """{class: (total_ms, launches, algorithmic work)} -- times from CUDA events on the launch stream."""
+        n = int(self.lib.qm_prof_num_classes())
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_longlong * n)()
+        code = self.lib.qm_prof_end(ms, cnt)
+        if code != 0:
+            raise RuntimeError(f"qm_prof_end failed with status {code}")
+        work = (ctypes.c_double * n)()
+        self.lib.qm_prof_work_get(work)
+        return {self.lib.qm_prof_class_name(i).decode(): (float(ms[i]), int(cnt[i]), float(work[i]))
+                for i in range(n)}
 
 
 _instances = {}

@@ -1,0 +1,319 @@
+"""``MPS``: device-resident matrix product state with the reference's interface.
+
+Mirrors ``qmprs.primitives.mps.MPS`` (qmprs/primitives/mps.py:50-1138): same constructor
+contract and error messages (:151-216), same method names and argument meaning.  The
+reference wraps a ``quimb.tensor.MatrixProductState``; here ``self.mps`` is a
+:class:`DeviceMPS`, a list of (l, 2, r) complex128 tensors in B200 HBM, and every method
+runs the sm_100a kernels through :mod:`qmprs_b200.host`.
+"""
+from __future__ import annotations
+
+from typing import Literal
+
+import numpy as np
+
+from qmprs_b200 import host
+from qmprs_b200.ket import Ket
+
+__all__ = ["MPS", "DeviceMPS", "GateTensor"]
+
+
+class GateTensor:
+    """Stand-in for the ``qtn.Tensor`` gate record (mps.py:615-619): ``.data`` is the
+    4x4 / 2x2 complex128 matrix, ``inds=("L","R")``, ``tags={"G"}``."""
+
+    def __init__(self, data, inds=("L", "R"), tags=("G",)):
+        self.data = np.asarray(data, dtype=np.complex128)
+        self.inds = tuple(inds)
+        self.tags = set(tags)
+
+
+UnitaryBlock = tuple  # (start, end, [GateTensor])
+UnitaryLayer = list   # [UnitaryBlock]
+
+
+class DeviceMPS:
+    """List of site tensors ``(l, 2, r)`` on the GPU (stand-in for quimb's
+    ``MatrixProductState``).  ``form`` tracks the orthogonality centre:
+    "right" (centre on site 0), "left" (centre on site N-1) or None."""
+
+    def __init__(self, tensors, K, form=None):
+        self.tensors = list(tensors)
+        self.K = K
+        self.form = form
+
+    @property
+    def num_tensors(self) -> int:
+        return len(self.tensors)
+
+    L = num_tensors
+
+    def phys_dim(self) -> int:
+        return int(self.tensors[0].shape[1])
+
+    def bond_sizes(self) -> list[int]:
+        return host.bond_dims(self.tensors)
+
+    def max_bond(self) -> int:
+        return max(self.bond_sizes()) if len(self.tensors) > 1 else 1
+
+    @property
+    def arrays(self):
+        return tuple(self.K.to_host(t) for t in self.tensors)
+
+    def copy(self) -> "DeviceMPS":
+        return DeviceMPS(host.copy_mps(self.K, self.tensors), self.K, self.form)
+
+    def to_dense(self) -> np.ndarray:
+        return self.K.to_host(host.to_dense(self.K, self.tensors))
+
+    @classmethod
+    def from_arrays(cls, arrays, K=None):
+        """Build from host arrays of shape (l,2,r) (edge tensors may be 2-D as in quimb)."""
+        if K is None:
+            from qmprs_b200.kernels import get_kernels
+            K = get_kernels()
+        n = len(arrays)
+        ts = []
+        for i, a in enumerate(arrays):
+            a = np.asarray(a, dtype=np.complex128)
+            if a.ndim == 2:
+                a = a.reshape((1,) + a.shape) if i == 0 else a.reshape(a.shape + (1,))
+            if a.ndim != 3:
+                raise ValueError("site tensors must have shape (l, p, r)")
+            ts.append(K.from_host(a))
+        return cls(ts, K)
+
+
+def _default_kernels():
+    from qmprs_b200.kernels import get_kernels
+    return get_kernels()
+
+
+class MPS:
+    """Matrix product state of a qubit register (reference: mps.py:50-216).
+
+    Pass only ``statevector`` or only ``mps`` (a :class:`DeviceMPS`).
+    """
+
+    def __init__(self, statevector=None, mps: DeviceMPS | None = None, bond_dimension: int = 64) -> None:
+        if not isinstance(bond_dimension, int) or isinstance(bond_dimension, bool) or bond_dimension < 1:
+            raise ValueError(
+                "`bond_dimension` must be an integer greater than 0. "
+                f"Received {bond_dimension}."
+            )
+        if (statevector is not None) and (mps is None):
+            if not isinstance(statevector, Ket):
+                statevector = Ket(statevector)
+            if statevector.num_qubits == 1:
+                raise ValueError(
+                    "The statevector must have at least 2 qubits. "
+                    f"Received {statevector.num_qubits}."
+                )
+            self.statevector: Ket = statevector
+            self.mps: DeviceMPS = self.from_statevector(statevector, bond_dimension)
+        elif (mps is not None) and (statevector is None):
+            if not isinstance(mps, DeviceMPS):
+                raise TypeError(
+                    "`mps` must be a `DeviceMPS` instance. "
+                    f"Received {type(mps)}."
+                )
+            if mps.num_tensors == 1:
+                raise ValueError(
+                    "The MPS must have at least 2 tensors. "
+                    f"Received {mps.num_tensors}."
+                )
+            self.mps = mps
+            self.statevector = self.to_statevector(mps)
+        else:
+            raise ValueError("Must provide either `statevector` or `mps` not both.")
+        self.bond_dimension = bond_dimension
+        self.num_sites = self.statevector.num_qubits
+        if self.mps.phys_dim() != 2:
+            raise ValueError(
+                "Only supports MPS with physical dimension of 2. "
+                f"Received {self.mps.phys_dim()}."
+            )
+        self.physical_dimension = 2
+
+    # ---- conversion (mps.py:218-270) -------------------------------------------------
+    @staticmethod
+    def from_statevector(statevector: Ket, max_bond_dimension: int, record=None) -> DeviceMPS:
+        K = _default_kernels()
+        psi = K.from_host(np.asarray(statevector.data, dtype=np.complex128).reshape(-1))
+        A = host.build_mps(K, psi, statevector.num_qubits, max_bond_dimension, record)
+        return DeviceMPS(A, K, form="right")
+
+    @staticmethod
+    def to_statevector(mps: DeviceMPS) -> Ket:
+        return Ket(mps.to_dense())
+
+    # ---- norm (mps.py:272-310) -------------------------------------------------------
+    @property
+    def norm(self) -> float:
+        K = self.mps.K
+        if self.mps.form == "right":
+            v = self.mps.tensors[0]
+        elif self.mps.form == "left":
+            v = self.mps.tensors[-1]
+        else:
+            v = host.to_dense(K, self.mps.tensors)
+        return float(np.sqrt(K.to_host(K.vdot(v, v))[0]))
+
+    @property
+    def is_normalized(self) -> bool:
+        return True if np.isclose(self.norm, 1) else False
+
+    def normalize(self) -> None:
+        if not self.is_normalized:
+            K = self.mps.K
+            t = self.mps.tensors
+            idx = 0 if self.mps.form == "right" else len(t) - 1
+            t[idx] = K.conj_scale_copy(t[idx], conj=False, scale=1.0 / self.norm)
+
+    # ---- canonical forms (mps.py:312-400) ----------------------------------------------
+    @property
+    def orthogonal_center_range(self) -> tuple[int, int]:
+        if self.mps.form == "right":
+            return (0, 0)
+        if self.mps.form == "left":
+            return (self.num_sites - 1, self.num_sites - 1)
+        return (0, self.num_sites - 1)
+
+    @property
+    def canonical_form(self) -> Literal["left", "right", "unknown"]:
+        if self.orthogonal_center_range == (0, 0):
+            return "right"
+        elif self.orthogonal_center_range == (self.num_sites - 1, self.num_sites - 1):
+            return "left"
+        return "unknown"
+
+    def canonicalize(self, mode: Literal["left", "right"], normalize=False) -> None:
+        K = self.mps.K
+        if mode == "left":
+            A = host.left_canon(K, self.mps.tensors)
+            if normalize:
+                K.div_sqrt(A[-1], K.vdot(A[-1], A[-1]))
+            self.mps = DeviceMPS(A, K, form="left")
+        elif mode == "right":
+            A = host.mirror(K, host.left_canon(K, host.mirror(K, self.mps.tensors)))
+            if normalize:
+                host.normalize_site0(K, A)
+            self.mps = DeviceMPS(A, K, form="right")
+        else:
+            raise ValueError("`mode` must be either 'left' or 'right'.")
+
+    def compress(self, max_bond_dimension: int | None = None,
+                 mode: Literal["left", "right"] | None = None) -> None:
+        """SVD-compress the bonds (mps.py:402-459)."""
+        K = self.mps.K
+        if not (max_bond_dimension or mode):
+            # quimb's default form; the state is identical, only the placement of the
+            # singular values differs -- kept right-canonical here.
+            self.mps = DeviceMPS(host.canonicalize_truncate(K, self.mps.tensors), K, form="right")
+        elif not mode and max_bond_dimension:
+            self.mps = DeviceMPS(host.canonicalize_truncate(K, self.mps.tensors, max_bond_dimension), K,
+                                 form="right")
+            self.bond_dimension = max_bond_dimension
+        else:
+            if mode in ["left", "right"]:
+                if mode == "right":
+                    A = host.canonicalize_truncate(K, self.mps.tensors, max_bond_dimension)
+                else:
+                    A = host.mirror(K, host.canonicalize_truncate(K, host.mirror(K, self.mps.tensors),
+                                                                  max_bond_dimension))
+                self.mps = DeviceMPS(A, K, form=mode)
+                if max_bond_dimension:
+                    self.bond_dimension = max_bond_dimension
+            else:
+                raise ValueError(
+                    "`mode` must be either 'left', or 'right'. "
+                    f"Received {mode}."
+                )
+
+    def permute(self, shape: Literal["lrp", "lpr"]) -> None:
+        """Index order of the site tensors (mps.py:538-563).  Device tensors are always
+        stored (l, p, r); the call only validates its argument."""
+        if shape not in ["lrp", "lpr"]:
+            raise ValueError(f"`shape` must be either 'lrp' or 'lpr'. Received {shape}.")
+
+    # ---- unitary layers (mps.py:746-1018) -----------------------------------------------
+    @staticmethod
+    def _layer_from_device(K, gates, kinds) -> UnitaryLayer:
+        g = K.to_host(gates)
+        layer = []
+        for s, e in host.blocks_from_kinds(kinds):
+            ts = []
+            for i in range(s, e + 1):
+                d = 4 if kinds[i] == 2 else 2
+                ts.append(GateTensor(g[i, : d * d].reshape(d, d).copy()))
+            layer.append((s, e, ts))
+        return layer
+
+    def _layer_to_device(self, unitary_layer: UnitaryLayer):
+        K = self.mps.K
+        N = self.num_sites
+        g = np.zeros((N, 16), dtype=np.complex128)
+        kinds = [1] * N
+        for s, e, ts in unitary_layer:
+            for i in range(s, e + 1):
+                m = np.asarray(ts[i - s].data, dtype=np.complex128)
+                g[i, : m.size] = m.reshape(-1)
+                kinds[i] = 2 if m.shape[0] == 4 else 1
+        return K.from_host(g), kinds
+
+    def generate_unitary_layer(self) -> UnitaryLayer:
+        """Unitary layer of a bond-dimension <= 2, right-canonical MPS (mps.py:746-847)."""
+        K = self.mps.K
+        N = self.num_sites
+        ts = self.mps.tensors
+        if max(self.mps.bond_sizes()) > 2:
+            raise ValueError("generate_unitary_layer needs bond dimension <= 2; use generate_bond_D_unitary_layer.")
+        pad = np.zeros((N, 2, 2, 2), dtype=np.complex128)
+        bonds = self.mps.bond_sizes()
+        for i, t in enumerate(ts):
+            a = K.to_host(t)
+            pad[i, : a.shape[0], :, : a.shape[2]] = a
+        import torch
+        gates, kinds, bad = K.complete_unitaries(K.from_host(pad.reshape(N, 8)),
+                                                 K.from_host(np.asarray(bonds, dtype=np.int32), torch.int32), N)
+        if K.read_int(bad):
+            raise ValueError("All the generated unitaries must be unitary.")
+        return self._layer_from_device(K, gates, [int(x) for x in K.to_host(kinds)])
+
+    def generate_bond_D_unitary_layer(self) -> UnitaryLayer:
+        """chi=2 truncation + completion (mps.py:849-891); ``self`` is not modified."""
+        K = self.mps.K
+        gates, kinds = host.chi2_layer(K, self.mps.tensors)
+        return self._layer_from_device(K, gates, kinds)
+
+    def apply_unitary_layer(self, unitary_layer: UnitaryLayer, inverse: bool = False) -> None:
+        """mps.py:973-995."""
+        K = self.mps.K
+        gates, kinds = self._layer_to_device(unitary_layer)
+        host.apply_inverse_layer(K, self.mps.tensors, gates, kinds, inverse=inverse)
+        self.mps.form = None
+
+    def apply_unitary_layers(self, unitary_layers: list, inverse: bool = False) -> None:
+        """mps.py:997-1018 (layers are visited in reverse order in both directions)."""
+        for layer in reversed(unitary_layers):
+            self.apply_unitary_layer(layer, inverse=inverse)
+
+    def fidelity_with_zero_state(self) -> complex:
+        """conj(<0...0|psi>) (mps.py:1020-1039)."""
+        return host.zero_overlap(self.mps.K, self.mps.tensors)
+
+    # ---- dunder (mps.py:1050-1138) ------------------------------------------------------
+    def __str__(self) -> str:
+        return f"MPS(num_sites={self.num_sites}, bond_dimensions={self.mps.bond_sizes()})"
+
+    def __repr__(self) -> str:
+        return f"MPS(statevector=..., bond_dimension={self.bond_dimension})"
+
+    def __len__(self) -> int:
+        return self.num_sites
+
+    def __eq__(self, other) -> bool:
+        if not isinstance(other, MPS) or other.num_sites != self.num_sites:
+            return False
+        return bool(np.allclose(self.mps.to_dense(), other.mps.to_dense()))

@@ -1,0 +1,72 @@
+"""``Sequential`` encoder (reference: qmprs/synthesis/mps_encoding/sequential.py:33-600).
+
+Analytic disentangling layers (Ran 2020) followed by environment-tensor optimisation
+sweeps (Rudolph et al. 2022), all numerics on the GPU through :mod:`qmprs_b200.host`.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from qmprs_b200 import host
+from qmprs_b200.primitives.mps import MPS
+from qmprs_b200.synthesis.mps_encoding.base import MPSEncoder
+
+__all__ = ["Sequential"]
+
+
+class Sequential(MPSEncoder):
+    def __init__(self, circuit_framework) -> None:
+        super().__init__(circuit_framework)
+        self._fidelity_threshold = 1 - 1e-6          # sequential.py:120
+        self.last_result = None                      # diagnostics of the last call (not in the reference)
+
+    @property
+    def fidelity_threshold(self) -> float:
+        return self._fidelity_threshold
+
+    @fidelity_threshold.setter
+    def fidelity_threshold(self, threshold: float) -> None:
+        if not isinstance(threshold, (int, float)) or threshold < 0 or threshold > 1:
+            raise ValueError("The fidelity threshold must be a float between 0 and 1.")
+        self._fidelity_threshold = threshold
+
+    @staticmethod
+    def _apply_unitary_layer_to_circuit(circuit, gates_layer, kinds) -> None:
+        """sequential.py:155-187: MPS site i <-> circuit qubit N-1-i."""
+        n = circuit.num_qubits
+        for index, kind in enumerate(kinds):
+            if kind == 1:
+                circuit.unitary(gates_layer[index, :4].reshape(2, 2).copy(), abs(index - n + 1))
+            else:
+                circuit.unitary(gates_layer[index].reshape(4, 4).copy(),
+                                [abs(index - n + 2), abs(index - n + 1)])
+
+    def _circuit_from_unitary_layers(self, num_sites, gates, kinds_per_layer):
+        """sequential.py:189-213."""
+        circuit = self.circuit_framework(num_sites)
+        for layer_gates, kinds in zip(gates, kinds_per_layer):
+            Sequential._apply_unitary_layer_to_circuit(circuit, layer_gates, kinds)
+        return circuit
+
+    def _sequential_unitary_circuit(self, mps: MPS, num_layers: int, num_sweeps: int = 0):
+        """sequential.py:543-586."""
+        K = mps.mps.K
+        A = mps.mps.tensors
+        N = mps.num_sites
+        record = {}
+        gates_all, layer_kinds, overlaps = host.disentangle(K, A, num_layers, self._fidelity_threshold, record)
+        if num_sweeps > 0:
+            target = host.to_dense(K, A)
+            host.optimize_layers(K, target, gates_all, layer_kinds, N, num_sweeps)
+        L = len(layer_kinds)
+        gates = K.to_host(gates_all).reshape(L, N, 16)
+        self.last_result = {"gates": gates, "kinds": layer_kinds, "n_layers": L, "overlaps": overlaps,
+                            "gates_device": gates_all}
+        return self._circuit_from_unitary_layers(N, gates, layer_kinds)
+
+    def prepare_mps(self, mps: MPS, **kwargs):
+        num_layers = kwargs.get("num_layers", 1)
+        num_sweeps = kwargs.get("num_sweeps", 0)
+        if not isinstance(num_layers, int) or num_layers < 1:
+            raise ValueError("The number of layers must be a positive integer.")
+        return self._sequential_unitary_circuit(mps, num_layers, num_sweeps)

@@ -162,6 +162,9 @@ class FakeKernels:
             kinds[i] = 2 if g.shape[0] == 4 else 1
         return torch.as_tensor(gates), torch.as_tensor(kinds), torch.tensor([bad], dtype=I32)
 
+    def reverse3(self, a):
+        return torch.as_tensor(np.ascontiguousarray(_np(a).transpose(2, 1, 0)))
+
     # ---- vectors ----
     def conj_scale_copy(self, inp, conj=False, scale=1.0):
         x = _np(inp)
