@@ -215,17 +215,26 @@ k_env_polar(const cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // last CTA: fixed-order sum over CTAs
+    // last CTA: fixed-order sum over CTAs, 256/(D*D) slices per entry then a serial combine
     __shared__ cplx Es[16];
-    if (threadIdx.x < D * D) {
+    __shared__ cplx Ep[NT];
+    {
+        constexpr int E2 = D * D, NS = NT / E2;
+        const int e = threadIdx.x % E2, sl = threadIdx.x / E2;
         cplx s = mk(0.0, 0.0);
         const volatile double* pv = (const volatile double*)partials;
-        for (unsigned int b = 0; b < gridDim.x; b++) {
-            long long o = ((long long)b * 16 + threadIdx.x) * 2;
+        for (unsigned int b = sl; b < gridDim.x; b += NS) {
+            long long o = ((long long)b * 16 + e) * 2;
             s.x += pv[o];
             s.y += pv[o + 1];
         }
-        Es[threadIdx.x] = s;
+        Ep[threadIdx.x] = s;
+        __syncthreads();
+        if (threadIdx.x < E2) {
+            cplx tsum = mk(0.0, 0.0);
+            for (int k = 0; k < NS; k++) tsum = cadd(tsum, Ep[k * E2 + threadIdx.x]);
+            Es[threadIdx.x] = tsum;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -141,101 +141,111 @@ k_gram(const cplx* __restrict__ W, long long ldw, int len, int chunk, int round,
 // (2) Hermitian eigen-solve of each Gram matrix: parallel cyclic two-sided Jacobi.
 // grid = npairs.  Writes the accumulated row transformation Q (W_new = Q W_old), the
 // diagonal (squared row norms), and re-zeroes G.
+//
+// One inner round = np disjoint rotations R = diag of 2x2 blocks; G' = R G R^H and
+// Q' = R Q are formed in ONE pass from the old matrices into a second shared-memory
+// buffer (two barriers per round).  `cross_only`: both 16-row blocks are already
+// internally orthogonal (true after the first outer sweep), so only the 16x16 cross
+// pairs are rotated: 16 rounds per inner sweep instead of 31.
 // ---------------------------------------------------------------------------------
+constexpr int GS = PMAX + 1;                              // row stride of the shared matrices
+constexpr size_t EIG_SMEM = 4ull * PMAX * GS * sizeof(cplx);   // g[2], q[2]
+
 __global__ void __launch_bounds__(NT)
-k_eig(double* __restrict__ G, cplx* __restrict__ Qout, int nrows, double tol2, int max_inner, int round,
-      int nbp, int single, int* __restrict__ notconv, int* __restrict__ rotated, double* __restrict__ sig2) {
-    __shared__ cplx g[PMAX][PMAX + 1], q[PMAX][PMAX + 1];
-    __shared__ double rc[PMAX / 2], rs[PMAX / 2], rd[PMAX / 2];
-    __shared__ cplx ru[PMAX / 2];
-    __shared__ int rp[PMAX / 2], rq[PMAX / 2], ract[PMAX / 2];
-    __shared__ int s_any, s_sweep, s_off;
+k_eig(double* __restrict__ G, cplx* __restrict__ Qout, int nrows, double tol2, int max_inner, int cross_only,
+      int round, int nbp, int single, int* __restrict__ notconv, int* __restrict__ rotated,
+      double* __restrict__ sig2) {
+    extern __shared__ __align__(16) unsigned char eig_smem[];
+    cplx* gbuf = (cplx*)eig_smem;                         // [2][PMAX][GS]
+    cplx* qbuf = gbuf + 2 * PMAX * GS;                    // [2][PMAX][GS]
+    __shared__ double cc[PMAX];
+    __shared__ cplx off[PMAX];
+    __shared__ int par[PMAX];
+    __shared__ int s_any, s_sweep, s_off, s_intra;
     const int tid = threadIdx.x, pair = blockIdx.x;
     const int n = nrows, ne = n + (n & 1), np = ne / 2;
     double* Gp = G + (long long)pair * PMAX * PMAX * 2;
+    int cur = 0;
+    cplx* g = gbuf;
+    cplx* q = qbuf;
     for (int e = tid; e < n * n; e += NT) {
         int i = e / n, j = e % n;
-        g[i][j] = mk(Gp[2 * e], Gp[2 * e + 1]);
+        g[i * GS + j] = mk(Gp[2 * e], Gp[2 * e + 1]);
         Gp[2 * e] = 0.0; Gp[2 * e + 1] = 0.0;
-        q[i][j] = mk(i == j ? 1.0 : 0.0, 0.0);
+        q[i * GS + j] = mk(i == j ? 1.0 : 0.0, 0.0);
     }
-    if (tid == 0) { s_any = 0; s_off = 0; }
+    if (tid == 0) { s_any = 0; s_off = 0; s_intra = 0; }
     __syncthreads();
     // is the fresh Gram matrix already diagonal to tolerance?
     {
-        int off = 0;
+        int offd = 0, intra = 0;
         for (int e = tid; e < n * n; e += NT) {
             int i = e / n, j = e % n;
             if (i < j) {
-                double a = g[i][i].x, b = g[j][j].x;
-                if (a > 0.0 && b > 0.0 && cabs2(g[i][j]) > tol2 * a * b) off = 1;
+                double a = g[i * GS + i].x, b = g[j * GS + j].x;
+                if (a > 0.0 && b > 0.0 && cabs2(g[i * GS + j]) > tol2 * a * b) {
+                    offd = 1;
+                    if ((i < BSZ) == (j < BSZ)) intra = 1;
+                }
             }
         }
-        if (off) s_off = 1;
+        if (offd) s_off = 1;
+        if (intra) s_intra = 1;
     }
     __syncthreads();
+    const bool cross = cross_only && !single && n == PMAX && !s_intra;
+    const int nrounds = cross ? BSZ : ne - 1;
     if (s_off) {
         for (int sweep = 0; sweep < max_inner; sweep++) {
             if (tid == 0) s_sweep = 0;
             __syncthreads();
-            for (int r = 0; r < ne - 1; r++) {
+            for (int r = 0; r < nrounds; r++) {
                 if (tid < np) {
                     int p, qq;
-                    if (ne == 2) { p = 0; qq = 1; } else circle_pair(r, tid, ne, p, qq);
-                    int act = 0;
+                    if (cross) { p = tid; qq = BSZ + ((tid + r) & (BSZ - 1)); }
+                    else if (ne == 2) { p = 0; qq = 1; }
+                    else circle_pair(r, tid, ne, p, qq);
+                    bool act = false;
+                    double c = 1.0, s = 0.0;
+                    cplx u = mk(0.0, 0.0);
                     if (p < n && qq < n) {
-                        double a = g[p][p].x, b = g[qq][qq].x;
-                        cplx gpq = g[p][qq];
+                        double a = g[p * GS + p].x, b = g[qq * GS + qq].x;
+                        cplx gpq = g[p * GS + qq];
                         double mag2 = cabs2(gpq);
                         if (a > 0.0 && b > 0.0 && mag2 > tol2 * a * b) {
                             double mag = sqrt(mag2);
                             double zeta = (b - a) / (2.0 * mag);
                             double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                            double c = 1.0 / sqrt(1.0 + t * t);
-                            rc[tid] = c; rs[tid] = c * t; rd[tid] = t * mag;
-                            ru[tid] = mk(gpq.x / mag, gpq.y / mag);
-                            act = 1;
+                            c = 1.0 / sqrt(1.0 + t * t);
+                            s = c * t;
+                            u = mk(gpq.x / mag, gpq.y / mag);
+                            act = true;
                         }
                     }
-                    rp[tid] = p; rq[tid] = qq; ract[tid] = act;
+                    if (p < n) { cc[p] = c; off[p] = act ? mk(-s * u.x, -s * u.y) : mk(0.0, 0.0); par[p] = act ? qq : p; }
+                    if (qq < n) { cc[qq] = c; off[qq] = act ? mk(s * u.x, -s * u.y) : mk(0.0, 0.0); par[qq] = act ? p : qq; }
                     if (act) { s_sweep = 1; s_any = 1; }
                 }
                 __syncthreads();
-                // row phase: rows p,q of g and q
-                for (int item = tid; item < np * n; item += NT) {
-                    int k = item / n, col = item % n;
-                    if (!ract[k]) continue;
-                    int p = rp[k], qq = rq[k];
-                    double c = rc[k], s = rs[k];
-                    cplx su = cscale(ru[k], s);            // s*u
-                    cplx gp = g[p][col], gq = g[qq][col];
-                    g[p][col] = csub(cscale(gp, c), cmul(su, gq));
-                    g[qq][col] = cadd(cmul(cconj(su), gp), cscale(gq, c));
-                    cplx qp = q[p][col], qv = q[qq][col];
-                    q[p][col] = csub(cscale(qp, c), cmul(su, qv));
-                    q[qq][col] = cadd(cmul(cconj(su), qp), cscale(qv, c));
+                cplx* g2 = gbuf + (cur ^ 1) * PMAX * GS;
+                cplx* q2 = qbuf + (cur ^ 1) * PMAX * GS;
+                for (int e = tid; e < n * n; e += NT) {
+                    int i = e / n, j = e % n;
+                    int pi = par[i], pj = par[j];
+                    double ci = cc[i], cj = cc[j];
+                    cplx oi = off[i], oj = off[j];
+                    // (R G)[i][b] = ci G[i][b] + oi G[pi][b]
+                    cplx rg_j = cadd(cscale(g[i * GS + j], ci), cmul(oi, g[pi * GS + j]));
+                    cplx rg_pj = cadd(cscale(g[i * GS + pj], ci), cmul(oi, g[pi * GS + pj]));
+                    cplx v = cadd(cscale(rg_j, cj), cmulc(rg_pj, oj));
+                    if (i == j) v.y = 0.0;
+                    else if (j == pi) v = mk(0.0, 0.0);
+                    g2[i * GS + j] = v;
+                    q2[i * GS + j] = cadd(cscale(q[i * GS + j], ci), cmul(oi, q[pi * GS + j]));
                 }
-                __syncthreads();
-                // column phase: columns p,q of g
-                for (int item = tid; item < np * n; item += NT) {
-                    int k = item / n, row = item % n;
-                    if (!ract[k]) continue;
-                    int p = rp[k], qq = rq[k];
-                    double c = rc[k], s = rs[k];
-                    cplx su = cscale(ru[k], s);
-                    cplx gp = g[row][p], gq = g[row][qq];
-                    g[row][p] = csub(cscale(gp, c), cmul(cconj(su), gq));
-                    g[row][qq] = cadd(cmul(su, gp), cscale(gq, c));
-                }
-                __syncthreads();
-                if (tid < np && ract[tid]) {
-                    int p = rp[tid], qq = rq[tid];
-                    double a = g[p][p].x, b = g[qq][qq].x;   // analytically a - t|g|, b + t|g|; keep computed, force real
-                    g[p][p] = mk(a, 0.0);
-                    g[qq][qq] = mk(b, 0.0);
-                    g[p][qq] = mk(0.0, 0.0);
-                    g[qq][p] = mk(0.0, 0.0);
-                }
+                cur ^= 1;
+                g = gbuf + cur * PMAX * GS;
+                q = qbuf + cur * PMAX * GS;
                 __syncthreads();
             }
             if (!s_sweep) break;
@@ -243,11 +253,150 @@ k_eig(double* __restrict__ G, cplx* __restrict__ Qout, int nrows, double tol2, i
         }
     }
     cplx* Qp = Qout + (long long)pair * PMAX * PMAX;
-    for (int e = tid; e < n * n; e += NT) Qp[e] = q[e / n][e % n];
-    if (tid < n) sig2[pair_row(tid, pair, round, nbp, single)] = g[tid][tid].x;
+    for (int e = tid; e < n * n; e += NT) Qp[e] = q[(e / n) * GS + (e % n)];
+    if (tid < n) sig2[pair_row(tid, pair, round, nbp, single)] = g[tid * GS + tid].x;
     if (tid == 0) {
         rotated[pair] = s_any;
         if (s_off) atomicAdd(notconv, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// DMMA versions of (1) and (3) for full 32-row pairs (multi-block mode).  Fragments are
+// loaded straight from global memory: a lane's 16-byte load of W[row][col] carries the
+// re and im parts that serve as A and B operands of mma.sync.m8n8k4.f64.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// G = W_pair W_pair^H over a column chunk.  Each warp owns a 4-column slice per step; only
+// the upper block triangle of 8x8 tiles is accumulated (G is Hermitian).
+__global__ void __launch_bounds__(NT)
+k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, int round, int nbp,
+           double* __restrict__ G) {
+    __shared__ double gs[PMAX * PMAX * 2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = blockIdx.y;
+    const int g = lane >> 2, t = lane & 3;
+    int bi, bj;
+    circle_pair(round, pair, nbp, bi, bj);
+    const cplx* rowp[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) {
+        int r = mt * 8 + g;
+        rowp[mt] = W + (long long)(r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ)) * ldw;
+    }
+    for (int i = tid; i < PMAX * PMAX * 2; i += NT) gs[i] = 0.0;
+    double cr[10][2], ci[10][2];
+#pragma unroll
+    for (int i = 0; i < 10; i++) { cr[i][0] = cr[i][1] = ci[i][0] = ci[i][1] = 0.0; }
+    const long long c0 = (long long)blockIdx.x * chunk;
+    const long long c1 = (c0 + chunk < len) ? c0 + chunk : len;
+    __syncthreads();
+#pragma unroll 2
+    for (long long k0 = c0 + warp * 4; k0 < c1; k0 += 32) {
+        long long col = k0 + t;
+        bool ok = col < c1;
+        cplx w[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) w[mt] = ok ? rowp[mt][col] : mk(0.0, 0.0);
+        int idx = 0;
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+            for (int nt = mt; nt < 4; nt++) {
+                // W_m conj(W_n): re = ar*br + ai*bi ; im = ai*br - ar*bi
+                dmma884(cr[idx][0], cr[idx][1], w[mt].x, w[nt].x);
+                dmma884(cr[idx][0], cr[idx][1], w[mt].y, w[nt].y);
+                dmma884(ci[idx][0], ci[idx][1], w[mt].y, w[nt].x);
+                dmma884(ci[idx][0], ci[idx][1], -w[mt].x, w[nt].y);
+                idx++;
+            }
+    }
+    {
+        int idx = 0;
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+            for (int nt = mt; nt < 4; nt++) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    int row = mt * 8 + g, col = nt * 8 + 2 * t + e;
+                    atomicAdd(&gs[(row * PMAX + col) * 2], cr[idx][e]);
+                    atomicAdd(&gs[(row * PMAX + col) * 2 + 1], ci[idx][e]);
+                }
+                idx++;
+            }
+    }
+    __syncthreads();
+    double* Gp = G + (long long)pair * PMAX * PMAX * 2;
+    for (int e = tid; e < PMAX * PMAX; e += NT) {
+        int i = e / PMAX, j = e % PMAX;
+        double re, im;
+        if ((i >> 3) <= (j >> 3)) { re = gs[(i * PMAX + j) * 2]; im = gs[(i * PMAX + j) * 2 + 1]; }
+        else { re = gs[(j * PMAX + i) * 2]; im = -gs[(j * PMAX + i) * 2 + 1]; }
+        atomicAdd(&Gp[2 * e], re);
+        atomicAdd(&Gp[2 * e + 1], im);
+    }
+}
+
+// Wext[rows] <- Q Wext[rows]: each warp owns 8-column strips, loads the 32x8 strip as B
+// fragments, multiplies by Q (A fragments from padded shared planes) and stores in place.
+__global__ void __launch_bounds__(NT)
+k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, int round, int nbp,
+            const cplx* __restrict__ Q, const int* __restrict__ rotated) {
+    const int pair = blockIdx.y;
+    if (!rotated[pair]) return;
+    constexpr int QS = PMAX + 4;
+    __shared__ double qr[PMAX * QS], qi[PMAX * QS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int bi, bj;
+    circle_pair(round, pair, nbp, bi, bj);
+    const cplx* Qp = Q + (long long)pair * PMAX * PMAX;
+    for (int e = tid; e < PMAX * PMAX; e += NT) {
+        cplx v = Qp[e];
+        qr[(e / PMAX) * QS + (e % PMAX)] = v.x;
+        qi[(e / PMAX) * QS + (e % PMAX)] = v.y;
+    }
+    __syncthreads();
+    const long long c0 = (long long)blockIdx.x * chunk;
+    const long long c1 = (c0 + chunk < lenx) ? c0 + chunk : lenx;
+    for (long long n0 = c0 + warp * 8; n0 < c1; n0 += 64) {
+        long long col = n0 + g;
+        bool ok = col < c1;
+        cplx b[8];
+#pragma unroll
+        for (int kt = 0; kt < 8; kt++) {
+            int r = kt * 4 + t;
+            long long row = r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ);
+            b[kt] = ok ? W[row * ldw + col] : mk(0.0, 0.0);
+        }
+        double cr[4][2], ci[4][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) { cr[mt][0] = cr[mt][1] = ci[mt][0] = ci[mt][1] = 0.0; }
+#pragma unroll
+        for (int kt = 0; kt < 8; kt++)
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+                double ar = qr[(mt * 8 + g) * QS + kt * 4 + t];
+                double ai = qi[(mt * 8 + g) * QS + kt * 4 + t];
+                dmma884(cr[mt][0], cr[mt][1], ar, b[kt].x);
+                dmma884(cr[mt][0], cr[mt][1], -ai, b[kt].y);
+                dmma884(ci[mt][0], ci[mt][1], ar, b[kt].y);
+                dmma884(ci[mt][0], ci[mt][1], ai, b[kt].x);
+            }
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+            int r = mt * 8 + g;
+            long long row = r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ);
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                long long c2 = n0 + 2 * t + e;
+                if (c2 < c1) W[row * ldw + c2] = mk(cr[mt][e], ci[mt][e]);
+            }
+        }
     }
 }
 
@@ -448,16 +597,34 @@ extern "C" int qm_svd(int m, int n, const void* A_, long long lda, void* U_, lon
     const long long chunk_g = pick_chunk(g.len), chunk_a = pick_chunk(lenx);
     const int ncg = ceil_div(g.len, chunk_g), nca = ceil_div(lenx, chunk_a);
     const double tol2 = tol * tol;
+    static bool eig_attr_set = false;
+    if (!eig_attr_set) {
+        QM_CUDA(cudaFuncSetAttribute(k_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIG_SMEM));
+        eig_attr_set = true;
+    }
     int sweeps = 0, converged = 0;
     for (; sweeps < max_sweeps;) {
         QM_CUDA(cudaMemsetAsync(w.notconv, 0, sizeof(int), st));
+        const int max_inner = (sweeps == 0) ? 4 : 2;
+        const int cross_only = (sweeps > 0) ? 1 : 0;
         for (int r = 0; r < g.rounds; r++) {
-            QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram<<<dim3(ncg, g.npairs), NT, 0, st>>>(w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, g.single,
-                                                        g.nrows, w.G));
-            QM_LAUNCH(QM_CLS_SVD_EIG, st, k_eig<<<g.npairs, NT, 0, st>>>(w.G, w.Q, g.nrows, tol2, 12, r, g.nbp, g.single, w.notconv,
-                                           w.rotated, w.sig2));
-            QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply<<<dim3(nca, g.npairs), NT, 0, st>>>(w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, g.single,
-                                                         g.nrows, w.Q, w.rotated));
+            if (g.single) {
+                QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram<<<dim3(ncg, g.npairs), NT, 0, st>>>(
+                    w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, g.single, g.nrows, w.G));
+            } else {
+                QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram_mma<<<dim3(ncg, g.npairs), NT, 0, st>>>(
+                    w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, w.G));
+            }
+            QM_LAUNCH(QM_CLS_SVD_EIG, st, k_eig<<<g.npairs, NT, EIG_SMEM, st>>>(
+                w.G, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, cross_only, r, g.nbp, g.single, w.notconv,
+                w.rotated, w.sig2));
+            if (g.single) {
+                QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply<<<dim3(nca, g.npairs), NT, 0, st>>>(
+                    w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, g.single, g.nrows, w.Q, w.rotated));
+            } else {
+                QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply_mma<<<dim3(nca, g.npairs), NT, 0, st>>>(
+                    w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, w.Q, w.rotated));
+            }
         }
         // complex MAC = 8 flops: Gram nrows^2 x len, update nrows^2 x lenx, per pair and round
         qm_prof_work(QM_CLS_SVD_GRAM, 8.0 * g.nrows * g.nrows * (double)g.len * g.npairs * g.rounds);
