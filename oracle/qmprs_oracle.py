@@ -425,13 +425,41 @@ def circuit_state(layers, n_sites):
     return c
 
 
-def polar_unitary(E):
-    """u @ vh of the SVD of E (sequential.py:473-478)."""
+NULL_REL = 1.0e-13      # canonical polar: singular values <= NULL_REL * s_max are null directions
+
+
+def _polar_plain(E):
     u, _, vh = np.linalg.svd(E)
     return u @ vh
 
 
-def sweep(target, layers, n_sites):
+def polar_unitary(E, gauge="verbatim"):
+    """u @ vh of the SVD of E (sequential.py:473-478).
+
+    A rank-deficient E (a gate whose inputs do not span the full space: fresh |0> inputs,
+    the left edge of a layer, block starts) leaves u @ vh undetermined on null(E); the
+    reference gets whatever LAPACK returns there (decided by rounding noise), and that
+    choice does feed back into later updates of the same sweep.  ``canonical`` fixes it
+    independently of any basis: null(E) is mapped onto null(E^H) by the partial isometry
+    closest to the identity, N_l polar(N_l^H N_r) N_r^H, the eps->0 limit of
+    polar(E + eps*I)."""
+    if gauge == "verbatim":
+        return _polar_plain(E)
+    u, s, vh = np.linalg.svd(E)
+    smax = s[0] if s.size else 0.0
+    keep = s > NULL_REL * smax if smax > 0 else np.zeros(s.shape, dtype=bool)
+    r = int(np.count_nonzero(keep))
+    d = E.shape[0]
+    if r == d:
+        return u @ vh
+    P = u[:, :r] @ vh[:r]
+    Nl = u[:, r:]                    # orthonormal basis of null(E^H)
+    Nr = np.conj(vh[r:]).T           # orthonormal basis of null(E)
+    X = _polar_plain(np.conj(Nl).T @ Nr)
+    return P + Nl @ X @ np.conj(Nr).T
+
+
+def sweep(target, layers, n_sites, gauge="verbatim"):
     """A9: one environment sweep (sequential.py:400-507).  ``target`` is the dense
     (un-normalised) chi-truncated state; ``layers`` is updated in place."""
     N = n_sites
@@ -445,7 +473,7 @@ def sweep(target, layers, n_sites):
         R = 2 ** (N - site - k)
         c = apply_gate_dense(c, N, site, np.conj(G).T)                 # :460
         E = np.tensordot(tbar.reshape(L, d, R), c.reshape(L, d, R), axes=([0, 2], [0, 2]))  # :463
-        Gn = np.conj(polar_unitary(E))                                 # :473-491
+        Gn = np.conj(polar_unitary(E, gauge))                          # :473-491
         tbar = np.einsum("lor,ob->lbr", tbar.reshape(L, d, R), Gn).reshape(-1)   # :496
         layers[li][bi][2][ti] = Gn                                     # :501-505
     return layers
@@ -506,7 +534,7 @@ def prepare(psi, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 - 1e-6,
     n_used = len(layers)
 
     for _ in range(num_sweeps):                                        # :532-539
-        sweep(target, layers, N)
+        sweep(target, layers, N, gauge)
 
     return {"layers": layers, "n_layers": n_used, "mps": A, "target": target,
             "overlaps": overlaps, "n_sites": N}

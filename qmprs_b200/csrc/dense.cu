@@ -30,7 +30,7 @@ __device__ __forceinline__ void load_mat(const cplx* __restrict__ G, int dim, in
 
 // state <- M applied on the two bits (q+1, q).  One thread per group of 4 amplitudes.
 __global__ void __launch_bounds__(NT)
-k_gate2(cplx* __restrict__ x, int nbits, int q, const cplx* __restrict__ G, int op) {
+k_gate2(const cplx* xin, cplx* x, int nbits, int q, const cplx* __restrict__ G, int op) {
     __shared__ cplx Ms[16];
     if (threadIdx.x == 0) load_mat(G, 4, op, Ms);
     __syncthreads();
@@ -43,7 +43,7 @@ k_gate2(cplx* __restrict__ x, int nbits, int q, const cplx* __restrict__ G, int 
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ngroups;
          t += (long long)gridDim.x * blockDim.x) {
         long long base = ((t >> q) << (q + 2)) | (t & lowmask);
-        cplx v0 = x[base], v1 = x[base + stride], v2 = x[base + 2 * stride], v3 = x[base + 3 * stride];
+        cplx v0 = xin[base], v1 = xin[base + stride], v2 = xin[base + 2 * stride], v3 = xin[base + 3 * stride];
         cplx y[4];
 #pragma unroll
         for (int a = 0; a < 4; a++) {
@@ -59,7 +59,7 @@ k_gate2(cplx* __restrict__ x, int nbits, int q, const cplx* __restrict__ G, int 
 
 // state <- M applied on bit q.
 __global__ void __launch_bounds__(NT)
-k_gate1(cplx* __restrict__ x, int nbits, int q, const cplx* __restrict__ G, int op) {
+k_gate1(const cplx* xin, cplx* x, int nbits, int q, const cplx* __restrict__ G, int op) {
     __shared__ cplx Ms[4];
     if (threadIdx.x == 0) load_mat(G, 2, op, Ms);
     __syncthreads();
@@ -70,22 +70,23 @@ k_gate1(cplx* __restrict__ x, int nbits, int q, const cplx* __restrict__ G, int 
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ngroups;
          t += (long long)gridDim.x * blockDim.x) {
         long long base = ((t >> q) << (q + 1)) | (t & lowmask);
-        cplx v0 = x[base], v1 = x[base + stride];
+        cplx v0 = xin[base], v1 = xin[base + stride];
         x[base] = cadd(cmul(m0, v0), cmul(m1, v1));
         x[base + stride] = cadd(cmul(m2, v0), cmul(m3, v1));
     }
 }
 
 // ---------------------------------------------------------------------------------
-// Polar factor of a d x d matrix (d = 2 or 4) by one-sided Jacobi:  E V = U Sigma,
-// P = U V^H; null directions (sigma <= 1e-15 sigma_max, e.g. gates whose second input is
-// still |0>) are completed to an orthonormal basis.  Writes conj(P) (sequential.py:478-491).
-// Single thread.
+// Polar factor of a d x d matrix (d <= 4) by one-sided Jacobi:  E V = U Sigma, P = U V^H.
+// Rank-deficient E (gates whose inputs do not span the full space, e.g. a fresh |0> input
+// or the left edge of a layer) leaves P undetermined on null(E); the reference inherits
+// whatever LAPACK returns there.  Canonical rule (oracle `canonical` mode): directions with
+// sigma <= 1e-13 sigma_max are null, and null(E) is mapped onto null(E^H) by the partial
+// isometry closest to the identity, N_l polar(N_l^H N_r) N_r^H (the eps->0 limit of
+// polar(E + eps I)); it depends on E only, not on any basis choice.
+// Single thread.  polar_conj writes conj(P) (sequential.py:478-491).
 // ---------------------------------------------------------------------------------
-__device__ void polar_conj(const cplx* E, int d, cplx* out) {
-    cplx A[4][4], V[4][4];
-    for (int i = 0; i < d; i++)
-        for (int j = 0; j < d; j++) { A[i][j] = E[i * d + j]; V[i][j] = mk(i == j ? 1.0 : 0.0, 0.0); }
+__device__ void jacobi_cols(cplx A[4][4], cplx V[4][4], int d) {
     const double tol2 = 4e-30;
     for (int sweep = 0; sweep < 40; sweep++) {
         int rot = 0;
@@ -100,12 +101,12 @@ __device__ void polar_conj(const cplx* E, int d, cplx* out) {
                 double mag2 = cabs2(g);
                 if (!(a > 0.0 && b > 0.0) || mag2 <= tol2 * a * b) continue;
                 rot = 1;
-                double mag = sqrt(mag2);
-                double zeta = (b - a) / (2.0 * mag);
-                double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-                cplx e = mk(g.x / mag, g.y / mag);          // e^{i phi}
-                cplx se = cscale(e, s), sec = cconj(se);
+                double imag = rsqrt(mag2);
+                double zeta = 0.5 * (b - a) * imag;
+                double z1 = 1.0 + zeta * zeta;
+                double t = copysign(1.0, zeta) / (fabs(zeta) + z1 * rsqrt(z1));
+                double c = rsqrt(1.0 + t * t), s = c * t;
+                cplx se = mk(s * g.x * imag, s * g.y * imag), sec = cconj(se);   // s e^{+-i phi}
                 // x' = c x - s e^{-i phi} y ; y' = s e^{i phi} x + c y
                 for (int i = 0; i < d; i++) {
                     cplx xx = A[i][p], yy = A[i][q];
@@ -118,23 +119,11 @@ __device__ void polar_conj(const cplx* E, int d, cplx* out) {
             }
         if (!rot) break;
     }
-    double sig[4], smax = 0.0;
-    for (int j = 0; j < d; j++) {
-        double s = 0.0;
-        for (int i = 0; i < d; i++) s += cabs2(A[i][j]);
-        sig[j] = sqrt(s);
-        smax = sig[j] > smax ? sig[j] : smax;
-    }
-    bool isnull[4];
-    for (int j = 0; j < d; j++) {
-        isnull[j] = !(sig[j] > 1e-15 * smax) || smax == 0.0;
-        if (!isnull[j]) {
-            double inv = 1.0 / sig[j];
-            for (int i = 0; i < d; i++) A[i][j] = cscale(A[i][j], inv);
-        }
-    }
-    // complete null columns of U: Gram-Schmidt of the standard basis vector with the
-    // largest residual against every column fixed so far (twice for orthogonality)
+}
+
+// Gram-Schmidt completion: for every column j with isnull[j], pick the standard basis vector
+// with the largest residual against all fixed columns, orthogonalise twice, normalise.
+__device__ void complete_columns(cplx U[4][4], const bool* isnull, int d) {
     bool fixed[4];
     for (int j = 0; j < d; j++) fixed[j] = !isnull[j];
     for (int j = 0; j < d; j++) {
@@ -148,8 +137,8 @@ __device__ void polar_conj(const cplx* E, int d, cplx* out) {
                 for (int c = 0; c < d; c++) {
                     if (!fixed[c]) continue;
                     cplx dot = mk(0.0, 0.0);
-                    for (int i = 0; i < d; i++) ccfma(dot, A[i][c], v[i]);     // u_c^H v
-                    for (int i = 0; i < d; i++) v[i] = csub(v[i], cmul(A[i][c], dot));
+                    for (int i = 0; i < d; i++) ccfma(dot, U[i][c], v[i]);
+                    for (int i = 0; i < d; i++) v[i] = csub(v[i], cmul(U[i][c], dot));
                 }
             double nr = 0.0;
             for (int i = 0; i < d; i++) nr += cabs2(v[i]);
@@ -158,17 +147,76 @@ __device__ void polar_conj(const cplx* E, int d, cplx* out) {
                 for (int i = 0; i < d; i++) bestv[i] = v[i];
             }
         }
-        double inv = 1.0 / sqrt(best);
-        for (int i = 0; i < d; i++) A[i][j] = cscale(bestv[i], inv);
+        double inv = rsqrt(best);
+        for (int i = 0; i < d; i++) U[i][j] = cscale(bestv[i], inv);
         fixed[j] = true;
     }
-    // out = conj(U V^H):  out[i][j] = conj( sum_k U[i][k] conj(V[j][k]) )
+}
+
+// M (d x d) <- its polar factor.  NESTED: canonical completion of the null directions.
+template <bool NESTED>
+__device__ void polar_factor(cplx M[4][4], int d) {
+    cplx A[4][4], V[4][4];
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j < d; j++) { A[i][j] = M[i][j]; V[i][j] = mk(i == j ? 1.0 : 0.0, 0.0); }
+    jacobi_cols(A, V, d);
+    double sig[4], smax = 0.0;
+    for (int j = 0; j < d; j++) {
+        double s = 0.0;
+        for (int i = 0; i < d; i++) s += cabs2(A[i][j]);
+        sig[j] = sqrt(s);
+        smax = sig[j] > smax ? sig[j] : smax;
+    }
+    bool isnull[4];
+    int m = 0;
+    for (int j = 0; j < d; j++) {
+        isnull[j] = !(sig[j] > 1e-13 * smax) || smax == 0.0;
+        if (isnull[j]) m++;
+        else {
+            double inv = 1.0 / sig[j];
+            for (int i = 0; i < d; i++) A[i][j] = cscale(A[i][j], inv);
+        }
+    }
+    if (m > 0) {
+        complete_columns(A, isnull, d);                  // columns isnull[] of A: some basis N_l of null(M^H)
+        if (NESTED) {
+            int nidx[4];
+            int c = 0;
+            for (int j = 0; j < d; j++) if (isnull[j]) nidx[c++] = j;
+            cplx X[4][4];                                // X = N_l^H N_r  (m x m), N_r = V[:, null]
+            for (int a = 0; a < m; a++)
+                for (int b = 0; b < m; b++) {
+                    cplx sacc = mk(0.0, 0.0);
+                    for (int i = 0; i < d; i++) ccfma(sacc, A[i][nidx[a]], V[i][nidx[b]]);
+                    X[a][b] = sacc;
+                }
+            polar_factor<false>(X, m);
+            cplx Nl[4][4];
+            for (int i = 0; i < d; i++)
+                for (int a = 0; a < m; a++) Nl[i][a] = A[i][nidx[a]];
+            for (int i = 0; i < d; i++)
+                for (int b = 0; b < m; b++) {
+                    cplx sacc = mk(0.0, 0.0);
+                    for (int a = 0; a < m; a++) cfma(sacc, Nl[i][a], X[a][b]);
+                    A[i][nidx[b]] = sacc;
+                }
+        }
+    }
     for (int i = 0; i < d; i++)
         for (int j = 0; j < d; j++) {
-            cplx s = mk(0.0, 0.0);
-            for (int k = 0; k < d; k++) cfmac(s, A[i][k], V[j][k]);
-            out[i * d + j] = cconj(s);
+            cplx sacc = mk(0.0, 0.0);
+            for (int k = 0; k < d; k++) cfmac(sacc, A[i][k], V[j][k]);      // U V^H
+            M[i][j] = sacc;
         }
+}
+
+__device__ void polar_conj(const cplx* E, int d, cplx* out) {
+    cplx M[4][4];
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j < d; j++) M[i][j] = E[i * d + j];
+    polar_factor<true>(M, d);
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j < d; j++) out[i * d + j] = cconj(M[i][j]);
 }
 
 // ---------------------------------------------------------------------------------
@@ -249,6 +297,146 @@ k_env_polar(const cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits
     }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Stored-intermediates sweep.  While the circuit state is built (A8) every intermediate
+// c_k = g_{k-1}...g_0|0> is kept in HBM ((M+1) x 2^N amplitudes: 4.8 GB at the 20-qubit
+// headline config, 180 GB available), so the backward sweep never re-derives c:
+// one fused pass per gate reads tbar, applies the previously updated gate (its axes sit
+// directly below the current gate's axes), writes tbar, reads c_k and accumulates E_k.
+// 48 bytes per amplitude per gate-step instead of 96.
+// ---------------------------------------------------------------------------------
+// warp transpose-reduce of 32 doubles: lane L ends with the warp sum of v[L] in v[0]
+__device__ __forceinline__ double warp_reduce32(double* v, int lane) {
+#pragma unroll
+    for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; i++) {
+            double send = upper ? v[i] : v[i + n / 2];
+            double keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// NU: bits in the window [q0, q0+NU); the current gate (dimension CD) acts on the top
+// log2(CD) bits of the window, the pending gate (dimension PD, 0 = none) on the bottom ones.
+template <int NU, int CD, int PD>
+__global__ void __launch_bounds__(NT)
+k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int q0,
+            const cplx* __restrict__ Gpend, cplx* __restrict__ partials, unsigned int* __restrict__ counter,
+            cplx* __restrict__ gate_out, cplx* __restrict__ env_out) {
+    constexpr int GSZ = 1 << NU;
+    constexpr int CSH = NU - (CD == 4 ? 2 : 1);
+    constexpr int NLOW = 1 << CSH;
+    __shared__ cplx Pm[16];
+    __shared__ double wsum[NT / 32][32];
+    __shared__ int s_last;
+    if (PD > 0 && threadIdx.x < PD * PD) {
+        int a = threadIdx.x / PD, b = threadIdx.x % PD;
+        Pm[threadIdx.x] = Gpend[b * PD + a];                  // M = G^T : tbar'[b] = sum_o G[o][b] tbar[o]
+    }
+    __syncthreads();
+    cplx P[PD > 0 ? PD * PD : 1];
+    if (PD > 0) {
+#pragma unroll
+        for (int i = 0; i < PD * PD; i++) P[i] = Pm[i];
+    }
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) acc[i] = 0.0;
+    const long long ngroups = 1LL << (nbits - NU);
+    const long long stride = 1LL << q0;
+    const long long lowmask = stride - 1;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ngroups;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long base = ((t >> q0) << (q0 + NU)) | (t & lowmask);
+        cplx tv[GSZ], cv[GSZ];
+#pragma unroll
+        for (int j = 0; j < GSZ; j++) tv[j] = tbar[base + j * stride];
+#pragma unroll
+        for (int j = 0; j < GSZ; j++) cv[j] = c[base + j * stride];
+        if (PD > 0) {
+#pragma unroll
+            for (int h = 0; h < GSZ / PD; h++) {
+                cplx y[PD > 0 ? PD : 1];
+#pragma unroll
+                for (int a = 0; a < PD; a++) {
+                    cplx sacc = mk(0.0, 0.0);
+#pragma unroll
+                    for (int b = 0; b < PD; b++) cfma(sacc, P[a * PD + b], tv[h * PD + b]);
+                    y[a] = sacc;
+                }
+#pragma unroll
+                for (int a = 0; a < PD; a++) tv[h * PD + a] = y[a];
+            }
+#pragma unroll
+            for (int j = 0; j < GSZ; j++) tbar[base + j * stride] = tv[j];
+        }
+#pragma unroll
+        for (int o = 0; o < CD; o++)
+#pragma unroll
+            for (int b = 0; b < CD; b++) {
+                cplx e = mk(acc[2 * (o * CD + b)], acc[2 * (o * CD + b) + 1]);
+#pragma unroll
+                for (int lo = 0; lo < NLOW; lo++) cfma(e, tv[(o << CSH) | lo], cv[(b << CSH) | lo]);
+                acc[2 * (o * CD + b)] = e.x;
+                acc[2 * (o * CD + b) + 1] = e.y;
+            }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double mine = warp_reduce32(acc, lane);
+    wsum[warp][lane] = mine;
+    __syncthreads();
+    if (warp == 0) {
+        double ssum = 0.0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++) ssum += wsum[w][lane];
+        ((double*)partials)[(long long)blockIdx.x * 32 + lane] = ssum;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int done = atomicAdd(counter, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last CTA: fixed-order reduction over CTAs (8 slices per value, then serial combine), then the polar update
+    __shared__ double Ep[NT];
+    __shared__ cplx Es[16];
+    {
+        const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
+        const volatile double* pv = (const volatile double*)partials;
+        double ssum = 0.0;
+        for (unsigned int b = sl; b < gridDim.x; b += NT / 32) ssum += pv[(long long)b * 32 + e];
+        Ep[threadIdx.x] = ssum;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double tsum = 0.0;
+#pragma unroll
+            for (int k = 0; k < NT / 32; k++) tsum += Ep[k * 32 + threadIdx.x];
+            Ep[threadIdx.x] = tsum;
+        }
+        __syncthreads();
+        if (threadIdx.x < CD * CD) Es[threadIdx.x] = mk(Ep[2 * threadIdx.x], Ep[2 * threadIdx.x + 1]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cplx E[16], Pout[16];
+        for (int i = 0; i < CD * CD; i++) E[i] = Es[i];
+        polar_conj(E, CD, Pout);
+        for (int i = 0; i < CD * CD; i++) gate_out[i] = Pout[i];
+        if (env_out)
+            for (int i = 0; i < CD * CD; i++) env_out[i] = E[i];
+        *counter = 0u;
+        __threadfence();
+    }
+}
+
 __global__ void k_basis_state(cplx* __restrict__ x, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x)
@@ -263,14 +451,16 @@ int grid_groups(long long ngroups) {
     return (int)g;
 }
 
-int launch_gate(cplx* x, int nbits, int site, int kind, const cplx* G, int op, cudaStream_t st) {
+int launch_gate(cplx* x, int nbits, int site, int kind, const cplx* G, int op, cudaStream_t st,
+                const cplx* xin = nullptr) {
+    if (!xin) xin = x;
     qm_prof_work(QM_CLS_GATE, 32.0 * (double)(1LL << nbits));      // read + write every amplitude
     if (kind == 2) {
         int q = nbits - 2 - site;
-        QM_LAUNCH(QM_CLS_GATE, st, k_gate2<<<grid_groups(1LL << (nbits - 2)), NT, 0, st>>>(x, nbits, q, G, op));
+        QM_LAUNCH(QM_CLS_GATE, st, k_gate2<<<grid_groups(1LL << (nbits - 2)), NT, 0, st>>>(xin, x, nbits, q, G, op));
     } else {
         int q = nbits - 1 - site;
-        QM_LAUNCH(QM_CLS_GATE, st, k_gate1<<<grid_groups(1LL << (nbits - 1)), NT, 0, st>>>(x, nbits, q, G, op));
+        QM_LAUNCH(QM_CLS_GATE, st, k_gate1<<<grid_groups(1LL << (nbits - 1)), NT, 0, st>>>(xin, x, nbits, q, G, op));
     }
     return (int)cudaGetLastError();
 }
@@ -291,6 +481,87 @@ extern "C" int qm_circuit_state(void* c, int n_sites, const void* gates, const i
     for (int g = 0; g < n_gates; g++) {
         int e = launch_gate((cplx*)c, n_sites, sites[g], kinds[g], (const cplx*)gates + (long long)g * 16, 0, st);
         if (e) return e;
+    }
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+
+// cs: (n_gates+1) x 2^N amplitudes; cs[0] = |0..0>, cs[k+1] = g_k cs[k].  A8 with every
+// intermediate kept for the stored sweep.
+extern "C" int qm_circuit_states(void* cs_, int n_sites, const void* gates, const int* sites, const int* kinds,
+                                 int n_gates, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cplx* cs = (cplx*)cs_;
+    const long long n = 1LL << n_sites;
+    QM_LAUNCH(QM_CLS_GATE, st, k_basis_state<<<grid_groups(n), NT, 0, st>>>(cs, n));
+    for (int g = 0; g < n_gates; g++) {
+        int e = launch_gate(cs + (long long)(g + 1) * n, n_sites, sites[g], kinds[g],
+                            (const cplx*)gates + (long long)g * 16, 0, st, cs + (long long)g * n);
+        if (e) return e;
+    }
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+namespace {
+template <int NU, int CD, int PD>
+void launch_env_fused(cplx* tbar, const cplx* c, int nbits, int q0, const cplx* Gpend, cplx* partials,
+                      unsigned int* counter, cplx* gate_out, cplx* env_out, cudaStream_t st) {
+    const long long ngroups = 1LL << (nbits - NU);
+    qm_prof_work(QM_CLS_ENV, (PD > 0 ? 48.0 : 32.0) * (double)(1LL << nbits));
+    QM_LAUNCH(QM_CLS_ENV, st, (k_env_fused<NU, CD, PD><<<grid_groups(ngroups), NT, 0, st>>>(
+        tbar, c, nbits, q0, Gpend, partials, counter, gate_out, env_out)));
+}
+}  // namespace
+
+// One environment sweep using the stored intermediates cs (from qm_circuit_states).
+// tbar = conj(target) on entry; gates updated in place.
+extern "C" int qm_sweep_stored(const void* cs_, void* tbar_, int n_sites, void* gates_, const int* sites,
+                               const int* kinds, int n_gates, void* work, void* envs_, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const cplx* cs = (const cplx*)cs_;
+    cplx* tbar = (cplx*)tbar_;
+    cplx* gates = (cplx*)gates_;
+    cplx* envs = (cplx*)envs_;
+    unsigned int* counter = (unsigned int*)work;
+    cplx* partials = (cplx*)((char*)work + 256);
+    const long long n = 1LL << n_sites;
+    const int N = n_sites;
+    QM_CUDA(cudaMemsetAsync(counter, 0, 256, st));
+    for (int g = n_gates - 1; g >= 0; g--) {
+        cplx* G = gates + (long long)g * 16;
+        cplx* env = envs ? envs + (long long)g * 16 : nullptr;
+        const cplx* c = cs + (long long)g * n;
+        const int ck = kinds[g];
+        const int cb = (ck == 2) ? N - 2 - sites[g] : N - 1 - sites[g];      // lowest bit of the current gate
+        bool fused = false;
+        if (g + 1 < n_gates) {
+            const cplx* Gp = gates + (long long)(g + 1) * 16;
+            const int pk = kinds[g + 1];
+            const int pb = (pk == 2) ? N - 2 - sites[g + 1] : N - 1 - sites[g + 1];
+            const int ptop = pb + (pk == 2 ? 1 : 0);                          // highest bit of the pending gate
+            if (ck == 2 && pk == 2 && ptop == cb) {                          // overlap on one site
+                launch_env_fused<3, 4, 4>(tbar, c, N, pb, Gp, partials, counter, G, env, st);
+                fused = true;
+            } else if (ck == 2 && pk == 1 && pb == cb) {
+                launch_env_fused<2, 4, 2>(tbar, c, N, pb, Gp, partials, counter, G, env, st);
+                fused = true;
+            } else if (ck == 1 && pk == 2 && ptop == cb - 1) {
+                launch_env_fused<3, 2, 4>(tbar, c, N, pb, Gp, partials, counter, G, env, st);
+                fused = true;
+            } else if (ck == 1 && pk == 1 && pb == cb - 1) {
+                launch_env_fused<2, 2, 2>(tbar, c, N, pb, Gp, partials, counter, G, env, st);
+                fused = true;
+            } else {
+                int e = launch_gate(tbar, N, sites[g + 1], pk, Gp, 2, st);    // tbar <- G_new^T tbar (unfused)
+                if (e) return e;
+            }
+        }
+        if (!fused) {
+            if (ck == 2) launch_env_fused<2, 4, 0>(tbar, c, N, cb, nullptr, partials, counter, G, env, st);
+            else launch_env_fused<1, 2, 0>(tbar, c, N, cb, nullptr, partials, counter, G, env, st);
+        }
     }
     QM_CHECK_LAUNCH();
     return 0;

@@ -243,17 +243,27 @@ def flat_schedule(kinds_per_layer, n_sites):
     return sites, kinds
 
 
-def optimize_layers(K, target, gates_all, kinds_per_layer, n_sites, num_sweeps, envs=None):
+STORED_SWEEP_MAX_BYTES = 64 << 30      # intermediates kept in HBM up to 64 GiB (180 GB per B200)
+
+
+def optimize_layers(K, target, gates_all, kinds_per_layer, n_sites, num_sweeps, envs=None, stored=True):
     """``_optimize_unitary_layers``: per sweep rebuild the dense circuit state from the
     current gates (sequential.py:533, 443-447; the reference's full-rank re-compression
     of that state into an MPS is an identity and is skipped) and run one environment
     sweep (sequential.py:452-505).  ``gates_all``: [L*N, 16] in application order."""
     sites, kinds = flat_schedule(kinds_per_layer, n_sites)
+    stored_bytes = (len(sites) + 1) * 16 * (1 << n_sites)
+    use_stored = stored and stored_bytes <= STORED_SWEEP_MAX_BYTES
     c = None
     for _ in range(num_sweeps):
-        c = K.circuit_state(n_sites, gates_all, sites, kinds, out=c)
         tbar = K.conj_scale_copy(target, conj=True)
-        K.sweep(c, tbar, n_sites, gates_all, sites, kinds, envs)
+        if use_stored:
+            # every intermediate c_k stays in HBM; one fused pass per gate in the sweep
+            c = K.circuit_states(n_sites, gates_all, sites, kinds, out=c)
+            K.sweep_stored(c, tbar, n_sites, gates_all, sites, kinds, envs)
+        else:
+            c = K.circuit_state(n_sites, gates_all, sites, kinds, out=c)
+            K.sweep(c, tbar, n_sites, gates_all, sites, kinds, envs)
     return gates_all
 
 

@@ -203,6 +203,21 @@ class CudaKernels:
         self.launches += 3 * len(sites)
 
 
+    def circuit_states(self, n_sites, gates, sites, kinds, out=None):
+        """All intermediates c_0..c_M ((M+1) x 2^N) of the circuit applied to |0..0>."""
+        M = len(sites)
+        cs = out if out is not None else self.empty((M + 1, 1 << n_sites))
+        self._check(self.lib.qm_circuit_states(_p(cs), n_sites, _p(gates), self._int_array(sites),
+                                               self._int_array(kinds), M, self._stream()), "qm_circuit_states")
+        return cs
+
+    def sweep_stored(self, cs, tbar, n_sites, gates, sites, kinds, envs=None):
+        if self._sweep_work is None:
+            self._sweep_work = torch.empty(int(self.lib.qm_sweep_work_bytes()), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.qm_sweep_stored(_p(cs), _p(tbar), n_sites, _p(gates), self._int_array(sites),
+                                             self._int_array(kinds), len(sites), _p(self._sweep_work), _p(envs),
+                                             self._stream()), "qm_sweep_stored")
+
     # ---- instrumentation ------------------------------------------------------------
     def launch_count(self):
         """Kernel launches issued by the library since load (counted in QM_LAUNCH)."""

@@ -200,6 +200,30 @@ class FakeKernels:
             self.apply_gate(c, n_sites, sites[g], kinds[g], gates[g], 0)
         return c
 
+    def circuit_states(self, n_sites, gates, sites, kinds, out=None):
+        M = len(sites)
+        cs = out if out is not None else torch.zeros((M + 1, 1 << n_sites), dtype=C128)
+        cs.zero_()
+        cs[0, 0] = 1.0
+        for g in range(M):
+            cs[g + 1].copy_(cs[g])
+            self.apply_gate(cs[g + 1], n_sites, sites[g], kinds[g], gates[g], 0)
+        return cs
+
+    def sweep_stored(self, cs, tbar, n_sites, gates, sites, kinds, envs=None):
+        N = n_sites
+        for g in range(len(sites) - 1, -1, -1):
+            site, kind = sites[g], kinds[g]
+            d = 4 if kind == 2 else 2
+            k = 2 if kind == 2 else 1
+            L, R = 2 ** site, 2 ** (N - site - k)
+            E = np.tensordot(_np(tbar).reshape(L, d, R), _np(cs[g]).reshape(L, d, R), axes=([0, 2], [0, 2]))
+            Gn = np.conj(O.polar_unitary(E, "canonical"))
+            gates[g, : d * d] = torch.as_tensor(Gn.reshape(-1))
+            if envs is not None:
+                envs[g, : d * d] = torch.as_tensor(E.reshape(-1))
+            self.apply_gate(tbar, N, site, kind, gates[g], 2)
+
     def sweep(self, c, tbar, n_sites, gates, sites, kinds, envs=None):
         N = n_sites
         for g in range(len(sites) - 1, -1, -1):
@@ -209,7 +233,7 @@ class FakeKernels:
             self.apply_gate(c, N, site, kind, gates[g], 1)
             L, R = 2 ** site, 2 ** (N - site - k)
             E = np.tensordot(_np(tbar).reshape(L, d, R), _np(c).reshape(L, d, R), axes=([0, 2], [0, 2]))
-            Gn = np.conj(O.polar_unitary(E))
+            Gn = np.conj(O.polar_unitary(E, "canonical"))
             gates[g, : d * d] = torch.as_tensor(Gn.reshape(-1))
             if envs is not None:
                 envs[g, : d * d] = torch.as_tensor(E.reshape(-1))

@@ -227,7 +227,7 @@ def test_polar_via_sweep_full_rank(K):
         assert np.abs(K.to_host(c) - cref).max() <= 1e-10
         tbar = K.conj_scale_copy(K.from_host(target), conj=True)
         K.sweep(c, tbar, N, G, sites, kinds)
-        O.sweep(target, ref_layers, N)
+        O.sweep(target, ref_layers, N, "canonical")
     c = K.to_host(K.circuit_state(N, G, sites, kinds))
     cref = O.circuit_state(ref_layers, N)
     assert np.abs(c - cref).max() <= 1e-9
@@ -236,3 +236,32 @@ def test_polar_via_sweep_full_rank(K):
         d = 4 if kinds[idx] == 2 else 2
         m = g[idx][: d * d].reshape(d, d)
         assert np.abs(m @ np.conj(m).T - np.eye(d)).max() <= 1e-12
+
+
+def test_sweep_stored_matches_recompute(K):
+    """The stored-intermediates sweep (fused kernel) and the recompute sweep are the same
+    algorithm: identical circuit states after each sweep, including block boundaries
+    (unfused pending gates) and one-qubit gates."""
+    rng = np.random.default_rng(77)
+    N = 7
+    kinds_layer = [2, 2, 1, 2, 1, 1, 1]            # blocks (0,2) (3,4) (5,5) (6,6)
+    L = 3
+    gates = np.zeros((L * N, 16), dtype=np.complex128)
+    kinds = kinds_layer * L
+    sites = list(range(N)) * L
+    for idx, k in enumerate(kinds):
+        d = 4 if k == 2 else 2
+        q, _ = np.linalg.qr(crand(rng, d, d))
+        gates[idx, : d * d] = q.reshape(-1)
+    target = crand(rng, 2 ** N)
+    Ga, Gb = K.from_host(gates), K.from_host(gates)
+    T = K.from_host(target)
+    for sweep in range(3):
+        ca = K.circuit_state(N, Ga, sites, kinds)
+        K.sweep(ca, K.conj_scale_copy(T, conj=True), N, Ga, sites, kinds)
+        cs = K.circuit_states(N, Gb, sites, kinds)
+        assert np.abs(K.to_host(cs[-1]) - K.to_host(K.circuit_state(N, Gb, sites, kinds))).max() <= 1e-14
+        K.sweep_stored(cs, K.conj_scale_copy(T, conj=True), N, Gb, sites, kinds)
+        fa = K.to_host(K.circuit_state(N, Ga, sites, kinds))
+        fb = K.to_host(K.circuit_state(N, Gb, sites, kinds))
+        assert np.abs(fa - fb).max() <= 1e-11, sweep
