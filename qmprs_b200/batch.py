@@ -1,0 +1,86 @@
+"""Batches of independent target states sharded over the GPUs of one node.
+
+BASELINE.json config 5 / SURVEY.md section 8(e): state s goes to rank ``s mod world``;
+there is no communication while the states are compiled (each rank runs the single-state
+path on its own B200), and one final all-gather of fixed-size records
+``{gates[L][N][16], kinds[L][N], n_layers, fidelity}`` over NCCL (NVLink/NVSwitch) -- about
+29 KB per 12-qubit / 10-layer state.  One process per GPU (torchrun); without an initialised
+process group the whole batch runs on the local device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from qmprs_b200 import host
+
+
+def shard_indices(n_states: int, rank: int, world: int) -> list[int]:
+    return list(range(rank, n_states, world))
+
+
+def record_len(n_sites: int, num_layers: int) -> int:
+    return num_layers * n_sites * 32 + num_layers * n_sites + 2
+
+
+def pack_record(res: dict, n_sites: int, num_layers: int) -> np.ndarray:
+    """float64 vector: gates (re,im interleaved, zero padded to num_layers), kinds, n_layers, fidelity."""
+    L = res["n_layers"]
+    g = np.zeros((num_layers, n_sites, 16), dtype=np.complex128)
+    k = np.zeros((num_layers, n_sites), dtype=np.float64)
+    g[:L] = res["gates"]
+    k[:L] = np.asarray(res["kinds"], dtype=np.float64)
+    return np.concatenate([g.view(np.float64).reshape(-1), k.reshape(-1), [float(L), float(res["fidelity"])]])
+
+
+def unpack_record(vec: np.ndarray, n_sites: int, num_layers: int) -> dict:
+    ng = num_layers * n_sites * 32
+    nk = num_layers * n_sites
+    L = int(round(vec[ng + nk]))
+    g = vec[:ng].view(np.complex128).reshape(num_layers, n_sites, 16)[:L].copy()
+    k = vec[ng:ng + nk].reshape(num_layers, n_sites)[:L].astype(np.int32)
+    return {"gates": g, "kinds": [list(map(int, row)) for row in k], "n_layers": L, "fidelity": float(vec[ng + nk + 1])}
+
+
+def prepare_state_batch(states, bond_dimension: int, num_layers: int = 1, num_sweeps: int = 0,
+                        threshold: float = 1 - 1e-6, kernels=None, gather: bool = True):
+    """Compile every row of ``states`` (B x 2^n) and return the list of B result records
+    (on every rank when ``gather``).  ``kernels``: kernel handle (default: CUDA on the
+    local rank's device)."""
+    import torch.distributed as dist
+
+    states = np.asarray(states, dtype=np.complex128)
+    B, dim = states.shape
+    n = int(round(np.log2(dim)))
+    if 2 ** n != dim:
+        raise ValueError("each state must have 2^n amplitudes")
+    if not isinstance(num_layers, int) or num_layers < 1:
+        raise ValueError("The number of layers must be a positive integer.")
+    distributed = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank() if distributed else 0
+    world = dist.get_world_size() if distributed else 1
+    if kernels is None:
+        from qmprs_b200.kernels import get_kernels
+        dev = f"cuda:{rank % max(torch.cuda.device_count(), 1)}"
+        kernels = get_kernels(dev)
+    K = kernels
+    mine = shard_indices(B, rank, world)
+    rl = record_len(n, num_layers)
+    per_rank = (B + world - 1) // world
+    local = np.zeros((per_rank, rl), dtype=np.float64)
+    for slot, s in enumerate(mine):
+        res = host.prepare(K, states[s], n, bond_dimension, num_layers, num_sweeps, threshold)
+        local[slot] = pack_record(res, n, num_layers)
+    if not (distributed and gather) or world == 1:
+        return [unpack_record(local[slot], n, num_layers) for slot in range(len(mine))] if world == 1 else \
+               {s: unpack_record(local[slot], n, num_layers) for slot, s in enumerate(mine)}
+    # one collective: all-gather of the fixed-size record blocks
+    send = torch.from_numpy(local).to(K.device)
+    recv = torch.empty((world, per_rank, rl), dtype=torch.float64, device=K.device)
+    dist.all_gather_into_tensor(recv.view(world * per_rank, rl), send)
+    allrec = recv.cpu().numpy()
+    out = [None] * B
+    for r in range(world):
+        for slot, s in enumerate(shard_indices(B, r, world)):
+            out[s] = unpack_record(allrec[r, slot], n, num_layers)
+    return out

@@ -18,6 +18,7 @@
 // At the end sigma_j = |row_j|, Z = rows / sigma, J = the accumulated unitary:
 //   m <  n :  A = J^H Sigma Z          U = J^H,  Vh = Z
 //   m >= n :  A = Z^T Sigma conj(J)    U = Z^T,  Vh = conj(J)
+#include <cstdlib>
 #include "common.cuh"
 #include "qmprs_b200.h"
 
@@ -149,25 +150,22 @@ k_gram(const cplx* __restrict__ W, long long ldw, int len, int chunk, int round,
 // pairs are rotated: 16 rounds per inner sweep instead of 31.
 // ---------------------------------------------------------------------------------
 constexpr int GS = PMAX + 1;                              // row stride of the shared matrices
-constexpr size_t EIG_SMEM = 4ull * PMAX * GS * sizeof(cplx);   // g[2], q[2]
+constexpr size_t EIG_SMEM = 2ull * PMAX * GS * sizeof(cplx);   // g, q
 
 __global__ void __launch_bounds__(NT)
 k_eig(double* __restrict__ G, cplx* __restrict__ Qout, int nrows, double tol2, int max_inner, int cross_only,
       int round, int nbp, int single, int* __restrict__ notconv, int* __restrict__ rotated,
       double* __restrict__ sig2) {
     extern __shared__ __align__(16) unsigned char eig_smem[];
-    cplx* gbuf = (cplx*)eig_smem;                         // [2][PMAX][GS]
-    cplx* qbuf = gbuf + 2 * PMAX * GS;                    // [2][PMAX][GS]
-    __shared__ double cc[PMAX];
-    __shared__ cplx off[PMAX];
-    __shared__ int par[PMAX];
-    __shared__ int s_any, s_sweep, s_off, s_mc, s_mi;
+    cplx* g = (cplx*)eig_smem;                            // [PMAX][GS]
+    cplx* q = g + PMAX * GS;                              // [PMAX][GS]
+    __shared__ double rcc[PMAX / 2];
+    __shared__ cplx roff[PMAX / 2];
+    __shared__ int rpp[PMAX / 2], rqq[PMAX / 2], ract[PMAX / 2];
+    __shared__ int s_any, s_sweep, s_off, s_mc, s_mi, s_round;
     const int tid = threadIdx.x, pair = blockIdx.x;
     const int n = nrows, ne = n + (n & 1), np = ne / 2;
     double* Gp = G + (long long)pair * PMAX * PMAX * 2;
-    int cur = 0;
-    cplx* g = gbuf;
-    cplx* q = qbuf;
     for (int e = tid; e < n * n; e += NT) {
         int i = e / n, j = e % n;
         g[i * GS + j] = mk(Gp[2 * e], Gp[2 * e + 1]);
@@ -210,6 +208,8 @@ k_eig(double* __restrict__ G, cplx* __restrict__ Qout, int nrows, double tol2, i
             if (tid == 0) s_sweep = 0;
             __syncthreads();
             for (int r = 0; r < nrounds; r++) {
+                if (tid == 0) s_round = 0;
+                __syncwarp();
                 if (tid < np) {
                     int p, qq;
                     if (cross) { p = tid; qq = BSZ + ((tid + r) & (BSZ - 1)); }
@@ -235,30 +235,56 @@ k_eig(double* __restrict__ G, cplx* __restrict__ Qout, int nrows, double tol2, i
                             act = true;
                         }
                     }
-                    if (p < n) { cc[p] = c; off[p] = act ? mk(-s * u.x, -s * u.y) : mk(0.0, 0.0); par[p] = act ? qq : p; }
-                    if (qq < n) { cc[qq] = c; off[qq] = act ? mk(s * u.x, -s * u.y) : mk(0.0, 0.0); par[qq] = act ? p : qq; }
-                    if (act) { s_sweep = 1; s_any = 1; }
+                    rpp[tid] = p; rqq[tid] = qq; rcc[tid] = c;
+                    roff[tid] = mk(-s * u.x, -s * u.y);
+                    ract[tid] = act ? 1 : 0;
+                    if (act) { s_sweep = 1; s_any = 1; s_round = 1; }
                 }
                 __syncthreads();
-                cplx* g2 = gbuf + (cur ^ 1) * PMAX * GS;
-                cplx* q2 = qbuf + (cur ^ 1) * PMAX * GS;
-                for (int e = tid; e < n * n; e += NT) {
-                    int i = e / n, j = e % n;
-                    int pi = par[i], pj = par[j];
-                    double ci = cc[i], cj = cc[j];
-                    cplx oi = off[i], oj = off[j];
-                    // (R G)[i][b] = ci G[i][b] + oi G[pi][b]
-                    cplx rg_j = cadd(cscale(g[i * GS + j], ci), cmul(oi, g[pi * GS + j]));
-                    cplx rg_pj = cadd(cscale(g[i * GS + pj], ci), cmul(oi, g[pi * GS + pj]));
-                    cplx v = cadd(cscale(rg_j, cj), cmulc(rg_pj, oj));
-                    if (i == j) v.y = 0.0;
-                    else if (j == pi) v = mk(0.0, 0.0);
-                    g2[i * GS + j] = v;
-                    q2[i * GS + j] = cadd(cscale(q[i * GS + j], ci), cmul(oi, q[pi * GS + j]));
+                if (s_round) {
+                    // G' = R G R^H by 2x2 blocks: block (k,l) = rows {p_k,q_k} x cols {p_l,q_l} depends only
+                    // on the same block of G (4 loads, 4 stores).  In place: every block is owned by one thread.
+                    for (int blk = tid; blk < np * np; blk += NT) {
+                        const int k = blk / np, l = blk % np;
+                        const int pk = rpp[k], qk = rqq[k], pl = rpp[l], ql = rqq[l];
+                        const bool vk = qk < n, vl = ql < n;           // dummy partner (odd n): single row/col
+                        const double ck = rcc[k], cl = rcc[l];
+                        const cplx ok = roff[k], ol = roff[l];         // -s u  (row p gets ck*x + ok*y, row q gets -conj(ok)*x + ck*y)
+                        cplx g00 = g[pk * GS + pl];
+                        cplx g01 = vl ? g[pk * GS + ql] : mk(0.0, 0.0);
+                        cplx g10 = vk ? g[qk * GS + pl] : mk(0.0, 0.0);
+                        cplx g11 = (vk && vl) ? g[qk * GS + ql] : mk(0.0, 0.0);
+                        // rows: [x0;x1] = R_k [g0*; g1*]
+                        cplx a00 = cadd(cscale(g00, ck), cmul(ok, g10));
+                        cplx a01 = cadd(cscale(g01, ck), cmul(ok, g11));
+                        cplx a10 = csub(cscale(g10, ck), cmul(cconj(ok), g00));
+                        cplx a11 = csub(cscale(g11, ck), cmul(cconj(ok), g01));
+                        // cols: [y0 y1] = [a*0 a*1] R_l^H :  y0 = cl a0 + conj(ol) a1 ; y1 = -ol a0 + cl a1
+                        cplx b00 = cadd(cscale(a00, cl), cmulc(a01, ol));
+                        cplx b01 = csub(cscale(a01, cl), cmul(ol, a00));
+                        cplx b10 = cadd(cscale(a10, cl), cmulc(a11, ol));
+                        cplx b11 = csub(cscale(a11, cl), cmul(ol, a10));
+                        if (k == l) {
+                            b00.y = 0.0; b11.y = 0.0;
+                            if (ract[k]) { b01 = mk(0.0, 0.0); b10 = mk(0.0, 0.0); }
+                        }
+                        g[pk * GS + pl] = b00;
+                        if (vl) g[pk * GS + ql] = b01;
+                        if (vk) g[qk * GS + pl] = b10;
+                        if (vk && vl) g[qk * GS + ql] = b11;
+                    }
+                    // Q' = R Q : rows p_k, q_k
+                    for (int item = tid; item < np * n; item += NT) {
+                        const int k = item / n, col = item % n;
+                        if (!ract[k]) continue;
+                        const int pk = rpp[k], qk = rqq[k];
+                        const double ck = rcc[k];
+                        const cplx ok = roff[k];
+                        cplx x = q[pk * GS + col], y = q[qk * GS + col];
+                        q[pk * GS + col] = cadd(cscale(x, ck), cmul(ok, y));
+                        q[qk * GS + col] = csub(cscale(y, ck), cmul(cconj(ok), x));
+                    }
                 }
-                cur ^= 1;
-                g = gbuf + cur * PMAX * GS;
-                q = qbuf + cur * PMAX * GS;
                 __syncthreads();
             }
             if (!s_sweep) break;
@@ -615,11 +641,21 @@ extern "C" int qm_svd(int m, int n, const void* A_, long long lda, void* U_, lon
         QM_CUDA(cudaFuncSetAttribute(k_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIG_SMEM));
         eig_attr_set = true;
     }
+    // schedule knobs (defaults chosen from the sweep study in profiles/; env overrides for experiments)
+    static int tune_inner0 = -1, tune_inner = 1, tune_cross = 1;
+    if (tune_inner0 < 0) {
+        const char* e0 = getenv("QM_SVD_INNER0");
+        const char* e1 = getenv("QM_SVD_INNER");
+        const char* e2 = getenv("QM_SVD_CROSS");
+        tune_inner0 = e0 ? atoi(e0) : 2;
+        tune_inner = e1 ? atoi(e1) : 1;
+        tune_cross = e2 ? atoi(e2) : 1;
+    }
     int sweeps = 0, converged = 0;
     for (; sweeps < max_sweeps;) {
         QM_CUDA(cudaMemsetAsync(w.notconv, 0, sizeof(int), st));
-        const int max_inner = (sweeps == 0) ? 4 : 2;
-        const int cross_only = (sweeps > 0) ? 1 : 0;
+        const int max_inner = (sweeps == 0) ? tune_inner0 : tune_inner;
+        const int cross_only = (sweeps > 0 && tune_cross) ? 1 : 0;
         for (int r = 0; r < g.rounds; r++) {
             if (g.single) {
                 QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram<<<dim3(ncg, g.npairs), NT, 0, st>>>(

@@ -1,0 +1,99 @@
+"""Public API on the GPU (-m gpu): Sequential.prepare_state / MPS methods through the
+reference's import paths, checked against the committed golden fixtures and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import qmprs_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_canonical.npz")
+
+
+def test_golden_fixtures_through_public_api(K):
+    from qmprs.synthesis.mps_encoding import Sequential
+    from qmprs_b200 import GateListCircuit
+    z = np.load(GOLDEN)
+    for key in ("c6", "c8", "c10"):
+        n, chi, L, S, seed = [int(x) for x in z[key + "_cfg"]]
+        psi = O.random_state(n, seed)
+        enc = Sequential(GateListCircuit)
+        circ = enc.prepare_state(psi, chi, num_layers=L, num_sweeps=S)
+        assert isinstance(circ, GateListCircuit) and circ.num_qubits == n
+        sv = circ.get_statevector()
+        assert abs(abs(np.vdot(psi, sv)) - float(z[key + "_fidelity"])) <= 1e-6       # north_star fidelity bar
+        assert np.abs(sv - z[key + "_state"]).max() <= 1e-6
+        kinds = np.array(enc.last_result["kinds"])
+        assert np.array_equal(kinds, z[key + "_kinds"])                                # same gate count / structure
+        g = enc.last_result["gates"]
+        assert np.abs(g - z[key + "_gates"]).max() <= 1e-6
+
+
+def test_mps_wrapper_methods(K):
+    """tests/primitives/test_mps.py:115-214 of the reference, on the device MPS."""
+    from qmprs.primitives import MPS
+    for n in (2, 4, 8):
+        psi = O.random_state(n, 20 + n)
+        mps = MPS(statevector=psi, bond_dimension=64)
+        assert mps.num_sites == n and len(mps) == n
+        assert np.abs(MPS.to_statevector(mps.mps).data - psi).max() < 1e-12
+        assert mps.is_normalized and mps.canonical_form == "right"
+    psi = O.random_state(8, 3)
+    mps = MPS(statevector=psi, bond_dimension=64)
+    mps.canonicalize("left")
+    assert mps.canonical_form == "left" and abs(mps.norm - 1) < 1e-12
+    assert np.abs(mps.mps.to_dense() - psi).max() < 1e-11
+    mps.canonicalize("right", normalize=True)
+    assert mps.canonical_form == "right" and abs(mps.norm - 1) < 1e-12
+    assert np.abs(mps.mps.to_dense() - psi).max() < 1e-11
+    for mode in ("left", "right"):
+        m2 = MPS(statevector=psi, bond_dimension=64)
+        m2.compress(max_bond_dimension=4, mode=mode)
+        assert m2.bond_dimension == 4 and max(m2.mps.bond_sizes()) == 4 and m2.canonical_form == mode
+        ref = O.build_mps(psi, 8, 4)
+        # both are optimal sequential truncations; the right-handed one must equal the oracle's state
+        if mode == "right":
+            assert np.abs(m2.mps.to_dense() - O.to_dense(ref)).max() < 1e-10
+    m3 = MPS(statevector=psi, bond_dimension=64)
+    m3.compress(max_bond_dimension=8)
+    assert m3.bond_dimension == 8 and max(m3.mps.bond_sizes()) == 8
+    with pytest.raises(ValueError):
+        m3.compress(mode="up")
+    with pytest.raises(ValueError):
+        m3.permute("plr")
+    with pytest.raises(ValueError):
+        m3.canonicalize("middle")
+
+
+def test_layer_methods_roundtrip(K):
+    from qmprs.primitives import MPS
+    psi = O.random_state(6, 31)
+    mps = MPS(statevector=psi, bond_dimension=64)
+    layer = mps.generate_bond_D_unitary_layer()
+    ref = O.generate_unitary_layer(O.chi2_truncate(O.right_canon(O.build_mps(psi, 6, 64), True), "canonical"),
+                                   "canonical")
+    for (s, e, ts), (s2, e2, gs) in zip(layer, ref):
+        assert (s, e) == (s2, e2)
+        for t, g in zip(ts, gs):
+            assert np.abs(t.data - g).max() <= 1e-8                                     # north_star gate bar
+    f0 = mps.fidelity_with_zero_state()
+    mps.apply_unitary_layer(layer, inverse=True)
+    f1 = mps.fidelity_with_zero_state()
+    assert abs(f1) > abs(f0)
+    mps.apply_unitary_layer(layer, inverse=False)
+    assert np.abs(mps.mps.to_dense() - psi).max() < 1e-9
+    small = MPS(statevector=psi, bond_dimension=2)
+    lay2 = small.generate_unitary_layer()
+    assert sum(len(ts) for _, _, ts in lay2) == 6
+
+
+def test_prepare_mps_does_not_modify_caller_mps(K):
+    from qmprs.primitives import MPS
+    from qmprs.synthesis.mps_encoding import Sequential
+    from qmprs_b200 import GateListCircuit
+    psi = O.random_state(6, 40)
+    mps = MPS(statevector=psi, bond_dimension=64)
+    before = mps.mps.to_dense()
+    Sequential(GateListCircuit).prepare_mps(mps, num_layers=2, num_sweeps=1)
+    assert np.abs(mps.mps.to_dense() - before).max() == 0.0

@@ -1,0 +1,82 @@
+"""Host-side logic (qmprs_b200/host.py) exercised on CPU with the numpy test double of the
+kernel interface (tests/fake_kernels.py): launch sequencing, reshapes, index conventions,
+rank plumbing, block structure, early break.  The CUDA kernels themselves are covered by
+the -m gpu tests."""
+import numpy as np
+import pytest
+
+from oracle import qmprs_oracle as O
+from qmprs_b200 import host
+from tests.fake_kernels import FakeKernels
+
+
+def gate_table(res):
+    return O.flatten_layers(res["layers"])
+
+
+@pytest.mark.parametrize("n,chi,L,S,seed", [(4, 4, 2, 0, 0), (6, 64, 3, 2, 1), (8, 32, 5, 3, 2), (8, 4, 4, 2, 3),
+                                           (10, 512, 6, 2, 4)])
+def test_pipeline_matches_oracle(n, chi, L, S, seed):
+    psi = O.random_state(n, seed)
+    ref = O.prepare(psi, n, chi, L, S, gauge="canonical")
+    # arbitrary SVD phases (as a Jacobi SVD returns) must not matter
+    out = host.prepare(FakeKernels(svd_phase_seed=seed + 10), psi, n, chi, L, S)
+    assert out["n_layers"] == ref["n_layers"]
+    g = out["gates"].reshape(-1, 16)
+    for idx, (_, _, _, site, G) in enumerate(gate_table(ref)):
+        assert np.abs(g[idx][: G.size] - G.reshape(-1)).max() < 1e-7
+    assert abs(out["fidelity"] - O.circuit_fidelity(psi, ref["layers"], n)) < 1e-9
+    assert host.bond_dims(out["mps"]) == O.bond_dims(ref["mps"])
+
+
+def test_recompute_and_stored_sweeps_agree():
+    psi = O.random_state(7, 5)
+    K = FakeKernels()
+    A = host.build_mps(K, K.from_host(psi), 7, 16)
+    gates, kinds, _ = host.disentangle(K, A, 3, 1 - 1e-6)
+    target = host.to_dense(K, A)
+    g1, g2 = gates.clone(), gates.clone()
+    host.optimize_layers(K, target, g1, kinds, 7, 2, stored=True)
+    host.optimize_layers(K, target, g2, kinds, 7, 2, stored=False)
+    assert np.abs(K.to_host(g1) - K.to_host(g2)).max() < 1e-10
+
+
+def test_block_structure_and_early_break():
+    h = np.array([1, 1]) / np.sqrt(2)
+    z = np.array([1.0, 0.0])
+    bell = np.zeros(4, dtype=complex); bell[0] = bell[3] = 1 / np.sqrt(2)
+    psi = np.array([1.0 + 0j])
+    for v in (bell, z, h, bell, z, h):
+        psi = np.kron(psi, v)
+    out = host.prepare(FakeKernels(), psi, 8, 32, 5, 0)
+    assert out["n_layers"] == 1                      # early break (sequential.py:390): already a product of blocks
+    assert host.blocks_from_kinds(out["kinds"][0]) == [(0, 1), (2, 2), (3, 3), (4, 5), (6, 6), (7, 7)]
+    assert out["fidelity"] > 1 - 1e-12
+
+
+def test_zero_overlap_and_to_dense():
+    K = FakeKernels()
+    psi = O.random_state(6, 8)
+    A = host.build_mps(K, K.from_host(psi), 6, 64)
+    dense = K.to_host(host.to_dense(K, A))
+    assert np.abs(dense - psi).max() < 1e-12
+    assert abs(host.zero_overlap(K, A) - np.conj(psi[0])) < 1e-12
+
+
+def test_forward_and_inverse_layer_are_inverse():
+    K = FakeKernels()
+    psi = O.random_state(6, 9)
+    A = host.build_mps(K, K.from_host(psi), 6, 64)
+    B = host.copy_mps(K, A)
+    gates, kinds = host.chi2_layer(K, B)
+    host.apply_inverse_layer(K, B, gates, kinds)
+    host.apply_inverse_layer(K, B, gates, kinds, inverse=False)
+    assert np.abs(K.to_host(host.to_dense(K, B)) - psi).max() < 1e-9
+
+
+def test_mirror_roundtrip():
+    K = FakeKernels()
+    A = host.build_mps(K, K.from_host(O.random_state(5, 1)), 5, 8)
+    M = host.mirror(K, host.mirror(K, A))
+    for a, b in zip(A, M):
+        assert a.shape == b.shape and np.abs(K.to_host(a) - K.to_host(b)).max() == 0.0

@@ -1,0 +1,176 @@
+"""CPU tests of the oracle: the reference's own test inequalities
+(tests/synthesis/mps_encoding/test_sequential_encoding.py, tests/primitives/test_mps.py),
+its published statistics (README.md:59-70) and the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+from scipy import linalg as sla
+
+from oracle import qmprs_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_canonical.npz")
+
+
+def fid(psi, res, n):
+    return O.circuit_fidelity(psi, res["layers"], n)
+
+
+@pytest.mark.parametrize("gauge", ["verbatim", "canonical"])
+def test_reference_inequality_8q_32_layers(gauge):
+    # test_sequential_encoding.py:50-67: 8 qubits, chi=32, 32 layers -> 1 - fidelity < 1e-2
+    for seed in range(3):
+        psi = O.random_state(8, seed)
+        res = O.prepare(psi, 8, 32, 32, 0, gauge=gauge)
+        assert 1 - fid(psi, res, 8) < 1e-2
+
+
+def partial_entanglement_state():
+    # test_sequential_encoding.py:91-121: H(0) CX(0,3) H(4) H(5) CX(5,7) on 8 qubits (little endian)
+    n = 8
+    psi = np.zeros(2 ** n, dtype=complex)
+    for b0 in (0, 1):
+        for b4 in (0, 1):
+            for b5 in (0, 1):
+                bits = [0] * n
+                bits[0] = b0; bits[3] = b0; bits[4] = b4; bits[5] = b5; bits[7] = b5
+                psi[sum(b << q for q, b in enumerate(bits))] = 1
+    return psi / np.linalg.norm(psi)
+
+
+@pytest.mark.parametrize("gauge", ["verbatim", "canonical"])
+def test_reference_partial_entanglement_blocks(gauge):
+    psi = partial_entanglement_state()
+    res = O.prepare(psi, 8, 32, 1, 0, gauge=gauge)
+    assert fid(psi, res, 8) > 0.99
+    blocks = [(s, e) for s, e, _ in res["layers"][0]]
+    # sites = reversed qubits: qubits {5,7} -> sites 0..2, qubit 4 -> site 3, qubits {0,3} -> sites 4..7
+    assert blocks == [(0, 2), (3, 3), (4, 7)]
+    n2, n1 = O.count_gates(res["layers"])
+    assert (n2, n1) == (5, 3)
+
+
+def test_reference_small_ghz_one_sweep():
+    # test_sequential_encoding.py:123-155: 4 qubits, GHZ-like + H(3), 1 layer, 1 sweep
+    n = 4
+    psi = np.zeros(2 ** n, dtype=complex)
+    for b in (0, 1):
+        for h in (0, 1):
+            psi[(b << 0) | (b << 1) | (b << 2) | (h << 3)] = 1
+    psi /= np.linalg.norm(psi)
+    res = O.prepare(psi, 4, 16, 1, 1, gauge="canonical")
+    assert fid(psi, res, 4) > 0.99
+    assert sum(O.count_gates(res["layers"])) <= 4
+
+
+def test_reference_monotone_in_layers_and_sweeps():
+    psi = O.random_state(8, 5)
+    prev = 0.0
+    for L in range(1, 8):
+        f = fid(psi, O.prepare(psi, 8, 64, L, 0, gauge="canonical"), 8)
+        assert f >= prev - 1e-9
+        prev = f
+    prev = 0.0
+    for S in range(0, 6):
+        f = fid(psi, O.prepare(psi, 8, 64, 6, S, gauge="canonical"), 8)
+        assert f >= prev - 1e-9
+        prev = f
+
+
+def test_readme_statistic():
+    # README.md:59-70: 10 qubits, 15 layers, chi=512, 50 sweeps -> fidelity 0.98676 (unseeded)
+    fs = []
+    for seed in (0, 1):
+        psi = O.random_state(10, seed)
+        res = O.prepare(psi, 10, 512, 15, 50, gauge="verbatim")
+        fs.append(fid(psi, res, 10))
+        assert O.count_gates(res["layers"]) == (135, 15)
+    assert abs(np.mean(fs) - 0.98676) < 5e-3
+
+
+def test_statevector_roundtrip_and_truncation():
+    # test_mps.py:115-138: to_statevector(from_statevector) reproduces the state when chi is not binding
+    for n in (2, 4, 8):
+        psi = O.random_state(n, n)
+        A = O.build_mps(psi, n, 64)
+        assert np.abs(O.to_dense(A) - psi).max() < 1e-12
+    psi = O.random_state(8, 1)
+    A = O.build_mps(psi, 8, 4)
+    assert max(O.bond_dims(A)) == 4
+    assert abs(O.mps_norm(A) - np.linalg.norm(O.to_dense(A))) < 1e-12
+
+
+def test_trim_rules():
+    s = np.array([1.0, 1e-3, 1e-6, 1e-9, 1e-12])
+    assert O.trim(s, 1e-10, "rel")[0] == 4
+    n, f = O.trim(s, 1e-10, "rsum2")
+    assert n == 2 and f > 1.0
+    assert O.trim(s, 1e-10, "rel", 2)[0] == 2
+    assert O.trim(np.array([0.5]), 1e-10, "rsum2") == (1, 1.0)
+
+
+def test_householder_null_space_equals_scipy():
+    rng = np.random.default_rng(0)
+    for shape in [(1, 2), (1, 4), (2, 4)]:
+        for _ in range(200):
+            M = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+            assert np.abs(sla.null_space(M) - O.null_space_householder(M)).max() < 1e-13
+
+
+def test_canonical_mode_is_gauge_invariant(monkeypatch):
+    """Random phases injected into every SVD must not change the canonical result."""
+    psi = O.random_state(8, 2)
+    ref = O.prepare(psi, 8, 32, 4, 3, gauge="canonical")
+    real_svd = np.linalg.svd
+    rng = np.random.default_rng(7)
+
+    def noisy(a, full_matrices=True, **kw):
+        u, s, vh = real_svd(a, full_matrices=full_matrices, **kw)
+        ph = np.exp(2j * np.pi * rng.random(s.size))
+        u = u.copy(); vh = vh.copy()
+        u[:, : s.size] *= ph[None, :]
+        vh[: s.size] *= np.conj(ph)[:, None]
+        return u, s, vh
+
+    monkeypatch.setattr(np.linalg, "svd", noisy)
+    got = O.prepare(psi, 8, 32, 4, 3, gauge="canonical")
+    monkeypatch.undo()
+    for (_, _, _, _, g0), (_, _, _, _, g1) in zip(O.flatten_layers(ref["layers"]), O.flatten_layers(got["layers"])):
+        assert np.abs(g0 - g1).max() < 1e-8
+
+
+def test_canonical_polar_completion_is_basis_independent():
+    rng = np.random.default_rng(3)
+    for r in (1, 2, 3):
+        a = rng.normal(size=(4, r)) + 1j * rng.normal(size=(4, r))
+        b = rng.normal(size=(r, 4)) + 1j * rng.normal(size=(r, 4))
+        E = a @ b
+        P = O.polar_unitary(E, "canonical")
+        assert np.abs(P @ np.conj(P).T - np.eye(4)).max() < 1e-12
+        # perturbing E at rounding level must not move P (LAPACK's own completion does move)
+        P2 = O.polar_unitary(E + 1e-17 * (rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))), "canonical")
+        assert np.abs(P - P2).max() < 1e-10
+    E = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    assert np.abs(O.polar_unitary(E, "canonical") - O.polar_unitary(E, "verbatim")).max() < 1e-12
+
+
+def test_emission_convention_matches_dense_contraction():
+    psi = O.random_state(6, 9)
+    res = O.prepare(psi, 6, 64, 3, 2, gauge="canonical")
+    sv = O.simulate_emitted(O.emit_gates(res["layers"], 6), 6)
+    assert np.abs(sv - O.circuit_state(res["layers"], 6)).max() < 1e-13
+
+
+def test_golden_fixture():
+    """Fixtures written by tests/golden/make_golden.py from this oracle (canonical gauge)."""
+    z = np.load(GOLDEN)
+    for key in ("c6", "c8", "c10"):
+        n, chi, L, S, seed = [int(x) for x in z[key + "_cfg"]]
+        psi = O.random_state(n, seed)
+        res = O.prepare(psi, n, chi, L, S, gauge="canonical")
+        g = np.zeros((L, n, 16), dtype=complex)
+        for li, _, _, site, G in O.flatten_layers(res["layers"]):
+            g[li, site, : G.size] = G.reshape(-1)
+        assert res["n_layers"] == L
+        assert abs(fid(psi, res, n) - float(z[key + "_fidelity"])) < 1e-9
+        assert np.abs(O.circuit_state(res["layers"], n) - z[key + "_state"]).max() < 1e-6
