@@ -21,12 +21,12 @@ extern "C" {
 
 /* ---- dense linear algebra ------------------------------------------------------ */
 
-/* C = alpha*A*B + beta*C (NN).  Replaces quimb tensordot/tensor_contract reached from
+/* C = alpha*op(A)*B + beta*C, op(A) = A (trans_a = 0) or A^H with A stored k x m (trans_a = 1).  Replaces quimb tensordot/tensor_contract reached from
  * qmprs/primitives/mps.py:270 (to_dense), :451-453 (compress), :968-971 (gate_split_).
  * batch > 1 strides the three operands. */
 int qm_zgemm(int m, int n, int k, double alpha_re, double alpha_im, const void* A, long long lda,
              const void* B, long long ldb, double beta_re, double beta_im, void* C, long long ldc,
-             int batch, long long strideA, long long strideB, long long strideC, void* stream);
+             int batch, long long strideA, long long strideB, long long strideC, int trans_a, void* stream);
 
 /* Thin SVD A = U diag(S) Vh by blocked one-sided Jacobi.  Replaces numpy/LAPACK zgesdd
  * behind quimb tensor_split: mps.py:242 (from_dense), :451-453, :928-931, :968-971;
@@ -65,9 +65,12 @@ int qm_site_gate(void* B, int l, int r, const void* G, int dagger, void* stream)
 
 /* chi=2 truncation bookkeeping for one bond (mps.py:881): picks n <= 2 by the 'rel'
  * cutoff, applies the canonical row-phase rule, writes the site tensor rows Csite[2][4],
- * the projector Vsel[4][2] and bond[0] = n. */
+ * the projector Vsel[4][2] and bond[0] = n.  squared = 1: S holds eigenvalues of T^H L T (squared
+ * singular values); then ambiguous[0] is set to 1 when s_1 <= ambiguous_rel * s_0, i.e. when the
+ * squared formulation cannot resolve the rank decision / second vector and the caller must redo
+ * the layer with the QR-based path. */
 int qm_chi2_select(const void* S, const void* Vh, long long ldvh, double cutoff, double tie, void* Csite,
-                   void* Vsel, void* bond, void* stream);
+                   void* Vsel, void* bond, int squared, double ambiguous_rel, void* ambiguous, void* stream);
 int qm_chi2_first(const void* T0, void* Csite, void* stream);
 
 /* Isometry -> unitary completion for all sites of a chi=2 MPS

@@ -19,7 +19,7 @@ _ip = ctypes.POINTER(ctypes.c_int)
 
 # name -> (restype, argtypes); mirrors include/qmprs_b200.h one to one
 SIGNATURES = {
-    "qm_zgemm": (_i, [_i, _i, _i, _d, _d, _vp, _ll, _vp, _ll, _d, _d, _vp, _ll, _i, _ll, _ll, _ll, _vp]),
+    "qm_zgemm": (_i, [_i, _i, _i, _d, _d, _vp, _ll, _vp, _ll, _d, _d, _vp, _ll, _i, _ll, _ll, _ll, _i, _vp]),
     "qm_svd_work_bytes": (_ll, [_i, _i]),
     "qm_svd": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _d, _i, _ip, _vp]),
     "qm_qr": (_i, [_i, _i, _vp, _ll, _vp, _vp]),
@@ -29,7 +29,7 @@ SIGNATURES = {
     "qm_scale_copy": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _i, _i, _vp]),
     "qm_theta_gate": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "qm_site_gate": (_i, [_vp, _i, _i, _vp, _i, _vp]),
-    "qm_chi2_select": (_i, [_vp, _vp, _ll, _d, _d, _vp, _vp, _vp, _vp]),
+    "qm_chi2_select": (_i, [_vp, _vp, _ll, _d, _d, _vp, _vp, _vp, _i, _d, _vp, _vp]),
     "qm_chi2_first": (_i, [_vp, _vp, _vp]),
     "qm_complete_unitaries": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _vp]),
     "qm_reverse3": (_i, [_vp, _vp, _i, _i, _vp]),

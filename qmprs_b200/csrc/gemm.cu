@@ -1,6 +1,6 @@
 // Complex128 GEMM on the FP64 tensor pipe (DMMA, mma.sync.m8n8k4.f64), row-major NN.
 //
-//   C[m x n] = alpha * A[m x k] * B[k x n] + beta * C
+//   C[m x n] = alpha * op(A)[m x k] * B[k x n] + beta * C,   op(A) = A or A^H
 //
 // This is the dense contraction under rows A2/A4/A6/A7 of SURVEY.md section 8
 // (quimb tensordot / gate_split contraction reached from qmprs/primitives/mps.py:928-931,
@@ -24,8 +24,10 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 
 // 256 threads = 8 warps laid out 4 (m) x 2 (n); warp tile 16 x 32 = 2 x 4 DMMA tiles.
+// TA: op(A) = A^H, A stored (k x m).
+template <bool TA>
 __global__ void __launch_bounds__(256)
-k_zgemm_nn(int m, int n, int k, cplx alpha, const cplx* __restrict__ A, long long lda,
+k_zgemm(int m, int n, int k, cplx alpha, const cplx* __restrict__ A, long long lda,
            const cplx* __restrict__ B, long long ldb, cplx beta, cplx* __restrict__ C, long long ldc,
            long long strideA, long long strideB, long long strideC) {
     __shared__ double sAr[BM * AS], sAi[BM * AS];
@@ -49,9 +51,13 @@ k_zgemm_nn(int m, int n, int k, cplx alpha, const cplx* __restrict__ A, long lon
     for (int k0 = 0; k0 < k; k0 += BK) {
         // A tile: BM x BK
         for (int idx = tid; idx < BM * BK; idx += 256) {
-            int r = idx / BK, c = idx % BK;
+            int r, c;
+            if (TA) { c = idx / BM; r = idx % BM; } else { r = idx / BK; c = idx % BK; }
             cplx v = mk(0.0, 0.0);
-            if (m0 + r < m && k0 + c < k) v = A[(long long)(m0 + r) * lda + (k0 + c)];
+            if (m0 + r < m && k0 + c < k) {
+                if (TA) v = cconj(A[(long long)(k0 + c) * lda + (m0 + r)]);
+                else v = A[(long long)(m0 + r) * lda + (k0 + c)];
+            }
             sAr[r * AS + c] = v.x;
             sAi[r * AS + c] = v.y;
         }
@@ -115,12 +121,20 @@ k_zgemm_nn(int m, int n, int k, cplx alpha, const cplx* __restrict__ A, long lon
 
 extern "C" int qm_zgemm(int m, int n, int k, double alpha_re, double alpha_im, const void* A, long long lda,
                         const void* B, long long ldb, double beta_re, double beta_im, void* C, long long ldc,
-                        int batch, long long strideA, long long strideB, long long strideC, void* stream) {
+                        int batch, long long strideA, long long strideB, long long strideC, int trans_a,
+                        void* stream) {
     if (m <= 0 || n <= 0 || batch <= 0) return 0;
     dim3 grid(ceil_div(n, BN), ceil_div(m, BM), batch);
-    QM_LAUNCH(QM_CLS_GEMM, (cudaStream_t)stream, k_zgemm_nn<<<grid, 256, 0, (cudaStream_t)stream>>>(m, n, k, mk(alpha_re, alpha_im), (const cplx*)A, lda,
-                                                        (const cplx*)B, ldb, mk(beta_re, beta_im), (cplx*)C, ldc,
-                                                        strideA, strideB, strideC));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (trans_a) {
+        QM_LAUNCH(QM_CLS_GEMM, st, (k_zgemm<true><<<grid, 256, 0, st>>>(
+            m, n, k, mk(alpha_re, alpha_im), (const cplx*)A, lda, (const cplx*)B, ldb, mk(beta_re, beta_im),
+            (cplx*)C, ldc, strideA, strideB, strideC)));
+    } else {
+        QM_LAUNCH(QM_CLS_GEMM, st, (k_zgemm<false><<<grid, 256, 0, st>>>(
+            m, n, k, mk(alpha_re, alpha_im), (const cplx*)A, lda, (const cplx*)B, ldb, mk(beta_re, beta_im),
+            (cplx*)C, ldc, strideA, strideB, strideC)));
+    }
     qm_prof_work(QM_CLS_GEMM, 8.0 * m * n * (double)k * batch);
     QM_CHECK_LAUNCH();
     return 0;

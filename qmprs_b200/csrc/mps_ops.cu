@@ -128,11 +128,14 @@ __global__ void k_site_gate(cplx* __restrict__ B, int l, int r, const cplx* __re
 // ---------------------------------------------------------------------------------
 __global__ void k_chi2_select(const double* __restrict__ S, const cplx* __restrict__ Vh, long long ldvh,
                               double cutoff, double tie, cplx* __restrict__ Csite, cplx* __restrict__ Vsel,
-                              int* __restrict__ bond) {
+                              int* __restrict__ bond, int squared, double amb_rel, int* __restrict__ ambiguous) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int n = 0;
-    double thr = cutoff * S[0];
-    for (int j = 0; j < 4; j++) n += (S[j] > thr) ? 1 : 0;
+    double sv[4];
+    for (int j = 0; j < 4; j++) sv[j] = squared ? sqrt(S[j] > 0.0 ? S[j] : 0.0) : S[j];
+    if (squared && ambiguous && sv[1] <= amb_rel * sv[0]) ambiguous[0] = 1;
+    double thr = cutoff * sv[0];
+    for (int j = 0; j < 4; j++) n += (sv[j] > thr) ? 1 : 0;
     if (n < 1) n = 1;
     if (n > 2) n = 2;
     for (int j = 0; j < 2; j++) {
@@ -365,9 +368,11 @@ extern "C" int qm_site_gate(void* B, int l, int r, const void* G, int dagger, vo
 }
 
 extern "C" int qm_chi2_select(const void* S, const void* Vh, long long ldvh, double cutoff, double tie, void* Csite,
-                              void* Vsel, void* bond, void* stream) {
-    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_chi2_select<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)S, (const cplx*)Vh, ldvh, cutoff, tie,
-                                                      (cplx*)Csite, (cplx*)Vsel, (int*)bond));
+                              void* Vsel, void* bond, int squared, double ambiguous_rel, void* ambiguous,
+                              void* stream) {
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_chi2_select<<<1, 32, 0, (cudaStream_t)stream>>>(
+        (const double*)S, (const cplx*)Vh, ldvh, cutoff, tie, (cplx*)Csite, (cplx*)Vsel, (int*)bond, squared,
+        ambiguous_rel, (int*)ambiguous));
     QM_CHECK_LAUNCH();
     return 0;
 }

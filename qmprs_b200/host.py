@@ -116,32 +116,40 @@ def normalize_site0(K, A):
 # --------------------------------------------------------------------------------------
 # A4 + A5  chi=2 truncation and unitary completion   mps.py:849-891, :565-847
 # --------------------------------------------------------------------------------------
-def chi2_layer(K, B, debug=None):
+def chi2_layer(K, B, debug=None, accurate=False):
     """Returns (gates [N,16] device, kinds list[int] host).  ``B`` is not modified
     (the reference works on a deepcopy, mps.py:878).
 
     The reference left-canonises the copy and then truncates bond by bond from the right
-    (QR, LQ, SVD of R.L keeping <= 2 values).  Here only the R factors of the left
-    sweep are formed (R_i with  B_0..B_i = Q R_i), and every truncation step is the SVD
-    of the (k x 4) matrix R_{i-1} T_i, T_i being site i contracted with the already
-    truncated right part; bonds are zero-padded to 2 so that all shapes are static and
-    the bond dimensions stay on the device until the block structure is read back.
+    (QR, LQ, SVD of R.L keeping <= 2 values).  Every truncation step only needs the two
+    leading right singular vectors of  R_{i-1} T_i  (k x 4), T_i being site i contracted
+    with the already truncated right part and R_{i-1} any square root of the left
+    environment L_{i-1} = sum_p B^H L B.  Bonds are zero-padded to 2 so that all shapes are
+    static and the bond dimensions stay on the device until the block structure is read.
+
+    Fast path: L_i by two DMMA GEMMs per site and the 4x4 Hermitian problem T^H L T.  It
+    squares the singular values, so when s_1 <= 1e-3 s_0 anywhere (rank decision at the
+    1e-10 cutoff or second vector not resolvable: product-like / structured states) the
+    layer is redone with the ``accurate`` path: R factors from Householder QR and the
+    SVD of R_{i-1} T_i itself.
     """
     N = len(B)
-    # left sweep, R factors only
-    Rs = [None] * (N - 1)
-    Rprev = None
+    facs = [None] * (N - 1)        # R_i (accurate) or L_i (fast)
+    prev = None
     for i in range(N - 1):
         l, _, r = B[i].shape
-        if Rprev is None:
-            M = B[i].reshape(l * 2, r)
+        if accurate:
+            M = B[i].reshape(l * 2, r) if prev is None else K.gemm(prev, B[i].reshape(l, 2 * r)).reshape(-1, r)
+            _, prev = K.qr(M, want_q=False)
         else:
-            M = K.gemm(Rprev, B[i].reshape(l, 2 * r)).reshape(-1, r)
-        _, Rprev = K.qr(M, want_q=False)
-        Rs[i] = Rprev
+            Bm = B[i].reshape(l * 2, r)
+            X = Bm if prev is None else K.gemm(prev, B[i].reshape(l, 2 * r)).reshape(l * 2, r)
+            prev = K.gemm(Bm, X, transA=True)              # L_i = B^H (L_{i-1} (x) 1) B
+        facs[i] = prev
     # right->left truncation with padded bond 2
     C = K.zeros((N, 8))
     bond = K.zeros((max(N - 1, 1),), dtype=_i32(K))
+    ambiguous = K.zeros((1,), dtype=_i32(K))
     b_last = B[N - 1].shape[0]
     T = K.zeros((b_last, 4))
     K.scale_copy(B[N - 1].reshape(b_last * 2, 1), out=T.reshape(b_last * 2, 2)[:, 0:1])
@@ -149,16 +157,23 @@ def chi2_layer(K, B, debug=None):
     Vh4 = K.zeros((4, 4))
     Vsel = K.zeros((4, 2))
     for i in range(N - 1, 0, -1):
-        M = K.gemm(Rs[i - 1], T)                       # (k x 4)
-        if M.shape[0] < 4:
-            S4.zero_()
-            Vh4.zero_()
-        K.svd(M, want_u=False, out_s=S4, out_vh=Vh4)
-        K.chi2_select(S4, Vh4, C[i], Vsel, bond[i - 1:i])
-        W = K.gemm(T, Vsel)                            # (b x 2)
+        M = K.gemm(facs[i - 1], T)                         # R T (k x 4)  or  L T (b x 4)
+        if accurate:
+            if M.shape[0] < 4:
+                S4.zero_()
+                Vh4.zero_()
+            K.svd(M, want_u=False, out_s=S4, out_vh=Vh4)
+            K.chi2_select(S4, Vh4, C[i], Vsel, bond[i - 1:i])
+        else:
+            H = K.gemm(T, M, transA=True)                  # T^H L T, 4 x 4 Hermitian PSD: SVD == eigen-decomposition
+            K.svd(H, want_u=False, out_s=S4, out_vh=Vh4)
+            K.chi2_select(S4, Vh4, C[i], Vsel, bond[i - 1:i], squared=True, ambiguous=ambiguous)
+        W = K.gemm(T, Vsel)                                # (b x 2)
         l0, _, b = B[i - 1].shape
         T = K.gemm(B[i - 1].reshape(l0 * 2, b), W).reshape(l0, 4)
     K.chi2_first(T, C[0])
+    if not accurate and K.read_int(ambiguous):
+        return chi2_layer(K, B, debug, accurate=True)
     gates, kinds, bad = K.complete_unitaries(C, bond, N)
     kinds_h = [int(x) for x in K.to_host(kinds)]
     if K.read_int(bad):
@@ -166,6 +181,7 @@ def chi2_layer(K, B, debug=None):
     if debug is not None:
         debug["C"] = C
         debug["bond"] = bond
+        debug["accurate"] = accurate
     return gates, kinds_h
 
 

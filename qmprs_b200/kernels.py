@@ -21,6 +21,7 @@ CUTOFF = 1e-10
 TIE_REL = 1e-6
 SIGN_TOL = 1e-12
 MODE_REL, MODE_RSUM2 = 0, 1
+CHI2_AMBIGUOUS_REL = 1e-3   # squared chi=2 path: s_1 <= 1e-3 s_0 -> redo the layer with the QR-based path
 
 
 def _p(t):
@@ -76,14 +77,19 @@ class CudaKernels:
         return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
 
     # ---- dense linear algebra -----------------------------------------------------
-    def gemm(self, A, B, out=None):
-        m, k = A.shape
+    def gemm(self, A, B, out=None, transA=False):
+        """out = op(A) @ B, op(A) = A or A^H (A stored k x m when transA)."""
+        if transA:
+            k, m = A.shape
+        else:
+            m, k = A.shape
         k2, n = B.shape
         assert k == k2
         if out is None:
             out = self.empty((m, n))
         self._check(self.lib.qm_zgemm(m, n, k, 1.0, 0.0, _p(A), self._ld(A), _p(B), self._ld(B), 0.0, 0.0,
-                                      _p(out), self._ld(out), 1, 0, 0, 0, self._stream()), "qm_zgemm")
+                                      _p(out), self._ld(out), 1, 0, 0, 0, 1 if transA else 0, self._stream()),
+                    "qm_zgemm")
         return out
 
     def svd(self, A, want_u=True, want_vh=True, out_s=None, out_vh=None):
@@ -142,9 +148,10 @@ class CudaKernels:
     def site_gate(self, B, l, r, G, dagger):
         self._check(self.lib.qm_site_gate(_p(B), l, r, _p(G), 1 if dagger else 0, self._stream()), "qm_site_gate")
 
-    def chi2_select(self, S4, Vh4, Csite, Vsel, bond_slot):
+    def chi2_select(self, S4, Vh4, Csite, Vsel, bond_slot, squared=False, ambiguous=None):
         self._check(self.lib.qm_chi2_select(_p(S4), _p(Vh4), 4, CUTOFF, TIE_REL, _p(Csite), _p(Vsel), _p(bond_slot),
-                                            self._stream()), "qm_chi2_select")
+                                            1 if squared else 0, CHI2_AMBIGUOUS_REL, _p(ambiguous), self._stream()),
+                    "qm_chi2_select")
 
     def chi2_first(self, T0, Csite):
         self._check(self.lib.qm_chi2_first(_p(T0), _p(Csite), self._stream()), "qm_chi2_first")

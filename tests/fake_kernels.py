@@ -52,8 +52,9 @@ class FakeKernels:
         pass
 
     # ---- linear algebra ----
-    def gemm(self, A, B, out=None):
-        r = torch.as_tensor(_np(A) @ _np(B))
+    def gemm(self, A, B, out=None, transA=False):
+        a = np.conj(_np(A)).T if transA else _np(A)
+        r = torch.as_tensor(a @ _np(B))
         if out is None:
             return r.contiguous()
         out.copy_(r)
@@ -117,8 +118,12 @@ class FakeKernels:
         y = np.einsum("op,lpr->lor", g, _np(B).reshape(l, 2, r))
         B.copy_(torch.as_tensor(y.reshape(B.shape)))
 
-    def chi2_select(self, S4, Vh4, Csite, Vsel, bond_slot):
+    def chi2_select(self, S4, Vh4, Csite, Vsel, bond_slot, squared=False, ambiguous=None):
         s = _np(S4)
+        if squared:
+            s = np.sqrt(np.maximum(s, 0.0))
+            if ambiguous is not None and s[1] <= 1e-3 * s[0]:
+                ambiguous[0] = 1
         vh = _np(Vh4)
         n = int(np.count_nonzero(s > CUTOFF * s[0]))
         n = min(max(n, 1), 2)

@@ -84,6 +84,7 @@ def test_layer_methods_roundtrip(K):
     mps.apply_unitary_layer(layer, inverse=False)
     assert np.abs(mps.mps.to_dense() - psi).max() < 1e-9
     small = MPS(statevector=psi, bond_dimension=2)
+    small.canonicalize("right", normalize=True)          # as mps.py:881-889 does before generating
     lay2 = small.generate_unitary_layer()
     assert sum(len(ts) for _, _, ts in lay2) == 6
 

@@ -22,6 +22,15 @@ def test_zgemm(K, m, n, k):
     assert np.abs(c - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
 
 
+def test_zgemm_conj_transpose(K):
+    rng = np.random.default_rng(6)
+    for m, n, k in [(4, 4, 700), (96, 130, 65), (512, 512, 1024), (1, 3, 2)]:
+        a, b = crand(rng, k, m), crand(rng, k, n)
+        c = K.to_host(K.gemm(K.from_host(a), K.from_host(b), transA=True))
+        ref = np.conj(a).T @ b
+        assert np.abs(c - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
 def test_zgemm_strided_views(K):
     rng = np.random.default_rng(5)
     big = crand(rng, 40, 2, 30)
