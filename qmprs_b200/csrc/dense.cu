@@ -210,13 +210,92 @@ __device__ void polar_factor(cplx M[4][4], int d) {
         }
 }
 
-__device__ void polar_conj(const cplx* E, int d, cplx* out) {
+__device__ __noinline__ void polar_conj(const cplx* E, int d, cplx* out) {
     cplx M[4][4];
     for (int i = 0; i < d; i++)
         for (int j = 0; j < d; j++) M[i][j] = E[i * d + j];
     polar_factor<true>(M, d);
     for (int i = 0; i < d; i++)
         for (int j = 0; j < d; j++) out[i * d + j] = cconj(M[i][j]);
+}
+
+// ---------------------------------------------------------------------------------
+// Warp-cooperative version of polar_conj: lanes 0-15 hold A[i][j] (i = lane/4 % 4, j = lane%4),
+// lanes 16-31 hold V[i][j].  The three perfect matchings of the four columns are the xor
+// patterns 1,2,3, so the partner column of a lane is lane^m; Gram sums over the rows are
+// xor-4 / xor-8 shuffles; the two disjoint rotations of a round run concurrently.  A 2x2
+// input is embedded as diag(E, I).  Rank-deficient inputs (rare: 1 + L of the N*L gates)
+// fall back to the single-thread routine so that the canonical completion stays in one place.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ cplx shfl_xor_c(cplx v, int m) {
+    return mk(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+
+__device__ void polar_conj_warp(const cplx* Es, int d, cplx* gate_out, cplx* scratch /* smem, 32 cplx */) {
+    const int lane = threadIdx.x & 31;
+    const int half = lane >> 4, i = (lane >> 2) & 3, j = lane & 3;
+    cplx x;
+    if (half == 0) x = (i < d && j < d) ? Es[i * d + j] : mk(i == j ? 1.0 : 0.0, 0.0);
+    else x = mk(i == j ? 1.0 : 0.0, 0.0);
+    const double tol2 = 4e-30;
+    int quiet = 0;                                   // consecutive rounds without a rotation
+    for (int it = 0; it < 90 && quiet < 3; it++) {
+        const int m = (it % 3) + 1;
+        cplx y = shfl_xor_c(x, m);                   // partner column, same row, same matrix
+        const bool isp = j < (j ^ m);
+        double na = cabs2(x), nb = cabs2(y);
+        cplx gg = isp ? ccmul(x, y) : ccmul(y, x);   // conj(a_p) a_q contribution of this row
+        na += __shfl_xor_sync(0xffffffffu, na, 4); na += __shfl_xor_sync(0xffffffffu, na, 8);
+        nb += __shfl_xor_sync(0xffffffffu, nb, 4); nb += __shfl_xor_sync(0xffffffffu, nb, 8);
+        gg = cadd(gg, shfl_xor_c(gg, 4)); gg = cadd(gg, shfl_xor_c(gg, 8));
+        // the V half takes the sums of the A half
+        double na2 = __shfl_xor_sync(0xffffffffu, na, 16), nb2 = __shfl_xor_sync(0xffffffffu, nb, 16);
+        cplx gg2 = shfl_xor_c(gg, 16);
+        if (half) { na = na2; nb = nb2; gg = gg2; }
+        const double a = isp ? na : nb, b = isp ? nb : na;      // |a_p|^2, |a_q|^2
+        const double mag2 = cabs2(gg);
+        const bool rot = (a > 0.0 && b > 0.0 && mag2 > tol2 * a * b);
+        if (rot) {
+            double imag = rsqrt(mag2);
+            double zeta = 0.5 * (b - a) * imag;
+            double z1 = 1.0 + zeta * zeta;
+            double den = fabs(zeta) + z1 * rsqrt(z1);
+            double wv = rsqrt(den * den + 1.0);
+            double c = den * wv, sn = copysign(wv, zeta);
+            cplx e = mk(gg.x * imag, gg.y * imag);              // e^{i phi}
+            // x_p' = c x_p - s e^{-i phi} x_q ;  x_q' = s e^{i phi} x_p + c x_q
+            if (isp) x = csub(cscale(x, c), cmul(cscale(cconj(e), sn), y));
+            else x = cadd(cmul(cscale(e, sn), y), cscale(x, c));
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, rot);
+        quiet = any ? 0 : quiet + 1;
+    }
+    // column norms of A, null detection
+    double n2 = cabs2(x);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 4); n2 += __shfl_xor_sync(0xffffffffu, n2, 8);
+    double sig = sqrt(n2);
+    double smax = sig;
+    smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, 1));
+    smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, 2));
+    const bool isnull = (half == 0) && (!(sig > 1e-13 * smax) || smax == 0.0);
+    if (__ballot_sync(0xffffffffu, isnull)) {
+        if (lane == 0) {
+            cplx E[16], P[16];
+            for (int k = 0; k < d * d; k++) E[k] = Es[k];
+            polar_conj(E, d, P);
+            for (int k = 0; k < d * d; k++) gate_out[k] = P[k];
+        }
+        return;
+    }
+    if (half == 0) x = cscale(x, 1.0 / sig);
+    scratch[lane] = x;                                // [0..15] = U, [16..31] = V
+    __syncwarp();
+    if (lane < 16 && i < d && j < d) {
+        cplx sacc = mk(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) cfmac(sacc, scratch[i * 4 + k], scratch[16 + j * 4 + k]);   // U V^H
+        gate_out[i * d + j] = cconj(sacc);
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -339,11 +418,7 @@ k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int 
         Pm[threadIdx.x] = Gpend[b * PD + a];                  // M = G^T : tbar'[b] = sum_o G[o][b] tbar[o]
     }
     __syncthreads();
-    cplx P[PD > 0 ? PD * PD : 1];
-    if (PD > 0) {
-#pragma unroll
-        for (int i = 0; i < PD * PD; i++) P[i] = Pm[i];
-    }
+    const cplx* P = Pm;                      // broadcast reads from shared memory (keeps 64 registers free)
     double acc[32];
 #pragma unroll
     for (int i = 0; i < 32; i++) acc[i] = 0.0;
@@ -395,10 +470,10 @@ k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int 
 #pragma unroll
         for (int w = 0; w < NT / 32; w++) ssum += wsum[w][lane];
         ((double*)partials)[(long long)blockIdx.x * 32 + lane] = ssum;
-        __threadfence();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();                     // cumulative: publishes the CTA's partials before the ticket
         unsigned int done = atomicAdd(counter, 1u);
         s_last = (done == gridDim.x - 1);
     }
@@ -425,15 +500,14 @@ k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int 
         if (threadIdx.x < CD * CD) Es[threadIdx.x] = mk(Ep[2 * threadIdx.x], Ep[2 * threadIdx.x + 1]);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        cplx E[16], Pout[16];
-        for (int i = 0; i < CD * CD; i++) E[i] = Es[i];
-        polar_conj(E, CD, Pout);
-        for (int i = 0; i < CD * CD; i++) gate_out[i] = Pout[i];
-        if (env_out)
-            for (int i = 0; i < CD * CD; i++) env_out[i] = E[i];
-        *counter = 0u;
-        __threadfence();
+    __shared__ cplx pol_scratch[32];
+    if (threadIdx.x < 32) {
+        polar_conj_warp(Es, CD, gate_out, pol_scratch);
+        if (env_out && threadIdx.x < CD * CD) env_out[threadIdx.x] = Es[threadIdx.x];
+        if (threadIdx.x == 0) {
+            *counter = 0u;
+            __threadfence();
+        }
     }
 }
 

@@ -153,8 +153,8 @@ constexpr int GS = PMAX + 1;                              // row stride of the s
 constexpr size_t EIG_SMEM = 2ull * PMAX * GS * sizeof(cplx);   // g, q
 
 __global__ void __launch_bounds__(NT)
-k_eig(double* __restrict__ G, cplx* __restrict__ Qout, int nrows, double tol2, int max_inner, int cross_only,
-      int round, int nbp, int single, int* __restrict__ notconv, int* __restrict__ rotated,
+k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, double tol2, int max_inner,
+      int cross_only, int round, int nbp, int single, int* __restrict__ notconv, int* __restrict__ rotated,
       double* __restrict__ sig2) {
     extern __shared__ __align__(16) unsigned char eig_smem[];
     cplx* g = (cplx*)eig_smem;                            // [PMAX][GS]
@@ -163,15 +163,43 @@ k_eig(double* __restrict__ G, cplx* __restrict__ Qout, int nrows, double tol2, i
     __shared__ cplx roff[PMAX / 2];
     __shared__ int rpp[PMAX / 2], rqq[PMAX / 2], ract[PMAX / 2];
     __shared__ int s_any, s_sweep, s_off, s_mc, s_mi, s_round;
+    __shared__ unsigned char sched[(PMAX - 1) * (PMAX / 2) * 2];     // round-robin schedule (p,q) per round/slot
     const int tid = threadIdx.x, pair = blockIdx.x;
     const int n = nrows, ne = n + (n & 1), np = ne / 2;
-    double* Gp = G + (long long)pair * PMAX * PMAX * 2;
-    for (int e = tid; e < n * n; e += NT) {
-        int i = e / n, j = e % n;
-        g[i * GS + j] = mk(Gp[2 * e], Gp[2 * e + 1]);
-        Gp[2 * e] = 0.0; Gp[2 * e + 1] = 0.0;
-        q[i * GS + j] = mk(i == j ? 1.0 : 0.0, 0.0);
+    // nchunks > 0: G holds per-chunk partial Gram matrices [pair][chunk][PMAX*PMAX*2] written with plain
+    // stores by k_gram_mma (summed here in fixed order); nchunks == 0: one atomically accumulated matrix
+    // that is re-zeroed here (single-block path).
+    if (nchunks > 0) {
+        const double* Gp = G + (long long)pair * nchunks * PMAX * PMAX * 2;
+        for (int e = tid; e < n * n; e += NT) {
+            double re = 0.0, im = 0.0;
+            for (int c = 0; c < nchunks; c++) {
+                const double2 v = *(const double2*)(Gp + (long long)c * PMAX * PMAX * 2 + 2 * e);
+                re += v.x; im += v.y;
+            }
+            int i = e / n, j = e % n;
+            g[i * GS + j] = mk(re, im);
+            q[i * GS + j] = mk(i == j ? 1.0 : 0.0, 0.0);
+        }
+    } else {
+        double* Gp = G + (long long)pair * PMAX * PMAX * 2;
+        for (int e = tid; e < n * n; e += NT) {
+            int i = e / n, j = e % n;
+            g[i * GS + j] = mk(Gp[2 * e], Gp[2 * e + 1]);
+            Gp[2 * e] = 0.0; Gp[2 * e + 1] = 0.0;
+            q[i * GS + j] = mk(i == j ? 1.0 : 0.0, 0.0);
+        }
     }
+    for (int e = tid; e < (ne - 1) * np; e += NT) {
+        int r = e / np, k = e % np, a, b;
+        if (ne == 2) { a = 0; b = 1; } else circle_pair(r, k, ne, a, b);
+        sched[2 * e] = (unsigned char)a;
+        sched[2 * e + 1] = (unsigned char)b;
+    }
+    // per-thread work items of the update phase do not depend on the round
+    const int blk_k = tid / np, blk_l = tid % np;            // 2x2 block (valid if tid < np*np; np*np <= NT)
+    const int q_k0 = tid / n, q_c0 = tid % n;                // Q items tid and tid + NT
+    const int q_k1 = (tid + NT) / n, q_c1 = (tid + NT) % n;
     if (tid == 0) { s_any = 0; s_off = 0; s_mc = 0; s_mi = 0; }
     __syncthreads();
     // Fresh Gram matrix: already diagonal to tolerance?  Largest relative off-diagonal
@@ -213,8 +241,7 @@ k_eig(double* __restrict__ G, cplx* __restrict__ Qout, int nrows, double tol2, i
                 if (tid < np) {
                     int p, qq;
                     if (cross) { p = tid; qq = BSZ + ((tid + r) & (BSZ - 1)); }
-                    else if (ne == 2) { p = 0; qq = 1; }
-                    else circle_pair(r, tid, ne, p, qq);
+                    else { p = sched[2 * (r * np + tid)]; qq = sched[2 * (r * np + tid) + 1]; }
                     bool act = false;
                     double c = 1.0, s = 0.0;
                     cplx u = mk(0.0, 0.0);
@@ -224,13 +251,14 @@ k_eig(double* __restrict__ G, cplx* __restrict__ Qout, int nrows, double tol2, i
                         double mag2 = cabs2(gpq);
                         if (a > 0.0 && b > 0.0 && mag2 > tol2 * a * b) {
                             // reciprocal square roots instead of sqrt/div chains (latency-bound step)
+                            // t = sign/(|z| + sqrt(1+z^2)) =: sign/den;  c = den/sqrt(den^2+1), s = sign/sqrt(den^2+1)
                             double imag = rsqrt(mag2);
                             double zeta = 0.5 * (b - a) * imag;
                             double z1 = 1.0 + zeta * zeta;
-                            double rt = z1 * rsqrt(z1);                       // sqrt(1 + zeta^2)
-                            double t = copysign(1.0, zeta) / (fabs(zeta) + rt);
-                            c = rsqrt(1.0 + t * t);
-                            s = c * t;
+                            double den = fabs(zeta) + z1 * rsqrt(z1);
+                            double wv = rsqrt(den * den + 1.0);
+                            c = den * wv;
+                            s = copysign(wv, zeta);
                             u = mk(gpq.x * imag, gpq.y * imag);
                             act = true;
                         }
@@ -244,8 +272,8 @@ k_eig(double* __restrict__ G, cplx* __restrict__ Qout, int nrows, double tol2, i
                 if (s_round) {
                     // G' = R G R^H by 2x2 blocks: block (k,l) = rows {p_k,q_k} x cols {p_l,q_l} depends only
                     // on the same block of G (4 loads, 4 stores).  In place: every block is owned by one thread.
-                    for (int blk = tid; blk < np * np; blk += NT) {
-                        const int k = blk / np, l = blk % np;
+                    if (tid < np * np) {
+                        const int k = blk_k, l = blk_l;
                         const int pk = rpp[k], qk = rqq[k], pl = rpp[l], ql = rqq[l];
                         const bool vk = qk < n, vl = ql < n;           // dummy partner (odd n): single row/col
                         const double ck = rcc[k], cl = rcc[l];
@@ -274,9 +302,10 @@ k_eig(double* __restrict__ G, cplx* __restrict__ Qout, int nrows, double tol2, i
                         if (vk && vl) g[qk * GS + ql] = b11;
                     }
                     // Q' = R Q : rows p_k, q_k
-                    for (int item = tid; item < np * n; item += NT) {
-                        const int k = item / n, col = item % n;
-                        if (!ract[k]) continue;
+#pragma unroll
+                    for (int rep = 0; rep < 2; rep++) {
+                        const int k = rep ? q_k1 : q_k0, col = rep ? q_c1 : q_c0;
+                        if (k >= np || !ract[k]) continue;
                         const int pk = rpp[k], qk = rqq[k];
                         const double ck = rcc[k];
                         const cplx ok = roff[k];
@@ -310,79 +339,54 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// G = W_pair W_pair^H over a column chunk.  Each warp owns a 4-column slice per step; only
-// the upper block triangle of 8x8 tiles is accumulated (G is Hermitian).
+// G = W_pair W_pair^H over a column chunk.  Each of the 8 warps owns two of the sixteen 8x8 output
+// tiles (tile row w/2, tile columns 2(w%2), 2(w%2)+1) and runs over the whole chunk, so there is no
+// cross-warp reduction: the warp stores its tiles straight into the chunk's partial slab, which
+// k_eig sums over chunks.  A lane's 16-byte load W[row][k] is both an A and a B operand.
 __global__ void __launch_bounds__(NT)
 k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, int round, int nbp,
            double* __restrict__ G) {
-    __shared__ double gs[PMAX * PMAX * 2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = blockIdx.y;
     const int g = lane >> 2, t = lane & 3;
     int bi, bj;
     circle_pair(round, pair, nbp, bi, bj);
-    const cplx* rowp[4];
-#pragma unroll
-    for (int mt = 0; mt < 4; mt++) {
-        int r = mt * 8 + g;
-        rowp[mt] = W + (long long)(r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ)) * ldw;
-    }
-    for (int i = tid; i < PMAX * PMAX * 2; i += NT) gs[i] = 0.0;
-    double cr[10][2], ci[10][2];
-#pragma unroll
-    for (int i = 0; i < 10; i++) { cr[i][0] = cr[i][1] = ci[i][0] = ci[i][1] = 0.0; }
+    const int mt = warp >> 1, nt0 = (warp & 1) * 2;
+    auto rowptr = [&](int r) { return W + (long long)(r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ)) * ldw; };
+    const cplx* pa = rowptr(mt * 8 + g);
+    const cplx* pb0 = rowptr(nt0 * 8 + g);
+    const cplx* pb1 = rowptr(nt0 * 8 + 8 + g);
+    double cr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, ci[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     const long long c0 = (long long)blockIdx.x * chunk;
     const long long c1 = (c0 + chunk < len) ? c0 + chunk : len;
-    __syncthreads();
-#pragma unroll 2
-    for (long long k0 = c0 + warp * 4; k0 < c1; k0 += 32) {
-        long long col = k0 + t;
-        bool ok = col < c1;
-        cplx w[4];
-#pragma unroll
-        for (int mt = 0; mt < 4; mt++) w[mt] = ok ? rowp[mt][col] : mk(0.0, 0.0);
-        int idx = 0;
-#pragma unroll
-        for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-            for (int nt = mt; nt < 4; nt++) {
-                // W_m conj(W_n): re = ar*br + ai*bi ; im = ai*br - ar*bi
-                dmma884(cr[idx][0], cr[idx][1], w[mt].x, w[nt].x);
-                dmma884(cr[idx][0], cr[idx][1], w[mt].y, w[nt].y);
-                dmma884(ci[idx][0], ci[idx][1], w[mt].y, w[nt].x);
-                dmma884(ci[idx][0], ci[idx][1], -w[mt].x, w[nt].y);
-                idx++;
-            }
+#pragma unroll 4
+    for (long long k0 = c0; k0 < c1; k0 += 4) {
+        const long long col = k0 + t;
+        const bool ok = col < c1;
+        const cplx wa = ok ? pa[col] : mk(0.0, 0.0);
+        const cplx wb0 = ok ? pb0[col] : mk(0.0, 0.0);
+        const cplx wb1 = ok ? pb1[col] : mk(0.0, 0.0);
+        // W_m conj(W_n): re = ar*br + ai*bi ; im = ai*br - ar*bi
+        dmma884(cr[0][0], cr[0][1], wa.x, wb0.x);
+        dmma884(cr[0][0], cr[0][1], wa.y, wb0.y);
+        dmma884(ci[0][0], ci[0][1], wa.y, wb0.x);
+        dmma884(ci[0][0], ci[0][1], -wa.x, wb0.y);
+        dmma884(cr[1][0], cr[1][1], wa.x, wb1.x);
+        dmma884(cr[1][0], cr[1][1], wa.y, wb1.y);
+        dmma884(ci[1][0], ci[1][1], wa.y, wb1.x);
+        dmma884(ci[1][0], ci[1][1], -wa.x, wb1.y);
     }
-    {
-        int idx = 0;
+    double* Gp = G + ((long long)pair * gridDim.x + blockIdx.x) * PMAX * PMAX * 2;
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-            for (int nt = mt; nt < 4; nt++) {
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    int row = mt * 8 + g, col = nt * 8 + 2 * t + e;
-                    atomicAdd(&gs[(row * PMAX + col) * 2], cr[idx][e]);
-                    atomicAdd(&gs[(row * PMAX + col) * 2 + 1], ci[idx][e]);
-                }
-                idx++;
-            }
-    }
-    __syncthreads();
-    double* Gp = G + (long long)pair * PMAX * PMAX * 2;
-    for (int e = tid; e < PMAX * PMAX; e += NT) {
-        int i = e / PMAX, j = e % PMAX;
-        double re, im;
-        if ((i >> 3) <= (j >> 3)) { re = gs[(i * PMAX + j) * 2]; im = gs[(i * PMAX + j) * 2 + 1]; }
-        else { re = gs[(j * PMAX + i) * 2]; im = -gs[(j * PMAX + i) * 2 + 1]; }
-        atomicAdd(&Gp[2 * e], re);
-        atomicAdd(&Gp[2 * e + 1], im);
+    for (int j = 0; j < 2; j++) {
+        const int row = mt * 8 + g, col = (nt0 + j) * 8 + 2 * t;
+        double* dst = Gp + ((long long)row * PMAX + col) * 2;
+        *(double4*)dst = make_double4(cr[j][0], ci[j][0], cr[j][1], ci[j][1]);
     }
 }
 
 // Wext[rows] <- Q Wext[rows]: each warp owns 8-column strips, loads the 32x8 strip as B
 // fragments, multiplies by Q (A fragments from padded shared planes) and stores in place.
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 2)
 k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, int round, int nbp,
             const cplx* __restrict__ Q, const int* __restrict__ rotated) {
     const int pair = blockIdx.y;
@@ -402,15 +406,31 @@ k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, int 
     __syncthreads();
     const long long c0 = (long long)blockIdx.x * chunk;
     const long long c1 = (c0 + chunk < lenx) ? c0 + chunk : lenx;
-    for (long long n0 = c0 + warp * 8; n0 < c1; n0 += 64) {
+    // software pipeline: the next strip's B fragments are in flight while the current one is multiplied
+    long long n0 = c0 + warp * 8;
+    cplx b[8];
+    {
         long long col = n0 + g;
-        bool ok = col < c1;
-        cplx b[8];
+        bool ok = (n0 < c1) && (col < c1);
 #pragma unroll
         for (int kt = 0; kt < 8; kt++) {
             int r = kt * 4 + t;
             long long row = r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ);
             b[kt] = ok ? W[row * ldw + col] : mk(0.0, 0.0);
+        }
+    }
+    while (n0 < c1) {
+        const long long n1 = n0 + 64;
+        cplx bn[8];
+        {
+            long long col = n1 + g;
+            bool ok = (n1 < c1) && (col < c1);
+#pragma unroll
+            for (int kt = 0; kt < 8; kt++) {
+                int r = kt * 4 + t;
+                long long row = r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ);
+                bn[kt] = ok ? W[row * ldw + col] : mk(0.0, 0.0);
+            }
         }
         double cr[4][2], ci[4][2];
 #pragma unroll
@@ -436,6 +456,9 @@ k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, int 
                 if (c2 < c1) W[row * ldw + c2] = mk(cr[mt][e], ci[mt][e]);
             }
         }
+#pragma unroll
+        for (int kt = 0; kt < 8; kt++) b[kt] = bn[kt];
+        n0 = n1;
     }
 }
 
@@ -558,6 +581,7 @@ __global__ void k_sort(const double* __restrict__ sig2, int nv, double* __restri
 }
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+constexpr int MAXCH = 32;     // Gram partial slots per pair (DMMA path)
 
 struct Work {
     cplx* W; double* G; cplx* Q; int* rotated; double* sig2; int* perm; int* notconv;
@@ -569,7 +593,7 @@ Work carve(const Geom& g, void* base) {
     size_t off = 0;
     char* b = (char*)base;
     w.W = (cplx*)(b + off); off += align_up((size_t)g.nvp * g.ldw * sizeof(cplx));
-    w.G = (double*)(b + off); off += align_up((size_t)g.npairs * PMAX * PMAX * 2 * sizeof(double));
+    w.G = (double*)(b + off); off += align_up((size_t)g.npairs * MAXCH * PMAX * PMAX * 2 * sizeof(double));
     w.Q = (cplx*)(b + off); off += align_up((size_t)g.npairs * PMAX * PMAX * sizeof(cplx));
     w.rotated = (int*)(b + off); off += align_up((size_t)g.npairs * sizeof(int));
     w.sig2 = (double*)(b + off); off += align_up((size_t)g.nvp * sizeof(double));
@@ -633,7 +657,18 @@ extern "C" int qm_svd(int m, int n, const void* A_, long long lda, void* U_, lon
         chunk = (chunk + TC - 1) / TC * TC;
         return chunk;
     };
-    const long long chunk_g = pick_chunk(g.len), chunk_a = pick_chunk(lenx);
+    // DMMA kernels: aim at ~3 CTAs per SM in flight; chunks in units of one CTA step (32 / 64 columns)
+    auto pick_chunk_mma = [&](long long cols, int unit) {
+        long long want = (3LL * 148 + g.npairs - 1) / g.npairs;
+        long long chunk = (cols + want - 1) / want;
+        chunk = (chunk + unit - 1) / unit * unit;
+        if (chunk < unit) chunk = unit;
+        return chunk;
+    };
+    long long chunk_g = g.single ? pick_chunk(g.len) : pick_chunk_mma(g.len, 32);
+    if (!g.single && chunk_g < 64) chunk_g = 64;
+    if (!g.single && (g.len + chunk_g - 1) / chunk_g > MAXCH) chunk_g = ((g.len + MAXCH - 1) / MAXCH + 31) / 32 * 32;
+    const long long chunk_a = g.single ? pick_chunk(lenx) : pick_chunk_mma(lenx, 64);
     const int ncg = ceil_div(g.len, chunk_g), nca = ceil_div(lenx, chunk_a);
     const double tol2 = tol * tol;
     static bool eig_attr_set = false;
@@ -665,7 +700,7 @@ extern "C" int qm_svd(int m, int n, const void* A_, long long lda, void* U_, lon
                     w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, w.G));
             }
             QM_LAUNCH(QM_CLS_SVD_EIG, st, k_eig<<<g.npairs, NT, EIG_SMEM, st>>>(
-                w.G, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, cross_only, r, g.nbp, g.single, w.notconv,
+                w.G, g.single ? 0 : ncg, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, cross_only, r, g.nbp, g.single, w.notconv,
                 w.rotated, w.sig2));
             if (g.single) {
                 QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply<<<dim3(nca, g.npairs), NT, 0, st>>>(
