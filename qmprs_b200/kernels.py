@@ -250,8 +250,13 @@ class CudaKernels:
 _instances = {}
 
 
-def get_kernels(device="cuda:0"):
-    """Process-wide kernel handle for ``device`` (fails loudly without CUDA / the .so)."""
+def get_kernels(device=None):
+    """Process-wide kernel handle for ``device`` (default: the current CUDA device, i.e. the
+    rank's GPU under torchrun).  Fails loudly without CUDA / the .so."""
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("qmprs_b200 requires a CUDA device (B200, sm_100a); there is no CPU fallback.")
+        device = f"cuda:{torch.cuda.current_device()}"
     key = str(device)
     if key not in _instances:
         _instances[key] = CudaKernels(device)
