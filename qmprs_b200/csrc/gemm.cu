@@ -39,7 +39,7 @@ k_zgemm(int m, int n, int k, cplx alpha, const cplx* __restrict__ A, long long l
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;   // x covers M (can be 2^23 rows in to_dense)
     const int g = lane >> 2, t = lane & 3;
 
     double cr[2][4][2], ci[2][4][2];
@@ -124,7 +124,8 @@ extern "C" int qm_zgemm(int m, int n, int k, double alpha_re, double alpha_im, c
                         int batch, long long strideA, long long strideB, long long strideC, int trans_a,
                         void* stream) {
     if (m <= 0 || n <= 0 || batch <= 0) return 0;
-    dim3 grid(ceil_div(n, BN), ceil_div(m, BM), batch);
+    dim3 grid(ceil_div(m, BM), ceil_div(n, BN), batch);
+    if (grid.y > 65535u) return -3;
     cudaStream_t st = (cudaStream_t)stream;
     if (trans_a) {
         QM_LAUNCH(QM_CLS_GEMM, st, (k_zgemm<true><<<grid, 256, 0, st>>>(

@@ -111,3 +111,45 @@ def test_structured_states(K):
     rd = host.prepare(K, ghz, 6, 16, 2, 1)
     assert rd["n_layers"] == ro["n_layers"]
     assert rd["fidelity"] > 1 - 1e-9
+
+
+def test_config2_shape_16_qubits(K):
+    """BASELINE config 2 shapes (16 qubits, chi=256: 256x256 and 128x512 gate-split SVDs, multi-block
+    Jacobi path) at a layer/sweep count the oracle finishes in seconds."""
+    psi, ro, rd, rec_o, rec_d = run_both(K, 16, 256, 3, 2, seed=5)
+    assert rd["n_layers"] == ro["n_layers"] == 3
+    assert host.bond_dims(rd["mps"]) == O.bond_dims(ro["mps"])
+    fo = O.circuit_fidelity(psi, ro["layers"], 16)
+    assert abs(rd["fidelity"] - fo) <= 1e-6
+    for so, sd in zip(rec_o["tt_svd"], rec_d["tt_svd"]):
+        assert np.abs(K.to_host(sd) - so).max() <= 1e-10 * so[0]
+    for so, sd in zip(rec_o["gate_split"][0], rec_d["gate_split"][0]):
+        sd = K.to_host(sd)
+        assert sd.shape == so.shape and np.abs(sd - so).max() <= 1e-10 * so[0]
+    flat = O.flatten_layers(ro["layers"])
+    g = rd["gates"].reshape(-1, 16)
+    for idx, (_, _, _, _, G) in enumerate(flat):
+        assert np.abs(g[idx][: G.size] - G.reshape(-1)).max() <= 1e-6
+
+
+def test_config4_tt_svd_properties(K):
+    """BASELINE config 4 (24-qubit TT-SVD to chi=1024) through size-independent properties: exact
+    bond dimensions, and the truncated state's error equals the discarded weight 1 - |psi_chi|^2
+    (right-canonical form with the norm on site 0).  Run at 22 qubits / chi=512 to keep the GPU
+    suite short; scripts/tt_svd_c4.py runs the full 24-qubit case (profiles/)."""
+    import torch
+    n, chi = 22, 512
+    psi = O.random_state(n, 7)
+    P = K.from_host(psi)
+    A = host.from_dense(K, P, n)
+    bonds = host.bond_dims(A)
+    exact = [min(2 ** (i + 1), 2 ** (n - 1 - i)) for i in range(n - 1)]
+    assert all(b <= e and b >= e - 4 for b, e in zip(bonds, exact))      # cutoff 1e-10 may drop a few at the centre
+    At = host.canonicalize_truncate(K, A, chi)
+    assert max(host.bond_dims(At)) == chi
+    d = host.to_dense(K, At)
+    err2 = float(torch.linalg.vector_norm(d - P).item()) ** 2
+    nrm2 = float(torch.linalg.vector_norm(d).item()) ** 2
+    a0 = At[0]
+    assert abs(float(K.to_host(K.vdot(a0, a0))[0]) - nrm2) <= 1e-10       # norm sits on site 0
+    assert abs(err2 - (1 - nrm2)) <= 1e-7
