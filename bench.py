@@ -313,15 +313,17 @@ def run_batch(args, wl, K, dev, world, rank, sync_all, max_over_ranks):
     from qmprs_b200 import batch as qb
     n, chi, L, S = wl["n"], wl["chi"], wl["layers"], wl["sweeps"]
     B = args.batch
+    from qmprs_b200.graphs import GraphedPreparer
     states = np.stack([rand_state(n, s) for s in range(B)])          # seed = state index
+    prep = GraphedPreparer(n, chi, L, S, lanes=args.lanes, device=str(dev)) if args.lanes > 0 else None
     for _ in range(max(args.warmup, 1)):
-        qb.prepare_state_batch(states[: 2 * world], chi, L, S, kernels=K)
+        qb.prepare_state_batch(states[: 2 * world * max(args.lanes, 1)], chi, L, S, kernels=K, preparer=prep)
     sync_all()
     l0 = K.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        recs = qb.prepare_state_batch(states, chi, L, S, kernels=K)
+        recs = qb.prepare_state_batch(states, chi, L, S, kernels=K, preparer=prep)
     e1.record()
     sync_all()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -334,7 +336,10 @@ def run_batch(args, wl, K, dev, world, rank, sync_all, max_over_ranks):
             "dtype": "c128", "data": "synthetic",
             "config": {"workload": wl["name"], "n_qubits": n, "chi": chi, "layers": L, "sweeps": S, "batch": B,
                        "parallelism": f"states sharded over {world} GPU(s), one all-gather of records"},
-            "fidelity_mean": fid, "gpu_launches": int(K.launch_count() - l0),
+            "fidelity_mean": fid,
+            "gpu_launches": int(K.launch_count() - l0 + (prep.replays * prep.nodes_per_graph if prep else 0)),
+            "graph": ({"lanes": args.lanes, "kernel_nodes_per_state": prep.nodes_per_graph,
+                       "eager_fallbacks": prep.fallbacks} if prep else None),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(B * 16 * 2 ** n // world),
                     "d2h_bytes_per_step": int(B * qb.record_len(n, L) * 8)},
         }))
@@ -345,6 +350,7 @@ def run_batch(args, wl, K, dev, world, rank, sync_all, max_over_ranks):
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--lanes", type=int, default=4, help="concurrent CUDA-graph lanes per GPU for --workload c5 (0 = eager)")
     ap.add_argument("--batch", type=int, default=64, help="states per step for --workload c5 (config 5 uses 4096)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

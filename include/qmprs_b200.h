@@ -37,6 +37,13 @@ int qm_svd(int m, int n, const void* A, long long lda, void* U, long long ldu, v
            long long ldvh, void* work, long long work_bytes, double tol, int max_sweeps, int* info_host,
            void* stream);
 
+/* Sync-free SVD for CUDA-graph capture: exactly fixed_sweeps sweeps are enqueued (kernels return
+ * immediately once a device-side flag says the iteration converged); mismatch[0] (int) is set to 1
+ * if it had not converged, in which case the caller re-runs the problem through qm_svd. */
+int qm_svd_static(int m, int n, const void* A, long long lda, void* U, long long ldu, void* S, void* Vh,
+                  long long ldvh, void* work, long long work_bytes, double tol, int fixed_sweeps, void* mismatch,
+                  void* stream);
+
 /* Householder QR (LAPACK zgeqr2 layout), explicit thin Q, and R with non-negative
  * diagonal.  Replaces quimb qr_stabilized behind left_canonize / right_canonize /
  * tensor_compress_bond: mps.py:396-398, :451-453. */
@@ -83,6 +90,13 @@ int qm_complete_unitaries(const void* C, const void* bond, int n_sites, void* ga
 /* out (r,2,l) = in (l,2,r) with the bond axes swapped: mirror image of a site tensor, used
  * for the left-handed canonicalize/compress variants (mps.py:396, :451-453 with mode="left"). */
 int qm_reverse3(void* out, const void* in, int l, int r, void* stream);
+
+/* Speculative static-shape execution (graphs.py): ranks / block structure / early break are assumed
+ * and validated on the device; mismatch[0] = 1 sends the state back through the eager path.
+ * qm_expect_ints: vals[i] must equal expect[i] (device array) or `scalar` when expect is NULL.
+ * qm_expect_not_close: the early-break test |f - 1| <= tol (sequential.py:390) must not fire. */
+int qm_expect_ints(const void* vals, const void* expect, int n, int scalar, void* mismatch, void* stream);
+int qm_expect_not_close(const void* f, double tol, void* mismatch, void* stream);
 
 /* ---- vectors ------------------------------------------------------------------- */
 int qm_conj_scale_copy(void* out, const void* in, long long n, int conj, double scale, void* stream);

@@ -22,6 +22,9 @@ SIGNATURES = {
     "qm_zgemm": (_i, [_i, _i, _i, _d, _d, _vp, _ll, _vp, _ll, _d, _d, _vp, _ll, _i, _ll, _ll, _ll, _i, _vp]),
     "qm_svd_work_bytes": (_ll, [_i, _i]),
     "qm_svd": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _d, _i, _ip, _vp]),
+    "qm_svd_static": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _d, _i, _vp, _vp]),
+    "qm_expect_ints": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "qm_expect_not_close": (_i, [_vp, _d, _vp, _vp]),
     "qm_qr": (_i, [_i, _i, _vp, _ll, _vp, _vp]),
     "qm_qr_formq": (_i, [_i, _i, _vp, _ll, _vp, _vp, _ll, _vp]),
     "qm_qr_finish": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp]),

@@ -43,7 +43,8 @@ def unpack_record(vec: np.ndarray, n_sites: int, num_layers: int) -> dict:
 
 
 def prepare_state_batch(states, bond_dimension: int, num_layers: int = 1, num_sweeps: int = 0,
-                        threshold: float = 1 - 1e-6, kernels=None, gather: bool = True):
+                        threshold: float = 1 - 1e-6, kernels=None, gather: bool = True, graph_lanes: int = 0,
+                        preparer=None):
     """Compile every row of ``states`` (B x 2^n) and return the list of B result records
     (on every rank when ``gather``).  ``kernels``: kernel handle (default: CUDA on the
     local rank's device)."""
@@ -68,9 +69,18 @@ def prepare_state_batch(states, bond_dimension: int, num_layers: int = 1, num_sw
     rl = record_len(n, num_layers)
     per_rank = (B + world - 1) // world
     local = np.zeros((per_rank, rl), dtype=np.float64)
-    for slot, s in enumerate(mine):
-        res = host.prepare(K, states[s], n, bond_dimension, num_layers, num_sweeps, threshold)
-        local[slot] = pack_record(res, n, num_layers)
+    if graph_lanes or preparer is not None:
+        # small states: captured CUDA graphs replayed per state on several concurrent lanes (graphs.py)
+        if preparer is None:
+            from qmprs_b200.graphs import GraphedPreparer
+            preparer = GraphedPreparer(n, bond_dimension, num_layers, num_sweeps, threshold, lanes=graph_lanes,
+                                       device=str(K.device))
+        for slot, res in enumerate(preparer.run(states[mine])):
+            local[slot] = pack_record(res, n, num_layers)
+    else:
+        for slot, s in enumerate(mine):
+            res = host.prepare(K, states[s], n, bond_dimension, num_layers, num_sweeps, threshold)
+            local[slot] = pack_record(res, n, num_layers)
     if not (distributed and gather) or world == 1:
         return [unpack_record(local[slot], n, num_layers) for slot in range(len(mine))] if world == 1 else \
                {s: unpack_record(local[slot], n, num_layers) for slot, s in enumerate(mine)}

@@ -327,6 +327,20 @@ __global__ void k_reverse3(cplx* __restrict__ out, const cplx* __restrict__ in, 
     out[((long long)c * 2 + p) * l + a] = in[idx];
 }
 
+// speculative static-shape execution: device-side validation of the assumptions
+__global__ void k_expect_ints(const int* __restrict__ vals, const int* __restrict__ expect, int n, int scalar,
+                              int* __restrict__ mismatch) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int e = expect ? expect[i] : scalar;
+    if (vals[i] != e) mismatch[0] = 1;
+}
+// early-break test of sequential.py:390 must NOT fire: |f - 1| <= atol + rtol  =>  mismatch
+__global__ void k_expect_not_close(const cplx* __restrict__ f, double tol, int* __restrict__ mismatch) {
+    double dr = f[0].x - 1.0, di = f[0].y;
+    if (sqrt(dr * dr + di * di) <= tol) mismatch[0] = 1;
+}
+
 int grid_for(long long n) {
     long long g = (n + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
@@ -393,6 +407,20 @@ extern "C" int qm_complete_unitaries(const void* C, const void* bond, int n_site
 
 extern "C" int qm_reverse3(void* out, const void* in, int l, int r, void* stream) {
     QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_reverse3<<<ceil_div(2LL * l * r, 256), 256, 0, (cudaStream_t)stream>>>((cplx*)out, (const cplx*)in, l, r));
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_expect_ints(const void* vals, const void* expect, int n, int scalar, void* mismatch, void* stream) {
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_expect_ints<<<ceil_div(n, 64), 64, 0, (cudaStream_t)stream>>>(
+        (const int*)vals, (const int*)expect, n, scalar, (int*)mismatch));
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_expect_not_close(const void* f, double tol, void* mismatch, void* stream) {
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_expect_not_close<<<1, 1, 0, (cudaStream_t)stream>>>(
+        (const cplx*)f, tol, (int*)mismatch));
     QM_CHECK_LAUNCH();
     return 0;
 }

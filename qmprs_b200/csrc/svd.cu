@@ -78,7 +78,8 @@ __device__ __forceinline__ int pair_row(int i, int pair, int round, int nbp, int
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT)
 k_gram(const cplx* __restrict__ W, long long ldw, int len, int chunk, int round, int nbp, int single,
-       int nrows, double* __restrict__ G) {
+       int nrows, double* __restrict__ G, const int* __restrict__ done) {
+    if (done && *done) return;      // static (sync-free) mode: this SVD already converged
     __shared__ cplx tile[PMAX * (TC + 1)];
     __shared__ double gacc[PMAX * PMAX * 2];
     __shared__ int rows[PMAX];
@@ -155,7 +156,8 @@ constexpr size_t EIG_SMEM = 2ull * PMAX * GS * sizeof(cplx);   // g, q
 __global__ void __launch_bounds__(NT)
 k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, double tol2, int max_inner,
       int cross_only, int round, int nbp, int single, int* __restrict__ notconv, int* __restrict__ rotated,
-      double* __restrict__ sig2) {
+      double* __restrict__ sig2, const int* __restrict__ done) {
+    if (done && *done) return;      // static (sync-free) mode: this SVD already converged
     extern __shared__ __align__(16) unsigned char eig_smem[];
     cplx* g = (cplx*)eig_smem;                            // [PMAX][GS]
     cplx* q = g + PMAX * GS;                              // [PMAX][GS]
@@ -345,7 +347,8 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // k_eig sums over chunks.  A lane's 16-byte load W[row][k] is both an A and a B operand.
 __global__ void __launch_bounds__(NT)
 k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, int round, int nbp,
-           double* __restrict__ G) {
+           double* __restrict__ G, const int* __restrict__ done) {
+    if (done && *done) return;      // static (sync-free) mode: this SVD already converged
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = blockIdx.y;
     const int g = lane >> 2, t = lane & 3;
     int bi, bj;
@@ -388,7 +391,8 @@ k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, int ro
 // fragments, multiplies by Q (A fragments from padded shared planes) and stores in place.
 __global__ void __launch_bounds__(NT, 2)
 k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, int round, int nbp,
-            const cplx* __restrict__ Q, const int* __restrict__ rotated) {
+            const cplx* __restrict__ Q, const int* __restrict__ rotated, const int* __restrict__ done) {
+    if (done && *done) return;      // static (sync-free) mode: this SVD already converged
     const int pair = blockIdx.y;
     if (!rotated[pair]) return;
     constexpr int QS = PMAX + 4;
@@ -467,7 +471,8 @@ k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, int 
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT)
 k_apply(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, int round, int nbp, int single,
-        int nrows, const cplx* __restrict__ Q, const int* __restrict__ rotated) {
+        int nrows, const cplx* __restrict__ Q, const int* __restrict__ rotated, const int* __restrict__ done) {
+    if (done && *done) return;      // static (sync-free) mode: this SVD already converged
     const int pair = blockIdx.y;
     if (!rotated[pair]) return;
     __shared__ cplx qs[PMAX][PMAX + 1];
@@ -580,6 +585,15 @@ __global__ void k_sort(const double* __restrict__ sig2, int nv, double* __restri
     }
 }
 
+// static mode bookkeeping: end of a sweep / end of the SVD
+__global__ void k_sweep_end(int* __restrict__ nc) {
+    if (nc[0] == 0) nc[1] = 1;
+    nc[0] = 0;
+}
+__global__ void k_static_check(const int* __restrict__ nc, int* __restrict__ mismatch) {
+    if (!nc[1]) mismatch[0] = 1;
+}
+
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 constexpr int MAXCH = 32;     // Gram partial slots per pair (DMMA path)
 
@@ -598,7 +612,7 @@ Work carve(const Geom& g, void* base) {
     w.rotated = (int*)(b + off); off += align_up((size_t)g.npairs * sizeof(int));
     w.sig2 = (double*)(b + off); off += align_up((size_t)g.nvp * sizeof(double));
     w.perm = (int*)(b + off); off += align_up((size_t)g.nvp * sizeof(int));
-    w.notconv = (int*)(b + off); off += align_up(sizeof(int));
+    w.notconv = (int*)(b + off); off += align_up(2 * sizeof(int));   // [0] not-converged count, [1] done flag
     w.total = off;
     return w;
 }
@@ -613,9 +627,9 @@ extern "C" long long qm_svd_work_bytes(int m, int n) {
 
 // A (m x n, row-major, lda) is not modified.  U: m x k (ldu), S: k, Vh: k x n (ldvh), k = min(m,n).
 // U or Vh may be NULL.  info_host (optional, host int[2]) receives {sweeps, converged}.
-extern "C" int qm_svd(int m, int n, const void* A_, long long lda, void* U_, long long ldu, void* S_, void* Vh_,
-                      long long ldvh, void* work, long long work_bytes, double tol, int max_sweeps,
-                      int* info_host, void* stream_) {
+static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long long ldu, void* S_, void* Vh_,
+                    long long ldvh, void* work, long long work_bytes, double tol, int max_sweeps,
+                    int* info_host, int fixed_sweeps, int* mismatch, void* stream_) {
     if (m <= 0 || n <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream_;
     Geom g = make_geom(m, n);
@@ -687,27 +701,30 @@ extern "C" int qm_svd(int m, int n, const void* A_, long long lda, void* U_, lon
         tune_cross = e2 ? atoi(e2) : 1;
     }
     int sweeps = 0, converged = 0;
+    const bool is_static = fixed_sweeps > 0;
+    const int* donep = is_static ? w.notconv + 1 : nullptr;
+    if (is_static) max_sweeps = fixed_sweeps;
+    QM_CUDA(cudaMemsetAsync(w.notconv, 0, 2 * sizeof(int), st));
     for (; sweeps < max_sweeps;) {
-        QM_CUDA(cudaMemsetAsync(w.notconv, 0, sizeof(int), st));
         const int max_inner = (sweeps == 0) ? tune_inner0 : tune_inner;
         const int cross_only = (sweeps > 0 && tune_cross) ? 1 : 0;
         for (int r = 0; r < g.rounds; r++) {
             if (g.single) {
                 QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram<<<dim3(ncg, g.npairs), NT, 0, st>>>(
-                    w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, g.single, g.nrows, w.G));
+                    w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, g.single, g.nrows, w.G, donep));
             } else {
                 QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram_mma<<<dim3(ncg, g.npairs), NT, 0, st>>>(
-                    w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, w.G));
+                    w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, w.G, donep));
             }
             QM_LAUNCH(QM_CLS_SVD_EIG, st, k_eig<<<g.npairs, NT, EIG_SMEM, st>>>(
                 w.G, g.single ? 0 : ncg, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, cross_only, r, g.nbp, g.single, w.notconv,
-                w.rotated, w.sig2));
+                w.rotated, w.sig2, donep));
             if (g.single) {
                 QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply<<<dim3(nca, g.npairs), NT, 0, st>>>(
-                    w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, g.single, g.nrows, w.Q, w.rotated));
+                    w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, g.single, g.nrows, w.Q, w.rotated, donep));
             } else {
                 QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply_mma<<<dim3(nca, g.npairs), NT, 0, st>>>(
-                    w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, w.Q, w.rotated));
+                    w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, w.Q, w.rotated, donep));
             }
         }
         // complex MAC = 8 flops: Gram nrows^2 x len, update nrows^2 x lenx, per pair and round
@@ -715,11 +732,18 @@ extern "C" int qm_svd(int m, int n, const void* A_, long long lda, void* U_, lon
         qm_prof_work(QM_CLS_SVD_APPLY, 8.0 * g.nrows * g.nrows * (double)lenx * g.npairs * g.rounds);
         QM_CHECK_LAUNCH();
         sweeps++;
+        if (is_static) {
+            // no host round trip: the remaining sweeps become empty launches once `done` is set
+            QM_LAUNCH(QM_CLS_SMALL, st, k_sweep_end<<<1, 1, 0, st>>>(w.notconv));
+            continue;
+        }
         int h = 0;
         QM_CUDA(cudaMemcpyAsync(&h, w.notconv, sizeof(int), cudaMemcpyDeviceToHost, st));
         QM_CUDA(cudaStreamSynchronize(st));
+        QM_CUDA(cudaMemsetAsync(w.notconv, 0, sizeof(int), st));
         if (h == 0) { converged = 1; break; }
     }
+    if (is_static && mismatch) QM_LAUNCH(QM_CLS_SMALL, st, k_static_check<<<1, 1, 0, st>>>(w.notconv, mismatch));
     if (info_host) { info_host[0] = sweeps; info_host[1] = converged; }
 
     // --- sort, emit ---
@@ -749,4 +773,21 @@ extern "C" int qm_svd(int m, int n, const void* A_, long long lda, void* U_, lon
     }
     QM_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int qm_svd(int m, int n, const void* A, long long lda, void* U, long long ldu, void* S, void* Vh,
+                      long long ldvh, void* work, long long work_bytes, double tol, int max_sweeps,
+                      int* info_host, void* stream) {
+    return svd_impl(m, n, A, lda, U, ldu, S, Vh, ldvh, work, work_bytes, tol, max_sweeps, info_host, 0, nullptr,
+                    stream);
+}
+
+// Sync-free variant (CUDA-graph capturable): exactly `fixed_sweeps` sweeps are enqueued, kernels of the
+// sweeps after convergence return immediately, and mismatch[0] is set to 1 if the SVD had not
+// converged by then (the caller re-runs that problem through qm_svd).
+extern "C" int qm_svd_static(int m, int n, const void* A, long long lda, void* U, long long ldu, void* S, void* Vh,
+                             long long ldvh, void* work, long long work_bytes, double tol, int fixed_sweeps,
+                             void* mismatch, void* stream) {
+    return svd_impl(m, n, A, lda, U, ldu, S, Vh, ldvh, work, work_bytes, tol, fixed_sweeps, nullptr,
+                    fixed_sweeps, (int*)mismatch, stream);
 }

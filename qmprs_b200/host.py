@@ -32,7 +32,7 @@ def from_dense(K, psi, n_sites, spectra=None):
         if spectra is not None:
             spectra.append(S)
         rank, f = K.trim(S, k, CUTOFF, MODE_RSUM2)
-        n = K.read_int(rank)
+        n = K.read_int(rank, expect=k)
         A[i] = K.scale_copy(Vh[:n], S, f, mode=1, half_power=True).reshape(n, 2, r)
         T = K.scale_copy(U[:, :n], S, f, mode=2, half_power=True)
         r = n
@@ -87,7 +87,7 @@ def right_compress(K, A, max_bond=None, spectra=None, cutoff=CUTOFF):
         if spectra is not None:
             spectra.append(S)
         rank, _ = K.trim(S, k, cutoff, MODE_REL, max_bond or 0)
-        n = K.read_int(rank)
+        n = K.read_int(rank, expect=min(k, max_bond) if max_bond else k)
         US = K.scale_copy(U[:, :n], S, None, mode=2, half_power=False)
         A[i] = K.scale_copy(Vh[:n]).reshape(n, 2, r)
         A[i - 1] = K.gemm(A[i - 1].reshape(l0 * 2, b), US).reshape(l0, 2, n)
@@ -172,11 +172,11 @@ def chi2_layer(K, B, debug=None, accurate=False):
         l0, _, b = B[i - 1].shape
         T = K.gemm(B[i - 1].reshape(l0 * 2, b), W).reshape(l0, 4)
     K.chi2_first(T, C[0])
-    if not accurate and K.read_int(ambiguous):
+    if not accurate and K.read_int(ambiguous, expect=0):
         return chi2_layer(K, B, debug, accurate=True)
     gates, kinds, bad = K.complete_unitaries(C, bond, N)
-    kinds_h = [int(x) for x in K.to_host(kinds)]
-    if K.read_int(bad):
+    kinds_h = K.read_kinds(kinds, N)
+    if K.read_int(bad, expect=0):
         raise ValueError("All the generated unitaries must be unitary.")     # mps.py:838-839
     if debug is not None:
         debug["C"] = C
@@ -230,7 +230,7 @@ def apply_inverse_layer(K, B, gates, kinds, spectra=None, inverse=True):
                 if spectra is not None:
                     spectra.append(S)
                 rank, f = K.trim(S, k, CUTOFF, MODE_RSUM2)
-                n = K.read_int(rank)
+                n = K.read_int(rank, expect=k)
                 B[i] = K.scale_copy(U[:, :n], S, f, mode=2, half_power=True).reshape(l, 2, n)
                 B[i + 1] = K.scale_copy(Vh[:n], S, f, mode=1, half_power=True).reshape(n, 2, r)
     return B
@@ -239,13 +239,15 @@ def apply_inverse_layer(K, B, gates, kinds, spectra=None, inverse=True):
 # --------------------------------------------------------------------------------------
 # A7  overlap with |0..0>             mps.py:1020-1039
 # --------------------------------------------------------------------------------------
-def zero_overlap(K, B):
-    """conj(psi[0]) as a product of the p=0 slices (only element 0 of the dense vector is used)."""
+def zero_overlap(K, B, break_tol=None):
+    """conj(psi[0]) as a product of the p=0 slices (only element 0 of the dense vector is used).
+    With ``break_tol`` the value only feeds the early-break test (sequential.py:390); in the
+    kernels' static mode that test is validated on the device and None is returned."""
     v = B[0][:, 0, :]
     for i in range(1, len(B)):
         v = K.gemm(v, B[i][:, 0, :])
-    z = K.to_host(v).reshape(-1)[0]
-    return complex(np.conj(z))
+    z = K.read_overlap(v, break_tol if break_tol is not None else -1.0)
+    return None if z is None else complex(np.conj(z))
 
 
 # --------------------------------------------------------------------------------------
@@ -313,14 +315,31 @@ def disentangle(K, A, num_layers, threshold, record=None):
         rec.setdefault("gate_split", []).append(sp)
         layer_gates.append(gates)
         layer_kinds.append(kinds)
-        f = zero_overlap(K, B)
+        # np.isclose(f, 1+0j, atol=1-threshold): |f - 1| <= atol + rtol*|1| with numpy's rtol = 1e-5
+        f = zero_overlap(K, B, break_tol=(1 - threshold) + 1e-5)
         overlaps.append(f)
-        if np.isclose(f, 1 + 0j, atol=1 - threshold):                 # sequential.py:390
+        if f is not None and np.isclose(f, 1 + 0j, atol=1 - threshold):   # sequential.py:390
             break
     layer_gates.reverse()                                             # sequential.py:396
     layer_kinds.reverse()
     gates_all = torch.cat(layer_gates, dim=0).contiguous()
     return gates_all, layer_kinds, overlaps
+
+
+def prepare_device(K, psi, n_sites, chi, num_layers, num_sweeps, threshold=1 - 1e-6, record=None):
+    """Device-to-device core of :func:`prepare`: ``psi`` is a device vector (overwritten by its
+    normalised copy), returns device tensors (gates_all [L*N,16], kinds per layer, overlap [2] =
+    <psi|circuit> as (re, im), overlaps list).  No host transfer; this is what graphs.py captures."""
+    N = int(n_sites)
+    K.div_sqrt(psi, K.vdot(psi, psi))                                 # quick Ket normalisation
+    A = build_mps(K, psi, N, chi, record)
+    gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record)
+    if num_sweeps > 0:
+        target = to_dense(K, A)                                       # sequential.py:440 (mps.mps)
+        optimize_layers(K, target, gates_all, layer_kinds, N, num_sweeps)
+    sites, kinds = flat_schedule(layer_kinds, N)
+    c = K.circuit_state(N, gates_all, sites, kinds)
+    return gates_all, layer_kinds, K.vdot(psi, c), overlaps, A
 
 
 def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 - 1e-6, record=None,

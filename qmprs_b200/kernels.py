@@ -43,6 +43,11 @@ class CudaKernels:
         self.svd_sweeps = 0
         self.svd_tol = 1e-14
         self.svd_max_sweeps = 30
+        # speculative static-shape mode (graphs.py): no host read-backs; assumptions are validated on
+        # the device and recorded in `mismatch`
+        self.static = False
+        self.static_sweeps = 12
+        self.mismatch = None
 
     # ---- memory / plumbing --------------------------------------------------------
     def _stream(self):
@@ -60,8 +65,41 @@ class CudaKernels:
     def to_host(self, t):
         return t.detach().cpu().numpy()
 
-    def read_int(self, t):
+    def read_int(self, t, expect=None):
+        """Scalar that decides a shape.  Static mode returns the assumed value and enqueues the check."""
+        if self.static:
+            assert expect is not None, "static mode needs the assumed value"
+            self._check(self.lib.qm_expect_ints(_p(t), None, 1, int(expect), _p(self.mismatch), self._stream()),
+                        "qm_expect_ints")
+            return int(expect)
         return int(t.item())
+
+    def read_kinds(self, kinds, n_sites):
+        """Per-site gate kinds of a layer; static mode assumes one block spanning all sites."""
+        if self.static:
+            st = self._stream()
+            self._check(self.lib.qm_expect_ints(_p(kinds), None, n_sites - 1, 2, _p(self.mismatch), st),
+                        "qm_expect_ints")
+            self._check(self.lib.qm_expect_ints(_p(kinds[n_sites - 1:]), None, 1, 1, _p(self.mismatch), st),
+                        "qm_expect_ints")
+            return [2] * (n_sites - 1) + [1]
+        return [int(x) for x in self.to_host(kinds)]
+
+    def read_overlap(self, v, tol):
+        """<0..0|psi> as a host complex (eager) or None (static: the early break is assumed not to
+        fire, i.e. |f - 1| > tol is validated on the device)."""
+        if self.static:
+            self._check(self.lib.qm_expect_not_close(_p(v), float(tol), _p(self.mismatch), self._stream()),
+                        "qm_expect_not_close")
+            return None
+        return complex(self.to_host(v).reshape(-1)[0])
+
+    def begin_static(self):
+        self.mismatch = self.zeros((1,), I32)
+        self.static = True
+
+    def end_static(self):
+        self.static = False
 
     def synchronize(self):
         torch.cuda.synchronize(self.device)
@@ -101,6 +139,12 @@ class CudaKernels:
         U = self.empty((m, k)) if want_u else None
         S = out_s if out_s is not None else self.empty((k,), F64)
         Vh = out_vh if out_vh is not None else (self.empty((k, n)) if want_vh else None)
+        if self.static:
+            self._check(self.lib.qm_svd_static(m, n, _p(A), self._ld(A), _p(U), k, _p(S), _p(Vh),
+                                               (self._ld(Vh) if Vh is not None else n), _p(self._svd_work),
+                                               self._svd_work.numel(), self.svd_tol, self.static_sweeps,
+                                               _p(self.mismatch), self._stream()), "qm_svd_static")
+            return U, S, Vh
         info = (ctypes.c_int * 2)()
         self._check(self.lib.qm_svd(m, n, _p(A), self._ld(A), _p(U), k, _p(S), _p(Vh),
                                     (self._ld(Vh) if Vh is not None else n), _p(self._svd_work),

@@ -45,8 +45,16 @@ class FakeKernels:
     def to_host(self, t):
         return _np(t).copy()
 
-    def read_int(self, t):
+    static = False
+
+    def read_int(self, t, expect=None):
         return int(t.item())
+
+    def read_kinds(self, kinds, n_sites):
+        return [int(x) for x in _np(kinds)]
+
+    def read_overlap(self, v, tol):
+        return complex(_np(v).reshape(-1)[0])
 
     def synchronize(self):
         pass

@@ -1,0 +1,48 @@
+"""CUDA-graph (speculative static-shape) path vs the eager path (-m gpu)."""
+import numpy as np
+import pytest
+
+from oracle import qmprs_oracle as O
+from qmprs_b200 import host
+
+pytestmark = pytest.mark.gpu
+
+
+def test_graph_replay_matches_eager_and_oracle(K):
+    from qmprs_b200.graphs import GraphedPreparer
+    n, chi, L, S = 8, 32, 3, 2
+    states = np.stack([O.random_state(n, 100 + s) for s in range(7)])
+    prep = GraphedPreparer(n, chi, L, S, lanes=3)
+    out = prep.run(states)
+    assert prep.fallbacks == 0 and prep.nodes_per_graph > 100
+    for s in range(len(states)):
+        eager = host.prepare(K, states[s], n, chi, L, S)
+        assert out[s]["n_layers"] == eager["n_layers"] == L
+        assert out[s]["kinds"] == eager["kinds"]
+        assert np.abs(out[s]["gates"] - eager["gates"]).max() <= 1e-9
+        assert abs(out[s]["fidelity"] - eager["fidelity"]) <= 1e-12
+        ref = O.prepare(states[s], n, chi, L, S, gauge="canonical")
+        assert abs(out[s]["fidelity"] - O.circuit_fidelity(states[s], ref["layers"], n)) <= 1e-6
+    # a second pass over the same lanes must give the same answers (buffers are reused)
+    again = prep.run(states[:3])
+    for s in range(3):
+        assert np.abs(again[s]["gates"] - out[s]["gates"]).max() <= 1e-12
+
+
+def test_graph_falls_back_when_assumptions_fail(K):
+    """A product state has bond dimension 1 everywhere and breaks after one layer: every static
+    assumption is wrong, the device flags it, and the eager path returns the exact result."""
+    from qmprs_b200.graphs import GraphedPreparer
+    n = 6
+    prep = GraphedPreparer(n, 16, 2, 1, lanes=1)
+    h = np.array([1, 1j]) / np.sqrt(2)
+    psi = np.array([1.0 + 0j])
+    for _ in range(n):
+        psi = np.kron(psi, h)
+    ghz = np.zeros(2 ** n, dtype=complex); ghz[0] = ghz[-1] = 1 / np.sqrt(2)
+    out = prep.run(np.stack([psi, O.random_state(n, 1), ghz]))
+    assert prep.fallbacks == 2
+    assert out[0]["n_layers"] == 1 and out[0]["fidelity"] > 1 - 1e-12
+    assert host.blocks_from_kinds(out[0]["kinds"][0]) == [(i, i) for i in range(n)]
+    assert out[1]["n_layers"] == 2
+    assert out[2]["fidelity"] > 1 - 1e-9
