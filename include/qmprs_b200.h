@@ -73,7 +73,8 @@ int qm_site_gate(void* B, int l, int r, const void* G, int dagger, void* stream)
 /* chi=2 truncation bookkeeping for one bond (mps.py:881): picks n <= 2 by the 'rel'
  * cutoff, applies the canonical row-phase rule, writes the site tensor rows Csite[2][4],
  * the projector Vsel[4][2] and bond[0] = n.  squared = 1: S holds eigenvalues of T^H L T (squared
- * singular values); then ambiguous[0] is set to 1 when s_1 <= ambiguous_rel * s_0, i.e. when the
+ * singular values); squared = 2: Vh points at the 4x4 Hermitian matrix T^H L T itself and the kernel
+ * diagonalises it (S unused); then ambiguous[0] is set to 1 when s_1 <= ambiguous_rel * s_0, i.e. when the
  * squared formulation cannot resolve the rank decision / second vector and the caller must redo
  * the layer with the QR-based path. */
 int qm_chi2_select(const void* S, const void* Vh, long long ldvh, double cutoff, double tie, void* Csite,

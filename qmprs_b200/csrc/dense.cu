@@ -10,6 +10,7 @@
 // reads and writes each amplitude once with 16-byte accesses that are contiguous across
 // a warp.
 #include "common.cuh"
+#include "small_linalg.cuh"
 #include "qmprs_b200.h"
 
 namespace {
@@ -86,41 +87,6 @@ k_gate1(const cplx* xin, cplx* x, int nbits, int q, const cplx* __restrict__ G, 
 // polar(E + eps I)); it depends on E only, not on any basis choice.
 // Single thread.  polar_conj writes conj(P) (sequential.py:478-491).
 // ---------------------------------------------------------------------------------
-__device__ void jacobi_cols(cplx A[4][4], cplx V[4][4], int d) {
-    const double tol2 = 4e-30;
-    for (int sweep = 0; sweep < 40; sweep++) {
-        int rot = 0;
-        for (int p = 0; p < d - 1; p++)
-            for (int q = p + 1; q < d; q++) {
-                double a = 0.0, b = 0.0;
-                cplx g = mk(0.0, 0.0);                     // g = a_p^H a_q
-                for (int i = 0; i < d; i++) {
-                    a += cabs2(A[i][p]); b += cabs2(A[i][q]);
-                    ccfma(g, A[i][p], A[i][q]);
-                }
-                double mag2 = cabs2(g);
-                if (!(a > 0.0 && b > 0.0) || mag2 <= tol2 * a * b) continue;
-                rot = 1;
-                double imag = rsqrt(mag2);
-                double zeta = 0.5 * (b - a) * imag;
-                double z1 = 1.0 + zeta * zeta;
-                double t = copysign(1.0, zeta) / (fabs(zeta) + z1 * rsqrt(z1));
-                double c = rsqrt(1.0 + t * t), s = c * t;
-                cplx se = mk(s * g.x * imag, s * g.y * imag), sec = cconj(se);   // s e^{+-i phi}
-                // x' = c x - s e^{-i phi} y ; y' = s e^{i phi} x + c y
-                for (int i = 0; i < d; i++) {
-                    cplx xx = A[i][p], yy = A[i][q];
-                    A[i][p] = csub(cscale(xx, c), cmul(sec, yy));
-                    A[i][q] = cadd(cmul(se, xx), cscale(yy, c));
-                    xx = V[i][p]; yy = V[i][q];
-                    V[i][p] = csub(cscale(xx, c), cmul(sec, yy));
-                    V[i][q] = cadd(cmul(se, xx), cscale(yy, c));
-                }
-            }
-        if (!rot) break;
-    }
-}
-
 // Gram-Schmidt completion: for every column j with isnull[j], pick the standard basis vector
 // with the largest residual against all fixed columns, orthogonalise twice, normalise.
 __device__ void complete_columns(cplx U[4][4], const bool* isnull, int d) {

@@ -165,9 +165,8 @@ def chi2_layer(K, B, debug=None, accurate=False):
             K.svd(M, want_u=False, out_s=S4, out_vh=Vh4)
             K.chi2_select(S4, Vh4, C[i], Vsel, bond[i - 1:i])
         else:
-            H = K.gemm(T, M, transA=True)                  # T^H L T, 4 x 4 Hermitian PSD: SVD == eigen-decomposition
-            K.svd(H, want_u=False, out_s=S4, out_vh=Vh4)
-            K.chi2_select(S4, Vh4, C[i], Vsel, bond[i - 1:i], squared=True, ambiguous=ambiguous)
+            H = K.gemm(T, M, transA=True)                  # T^H L T, 4 x 4 Hermitian PSD, diagonalised in the select kernel
+            K.chi2_select(S4, H, C[i], Vsel, bond[i - 1:i], squared=2, ambiguous=ambiguous)
         W = K.gemm(T, Vsel)                                # (b x 2)
         l0, _, b = B[i - 1].shape
         T = K.gemm(B[i - 1].reshape(l0 * 2, b), W).reshape(l0, 4)

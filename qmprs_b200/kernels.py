@@ -47,6 +47,7 @@ class CudaKernels:
         # the device and recorded in `mismatch`
         self.static = False
         self.static_sweeps = 12
+        self.static_sweeps_small = 6
         self.mismatch = None
 
     # ---- memory / plumbing --------------------------------------------------------
@@ -140,9 +141,11 @@ class CudaKernels:
         S = out_s if out_s is not None else self.empty((k,), F64)
         Vh = out_vh if out_vh is not None else (self.empty((k, n)) if want_vh else None)
         if self.static:
+            # single-block problems (<= 32 short vectors) converge in 3-4 Gram iterations
+            fixed = self.static_sweeps if k > 32 else self.static_sweeps_small
             self._check(self.lib.qm_svd_static(m, n, _p(A), self._ld(A), _p(U), k, _p(S), _p(Vh),
                                                (self._ld(Vh) if Vh is not None else n), _p(self._svd_work),
-                                               self._svd_work.numel(), self.svd_tol, self.static_sweeps,
+                                               self._svd_work.numel(), self.svd_tol, fixed,
                                                _p(self.mismatch), self._stream()), "qm_svd_static")
             return U, S, Vh
         info = (ctypes.c_int * 2)()
@@ -194,7 +197,7 @@ class CudaKernels:
 
     def chi2_select(self, S4, Vh4, Csite, Vsel, bond_slot, squared=False, ambiguous=None):
         self._check(self.lib.qm_chi2_select(_p(S4), _p(Vh4), 4, CUTOFF, TIE_REL, _p(Csite), _p(Vsel), _p(bond_slot),
-                                            1 if squared else 0, CHI2_AMBIGUOUS_REL, _p(ambiguous), self._stream()),
+                                            int(squared), CHI2_AMBIGUOUS_REL, _p(ambiguous), self._stream()),
                     "qm_chi2_select")
 
     def chi2_first(self, T0, Csite):

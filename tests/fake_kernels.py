@@ -128,6 +128,11 @@ class FakeKernels:
 
     def chi2_select(self, S4, Vh4, Csite, Vsel, bond_slot, squared=False, ambiguous=None):
         s = _np(S4)
+        if squared == 2:                       # Vh4 is the 4x4 Hermitian matrix: diagonalise it here
+            w, v = np.linalg.eigh(_np(Vh4))
+            order = np.argsort(w)[::-1]
+            s = w[order]
+            Vh4 = torch.as_tensor(np.conj(v[:, order]).T.copy())
         if squared:
             s = np.sqrt(np.maximum(s, 0.0))
             if ambiguous is not None and s[1] <= 1e-3 * s[0]:
