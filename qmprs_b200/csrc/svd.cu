@@ -153,7 +153,8 @@ k_gram(const cplx* __restrict__ W, long long ldw, int len, int chunk, int round,
 constexpr int GS = PMAX + 1;                              // row stride of the shared matrices
 constexpr size_t EIG_SMEM = 2ull * PMAX * GS * sizeof(cplx);   // g, q
 
-__global__ void __launch_bounds__(NT)
+constexpr int NTE = 768;   // k_eig block: 256 threads update G, 512 update Q in the same pass
+__global__ void __launch_bounds__(NTE)
 k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, double tol2, int max_inner,
       int cross_only, int round, int nbp, int single, int* __restrict__ notconv, int* __restrict__ rotated,
       double* __restrict__ sig2, const int* __restrict__ done) {
@@ -173,7 +174,7 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
     // that is re-zeroed here (single-block path).
     if (nchunks > 0) {
         const double* Gp = G + (long long)pair * nchunks * PMAX * PMAX * 2;
-        for (int e = tid; e < n * n; e += NT) {
+        for (int e = tid; e < n * n; e += NTE) {
             double re = 0.0, im = 0.0;
             for (int c = 0; c < nchunks; c++) {
                 const double2 v = *(const double2*)(Gp + (long long)c * PMAX * PMAX * 2 + 2 * e);
@@ -185,23 +186,24 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
         }
     } else {
         double* Gp = G + (long long)pair * PMAX * PMAX * 2;
-        for (int e = tid; e < n * n; e += NT) {
+        for (int e = tid; e < n * n; e += NTE) {
             int i = e / n, j = e % n;
             g[i * GS + j] = mk(Gp[2 * e], Gp[2 * e + 1]);
             Gp[2 * e] = 0.0; Gp[2 * e + 1] = 0.0;
             q[i * GS + j] = mk(i == j ? 1.0 : 0.0, 0.0);
         }
     }
-    for (int e = tid; e < (ne - 1) * np; e += NT) {
+    for (int e = tid; e < (ne - 1) * np; e += NTE) {
         int r = e / np, k = e % np, a, b;
         if (ne == 2) { a = 0; b = 1; } else circle_pair(r, k, ne, a, b);
         sched[2 * e] = (unsigned char)a;
         sched[2 * e + 1] = (unsigned char)b;
     }
     // per-thread work items of the update phase do not depend on the round
-    const int blk_k = tid / np, blk_l = tid % np;            // 2x2 block (valid if tid < np*np; np*np <= NT)
-    const int q_k0 = tid / n, q_c0 = tid % n;                // Q items tid and tid + NT
-    const int q_k1 = (tid + NT) / n, q_c1 = (tid + NT) % n;
+    // threads [0,256): one 2x2 block of G each (np*np <= 256); threads [256,768): one (pair, column) item of Q
+    const int blk_k = tid / np, blk_l = tid % np;
+    const int qt = tid - 256;
+    const int q_k0 = qt >= 0 ? qt / n : np, q_c0 = qt >= 0 ? qt % n : 0;
     if (tid == 0) { s_any = 0; s_off = 0; s_mc = 0; s_mi = 0; }
     __syncthreads();
     // Fresh Gram matrix: already diagonal to tolerance?  Largest relative off-diagonal
@@ -209,7 +211,7 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
     {
         int offd = 0;
         float mc = 0.f, mi = 0.f;
-        for (int e = tid; e < n * n; e += NT) {
+        for (int e = tid; e < n * n; e += NTE) {
             int i = e / n, j = e % n;
             if (i < j) {
                 double a = g[i * GS + i].x, b = g[j * GS + j].x;
@@ -304,16 +306,16 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
                         if (vk && vl) g[qk * GS + ql] = b11;
                     }
                     // Q' = R Q : rows p_k, q_k
-#pragma unroll
-                    for (int rep = 0; rep < 2; rep++) {
-                        const int k = rep ? q_k1 : q_k0, col = rep ? q_c1 : q_c0;
-                        if (k >= np || !ract[k]) continue;
+                    {
+                        const int k = q_k0, col = q_c0;
+                        if (k < np && ract[k]) {
                         const int pk = rpp[k], qk = rqq[k];
                         const double ck = rcc[k];
                         const cplx ok = roff[k];
                         cplx x = q[pk * GS + col], y = q[qk * GS + col];
                         q[pk * GS + col] = cadd(cscale(x, ck), cmul(ok, y));
                         q[qk * GS + col] = csub(cscale(y, ck), cmul(cconj(ok), x));
+                        }
                     }
                 }
                 __syncthreads();
@@ -323,7 +325,7 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
         }
     }
     cplx* Qp = Qout + (long long)pair * PMAX * PMAX;
-    for (int e = tid; e < n * n; e += NT) Qp[e] = q[(e / n) * GS + (e % n)];
+    for (int e = tid; e < n * n; e += NTE) Qp[e] = q[(e / n) * GS + (e % n)];
     if (tid < n) sig2[pair_row(tid, pair, round, nbp, single)] = g[tid * GS + tid].x;
     if (tid == 0) {
         rotated[pair] = s_any;
@@ -361,22 +363,36 @@ k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, int ro
     double cr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, ci[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     const long long c0 = (long long)blockIdx.x * chunk;
     const long long c1 = (c0 + chunk < len) ? c0 + chunk : len;
-#pragma unroll 4
-    for (long long k0 = c0; k0 < c1; k0 += 4) {
-        const long long col = k0 + t;
+    // register double-buffering, prefetch distance PF k-steps (operands come from L2)
+    constexpr int PF = 4;
+    cplx fa[PF], fb0[PF], fb1[PF];
+#pragma unroll
+    for (int s = 0; s < PF; s++) {
+        const long long col = c0 + 4 * s + t;
         const bool ok = col < c1;
-        const cplx wa = ok ? pa[col] : mk(0.0, 0.0);
-        const cplx wb0 = ok ? pb0[col] : mk(0.0, 0.0);
-        const cplx wb1 = ok ? pb1[col] : mk(0.0, 0.0);
-        // W_m conj(W_n): re = ar*br + ai*bi ; im = ai*br - ar*bi
-        dmma884(cr[0][0], cr[0][1], wa.x, wb0.x);
-        dmma884(cr[0][0], cr[0][1], wa.y, wb0.y);
-        dmma884(ci[0][0], ci[0][1], wa.y, wb0.x);
-        dmma884(ci[0][0], ci[0][1], -wa.x, wb0.y);
-        dmma884(cr[1][0], cr[1][1], wa.x, wb1.x);
-        dmma884(cr[1][0], cr[1][1], wa.y, wb1.y);
-        dmma884(ci[1][0], ci[1][1], wa.y, wb1.x);
-        dmma884(ci[1][0], ci[1][1], -wa.x, wb1.y);
+        fa[s] = ok ? pa[col] : mk(0.0, 0.0);
+        fb0[s] = ok ? pb0[col] : mk(0.0, 0.0);
+        fb1[s] = ok ? pb1[col] : mk(0.0, 0.0);
+    }
+    for (long long k0 = c0; k0 < c1; k0 += 4 * PF) {
+#pragma unroll
+        for (int s = 0; s < PF; s++) {
+            const cplx wa = fa[s], wb0 = fb0[s], wb1 = fb1[s];
+            const long long col = k0 + 4 * (PF + s) + t;          // same slot, PF steps ahead
+            const bool ok = col < c1;
+            fa[s] = ok ? pa[col] : mk(0.0, 0.0);
+            fb0[s] = ok ? pb0[col] : mk(0.0, 0.0);
+            fb1[s] = ok ? pb1[col] : mk(0.0, 0.0);
+            // W_m conj(W_n): re = ar*br + ai*bi ; im = ai*br - ar*bi   (zero operands past c1 add nothing)
+            dmma884(cr[0][0], cr[0][1], wa.x, wb0.x);
+            dmma884(cr[0][0], cr[0][1], wa.y, wb0.y);
+            dmma884(ci[0][0], ci[0][1], wa.y, wb0.x);
+            dmma884(ci[0][0], ci[0][1], -wa.x, wb0.y);
+            dmma884(cr[1][0], cr[1][1], wa.x, wb1.x);
+            dmma884(cr[1][0], cr[1][1], wa.y, wb1.y);
+            dmma884(ci[1][0], ci[1][1], wa.y, wb1.x);
+            dmma884(ci[1][0], ci[1][1], -wa.x, wb1.y);
+        }
     }
     double* Gp = G + ((long long)pair * gridDim.x + blockIdx.x) * PMAX * PMAX * 2;
 #pragma unroll
@@ -716,7 +732,7 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
                 QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram_mma<<<dim3(ncg, g.npairs), NT, 0, st>>>(
                     w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, w.G, donep));
             }
-            QM_LAUNCH(QM_CLS_SVD_EIG, st, k_eig<<<g.npairs, NT, EIG_SMEM, st>>>(
+            QM_LAUNCH(QM_CLS_SVD_EIG, st, k_eig<<<g.npairs, NTE, EIG_SMEM, st>>>(
                 w.G, g.single ? 0 : ncg, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, cross_only, r, g.nbp, g.single, w.notconv,
                 w.rotated, w.sig2, donep));
             if (g.single) {

@@ -287,10 +287,39 @@ def optimize_layers(K, target, gates_all, kinds_per_layer, n_sites, num_sweeps, 
 # --------------------------------------------------------------------------------------
 # A0  top level                       base.py:96-104, sequential.py:330-398, 543-600
 # --------------------------------------------------------------------------------------
-def build_mps(K, psi, n_sites, chi, record=None):
+def from_dense_truncated(K, psi, n_sites, chi, spectra=None):
+    """A1 + A2 in one right-to-left pass: the TT-SVD is run in Schmidt form (U.S carried to the
+    left, V^H kept) with the 'rel' 1e-10 cutoff and max_bond=chi applied at every split.  Each SVD
+    is then the Schmidt decomposition of the state whose right part is already truncated, which is
+    exactly what ``compress_right(from_dense(psi), chi)`` computes bond by bond, so the result is the
+    same right-canonical MPS (norm on site 0) up to bond phases -- without the QR sweep and the
+    second round of SVDs.  (The reference's intermediate 'rsum2' cut inside from_dense only removes
+    weight <= 1e-10 and is not reproduced here; ``build_mps(fused=False)`` is the two-pass form.)"""
+    N = int(n_sites)
+    A = [None] * N
+    T = psi.reshape(-1, 1)
+    r = 1
+    for i in range(N - 1, 0, -1):
+        U, S, Vh = K.svd(T.reshape(2 ** i, 2 * r))
+        k = S.shape[0]
+        if spectra is not None:
+            spectra.append(S)
+        rank, _ = K.trim(S, k, CUTOFF, MODE_REL, chi or 0)
+        n = K.read_int(rank, expect=min(k, chi) if chi else k)
+        A[i] = K.scale_copy(Vh[:n]).reshape(n, 2, r)
+        T = K.scale_copy(U[:, :n], S, None, mode=2, half_power=False)
+        r = n
+    A[0] = T.reshape(1, 2, r)
+    return A
+
+
+def build_mps(K, psi, n_sites, chi, record=None, fused=True):
     """``MPS.from_statevector`` (mps.py:218-249).  Returns the chi-truncated
-    right-canonical MPS (norm on site 0, not renormalised)."""
+    right-canonical MPS (norm on site 0, not renormalised).  ``fused=False`` follows the
+    reference's two steps literally (exact TT-SVD with sqrt(s) on both sides, then compression)."""
     rec = record if record is not None else {}
+    if fused:
+        return from_dense_truncated(K, psi, n_sites, chi, rec.setdefault("truncate", []))
     A = from_dense(K, psi, n_sites, rec.setdefault("tt_svd", []))
     return canonicalize_truncate(K, A, chi, rec.setdefault("truncate", []))
 
@@ -325,13 +354,13 @@ def disentangle(K, A, num_layers, threshold, record=None):
     return gates_all, layer_kinds, overlaps
 
 
-def prepare_device(K, psi, n_sites, chi, num_layers, num_sweeps, threshold=1 - 1e-6, record=None):
+def prepare_device(K, psi, n_sites, chi, num_layers, num_sweeps, threshold=1 - 1e-6, record=None, fused=True):
     """Device-to-device core of :func:`prepare`: ``psi`` is a device vector (overwritten by its
     normalised copy), returns device tensors (gates_all [L*N,16], kinds per layer, overlap [2] =
     <psi|circuit> as (re, im), overlaps list).  No host transfer; this is what graphs.py captures."""
     N = int(n_sites)
     K.div_sqrt(psi, K.vdot(psi, psi))                                 # quick Ket normalisation
-    A = build_mps(K, psi, N, chi, record)
+    A = build_mps(K, psi, N, chi, record, fused)
     gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record)
     if num_sweeps > 0:
         target = to_dense(K, A)                                       # sequential.py:440 (mps.mps)
@@ -342,8 +371,8 @@ def prepare_device(K, psi, n_sites, chi, num_layers, num_sweeps, threshold=1 - 1
 
 
 def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 - 1e-6, record=None,
-            mps=None):
-    """Whole path on the device.  ``psi_host``: normalised complex128 numpy vector.
+            mps=None, fused=True):
+    """Whole path on the device.  ``psi_host``: complex128 numpy vector or device tensor.
     Returns dict(gates [L,N,16] numpy, kinds [L][N], n_layers, overlaps, fidelity)."""
     N = int(n_sites)
     if hasattr(psi_host, "data_ptr"):                 # already a device tensor (bench: inputs resident in HBM)
@@ -351,17 +380,16 @@ def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 -
     else:
         psi = K.from_host(np.asarray(psi_host, dtype=np.complex128).reshape(-1))
     if mps is None:
-        K.div_sqrt(psi, K.vdot(psi, psi))                             # quick Ket normalisation
-        A = build_mps(K, psi, N, chi, record)
+        gates_all, layer_kinds, ovt, overlaps, A = prepare_device(K, psi, N, chi, num_layers, num_sweeps,
+                                                                  threshold, record, fused)
     else:
         A = mps
-    gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record)
-    if num_sweeps > 0:
-        target = to_dense(K, A)                                       # sequential.py:440 (mps.mps)
-        optimize_layers(K, target, gates_all, layer_kinds, N, num_sweeps)
-    sites, kinds = flat_schedule(layer_kinds, N)
-    c = K.circuit_state(N, gates_all, sites, kinds)
-    ov = K.to_host(K.vdot(psi, c))
+        gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record)
+        if num_sweeps > 0:
+            optimize_layers(K, to_dense(K, A), gates_all, layer_kinds, N, num_sweeps)
+        sites, kinds = flat_schedule(layer_kinds, N)
+        ovt = K.vdot(psi, K.circuit_state(N, gates_all, sites, kinds))
+    ov = K.to_host(ovt)
     L = len(layer_kinds)
     return {
         "gates": K.to_host(gates_all).reshape(L, N, 16),

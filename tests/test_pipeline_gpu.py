@@ -20,11 +20,11 @@ def oracle_gate_table(res):
     return flat
 
 
-def run_both(K, n, chi, L, S, seed=0, psi=None):
+def run_both(K, n, chi, L, S, seed=0, psi=None, fused=False):
     psi = O.random_state(n, seed) if psi is None else psi
     rec_o, rec_d = {}, {}
     ro = O.prepare(psi, n, chi, L, S, gauge="canonical", record=rec_o)
-    rd = host.prepare(K, psi, n, chi, L, S, record=rec_d)
+    rd = host.prepare(K, psi, n, chi, L, S, record=rec_d, fused=fused)
     return psi, ro, rd, rec_o, rec_d
 
 
@@ -153,3 +153,21 @@ def test_config4_tt_svd_properties(K):
     a0 = At[0]
     assert abs(float(K.to_host(K.vdot(a0, a0))[0]) - nrm2) <= 1e-10       # norm sits on site 0
     assert abs(err2 - (1 - nrm2)) <= 1e-7
+
+
+@pytest.mark.parametrize("n,chi,L,S", [(8, 32, 4, 2), (8, 4, 3, 2), (10, 8, 3, 1), (12, 64, 3, 1)])
+def test_fused_build_equals_two_pass(K, n, chi, L, S):
+    """A1+A2 in one Schmidt-form TT-SVD pass (default) vs the reference's two steps: same bond
+    dimensions, same Schmidt spectra as the oracle's truncation sweep (1e-10), same circuit."""
+    psi, ro, rd, rec_o, rec_d = run_both(K, n, chi, L, S, seed=3, fused=True)
+    assert host.bond_dims(rd["mps"]) == O.bond_dims(ro["mps"])
+    for so, sd in zip(rec_o["truncate"], rec_d["truncate"]):
+        sd = K.to_host(sd)
+        assert sd.shape == so.shape and np.abs(sd - so).max() <= 1e-10 * so[0]
+    assert np.abs(K.to_host(host.to_dense(K, rd["mps"])) - ro["target"]).max() <= 1e-10
+    fo = O.circuit_fidelity(psi, ro["layers"], n)
+    assert abs(rd["fidelity"] - fo) <= 1e-6
+    flat = O.flatten_layers(ro["layers"])
+    g = rd["gates"].reshape(-1, 16)
+    for idx, (_, _, _, _, G) in enumerate(flat):
+        assert np.abs(g[idx][: G.size] - G.reshape(-1)).max() <= 1e-6
