@@ -123,11 +123,13 @@ int qm_sweep(void* c, void* tbar, int n_sites, void* gates, const int* sites, co
 
 /* Stored-intermediates variant: qm_circuit_states keeps every c_k = g_{k-1}..g_0|0> in HBM
  * (cs: (n_gates+1) * 2^N amplitudes) and qm_sweep_stored runs the same sweep with one fused
- * pass per gate (tbar update by the previous new gate + environment reduction). */
+ * pass per gate (tbar update by the previous new gate + environment reduction).  vwarm (optional,
+ * [n_gates][16], zero-initialised by the caller before the first sweep) carries each gate's right
+ * singular vectors from one sweep to the next as the starting point of the 4x4 Jacobi polar. */
 int qm_circuit_states(void* cs, int n_sites, const void* gates, const int* sites, const int* kinds, int n_gates,
                       void* stream);
 int qm_sweep_stored(const void* cs, void* tbar, int n_sites, void* gates, const int* sites, const int* kinds,
-                    int n_gates, void* work, void* envs, void* stream);
+                    int n_gates, void* work, void* envs, void* vwarm, void* stream);
 
 /* Library identification: returns the compiled architecture number (100 for sm_100a). */
 int qm_version(void);

@@ -44,7 +44,7 @@ SIGNATURES = {
     "qm_sweep_work_bytes": (_ll, []),
     "qm_sweep": (_i, [_vp, _vp, _i, _vp, _ip, _ip, _i, _vp, _vp, _vp]),
     "qm_circuit_states": (_i, [_vp, _i, _vp, _ip, _ip, _i, _vp]),
-    "qm_sweep_stored": (_i, [_vp, _vp, _i, _vp, _ip, _ip, _i, _vp, _vp, _vp]),
+    "qm_sweep_stored": (_i, [_vp, _vp, _i, _vp, _ip, _ip, _i, _vp, _vp, _vp, _vp]),
     "qm_version": (_i, []),
     "qm_launch_count": (_ll, []),
     "qm_prof_num_classes": (_i, []),

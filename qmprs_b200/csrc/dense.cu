@@ -197,12 +197,29 @@ __device__ __forceinline__ cplx shfl_xor_c(cplx v, int m) {
     return mk(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
 
-__device__ void polar_conj_warp(const cplx* Es, int d, cplx* gate_out, cplx* scratch /* smem, 32 cplx */) {
+// vwarm (optional, global, 16 cplx): right singular vectors found for this gate in the previous sweep.
+// The environments change little from sweep to sweep, so E V_prev already has nearly orthogonal
+// columns and the Jacobi iteration starts in its quadratic regime (2 sweeps instead of 5-6).
+__device__ void polar_conj_warp(const cplx* Es, int d, cplx* gate_out, cplx* scratch /* smem, 32 cplx */,
+                                cplx* vwarm) {
     const int lane = threadIdx.x & 31;
     const int half = lane >> 4, i = (lane >> 2) & 3, j = lane & 3;
     cplx x;
-    if (half == 0) x = (i < d && j < d) ? Es[i * d + j] : mk(i == j ? 1.0 : 0.0, 0.0);
-    else x = mk(i == j ? 1.0 : 0.0, 0.0);
+    cplx vin = mk(i == j ? 1.0 : 0.0, 0.0);
+    if (vwarm) {
+        cplx v = vwarm[i * 4 + j];
+        if (__ballot_sync(0xffffffffu, cabs2(v) > 0.0)) vin = v;     // all-zero = no warm start yet
+    }
+    scratch[lane] = (half == 0) ? ((i < d && j < d) ? Es[i * d + j] : mk(i == j ? 1.0 : 0.0, 0.0)) : vin;
+    __syncwarp();
+    if (half == 0) {
+        x = mk(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) cfma(x, scratch[i * 4 + k], scratch[16 + k * 4 + j]);   // E V_prev
+    } else {
+        x = vin;
+    }
+    __syncwarp();
     const double tol2 = 4e-30;
     int quiet = 0;                                   // consecutive rounds without a rotation
     for (int it = 0; it < 90 && quiet < 3; it++) {
@@ -251,8 +268,10 @@ __device__ void polar_conj_warp(const cplx* Es, int d, cplx* gate_out, cplx* scr
             polar_conj(E, d, P);
             for (int k = 0; k < d * d; k++) gate_out[k] = P[k];
         }
+        if (vwarm && half) vwarm[i * 4 + j] = mk(0.0, 0.0);
         return;
     }
+    if (vwarm && half) vwarm[i * 4 + j] = x;
     if (half == 0) x = cscale(x, 1.0 / sig);
     scratch[lane] = x;                                // [0..15] = U, [16..31] = V
     __syncwarp();
@@ -372,7 +391,7 @@ template <int NU, int CD, int PD>
 __global__ void __launch_bounds__(NT)
 k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int q0,
             const cplx* __restrict__ Gpend, cplx* __restrict__ partials, unsigned int* __restrict__ counter,
-            cplx* __restrict__ gate_out, cplx* __restrict__ env_out) {
+            cplx* __restrict__ gate_out, cplx* __restrict__ env_out, cplx* __restrict__ vwarm) {
     constexpr int GSZ = 1 << NU;
     constexpr int CSH = NU - (CD == 4 ? 2 : 1);
     constexpr int NLOW = 1 << CSH;
@@ -451,9 +470,11 @@ k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int 
     __shared__ cplx Es[16];
     {
         const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
-        const volatile double* pv = (const volatile double*)partials;
+        // L2 loads (other CTAs wrote these; the fence above orders them), batched so they overlap
+        const double* pv = (const double*)partials;
         double ssum = 0.0;
-        for (unsigned int b = sl; b < gridDim.x; b += NT / 32) ssum += pv[(long long)b * 32 + e];
+#pragma unroll 8
+        for (unsigned int b = sl; b < gridDim.x; b += NT / 32) ssum += __ldcg(pv + (long long)b * 32 + e);
         Ep[threadIdx.x] = ssum;
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -468,7 +489,7 @@ k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int 
     __syncthreads();
     __shared__ cplx pol_scratch[32];
     if (threadIdx.x < 32) {
-        polar_conj_warp(Es, CD, gate_out, pol_scratch);
+        polar_conj_warp(Es, CD, gate_out, pol_scratch, vwarm);
         if (env_out && threadIdx.x < CD * CD) env_out[threadIdx.x] = Es[threadIdx.x];
         if (threadIdx.x == 0) {
             *counter = 0u;
@@ -547,18 +568,21 @@ extern "C" int qm_circuit_states(void* cs_, int n_sites, const void* gates, cons
 namespace {
 template <int NU, int CD, int PD>
 void launch_env_fused(cplx* tbar, const cplx* c, int nbits, int q0, const cplx* Gpend, cplx* partials,
-                      unsigned int* counter, cplx* gate_out, cplx* env_out, cudaStream_t st) {
+                      unsigned int* counter, cplx* gate_out, cplx* env_out, cplx* vwarm, cudaStream_t st) {
     const long long ngroups = 1LL << (nbits - NU);
     qm_prof_work(QM_CLS_ENV, (PD > 0 ? 48.0 : 32.0) * (double)(1LL << nbits));
+    // one group per thread (a 148-CTA persistent grid measured slower: 35 vs 30 us at 20 qubits, the
+    // per-iteration load latency is not overlapped at 1 CTA/SM)
     QM_LAUNCH(QM_CLS_ENV, st, (k_env_fused<NU, CD, PD><<<grid_groups(ngroups), NT, 0, st>>>(
-        tbar, c, nbits, q0, Gpend, partials, counter, gate_out, env_out)));
+        tbar, c, nbits, q0, Gpend, partials, counter, gate_out, env_out, vwarm)));
 }
 }  // namespace
 
 // One environment sweep using the stored intermediates cs (from qm_circuit_states).
 // tbar = conj(target) on entry; gates updated in place.
 extern "C" int qm_sweep_stored(const void* cs_, void* tbar_, int n_sites, void* gates_, const int* sites,
-                               const int* kinds, int n_gates, void* work, void* envs_, void* stream) {
+                               const int* kinds, int n_gates, void* work, void* envs_, void* vwarm_, void* stream) {
+    cplx* vwarm = (cplx*)vwarm_;
     cudaStream_t st = (cudaStream_t)stream;
     const cplx* cs = (const cplx*)cs_;
     cplx* tbar = (cplx*)tbar_;
@@ -573,6 +597,7 @@ extern "C" int qm_sweep_stored(const void* cs_, void* tbar_, int n_sites, void* 
         cplx* G = gates + (long long)g * 16;
         cplx* env = envs ? envs + (long long)g * 16 : nullptr;
         const cplx* c = cs + (long long)g * n;
+        cplx* vw = vwarm ? vwarm + (long long)g * 16 : nullptr;
         const int ck = kinds[g];
         const int cb = (ck == 2) ? N - 2 - sites[g] : N - 1 - sites[g];      // lowest bit of the current gate
         bool fused = false;
@@ -582,16 +607,16 @@ extern "C" int qm_sweep_stored(const void* cs_, void* tbar_, int n_sites, void* 
             const int pb = (pk == 2) ? N - 2 - sites[g + 1] : N - 1 - sites[g + 1];
             const int ptop = pb + (pk == 2 ? 1 : 0);                          // highest bit of the pending gate
             if (ck == 2 && pk == 2 && ptop == cb) {                          // overlap on one site
-                launch_env_fused<3, 4, 4>(tbar, c, N, pb, Gp, partials, counter, G, env, st);
+                launch_env_fused<3, 4, 4>(tbar, c, N, pb, Gp, partials, counter, G, env, vw, st);
                 fused = true;
             } else if (ck == 2 && pk == 1 && pb == cb) {
-                launch_env_fused<2, 4, 2>(tbar, c, N, pb, Gp, partials, counter, G, env, st);
+                launch_env_fused<2, 4, 2>(tbar, c, N, pb, Gp, partials, counter, G, env, vw, st);
                 fused = true;
             } else if (ck == 1 && pk == 2 && ptop == cb - 1) {
-                launch_env_fused<3, 2, 4>(tbar, c, N, pb, Gp, partials, counter, G, env, st);
+                launch_env_fused<3, 2, 4>(tbar, c, N, pb, Gp, partials, counter, G, env, vw, st);
                 fused = true;
             } else if (ck == 1 && pk == 1 && pb == cb - 1) {
-                launch_env_fused<2, 2, 2>(tbar, c, N, pb, Gp, partials, counter, G, env, st);
+                launch_env_fused<2, 2, 2>(tbar, c, N, pb, Gp, partials, counter, G, env, vw, st);
                 fused = true;
             } else {
                 int e = launch_gate(tbar, N, sites[g + 1], pk, Gp, 2, st);    // tbar <- G_new^T tbar (unfused)
@@ -599,8 +624,8 @@ extern "C" int qm_sweep_stored(const void* cs_, void* tbar_, int n_sites, void* 
             }
         }
         if (!fused) {
-            if (ck == 2) launch_env_fused<2, 4, 0>(tbar, c, N, cb, nullptr, partials, counter, G, env, st);
-            else launch_env_fused<1, 2, 0>(tbar, c, N, cb, nullptr, partials, counter, G, env, st);
+            if (ck == 2) launch_env_fused<2, 4, 0>(tbar, c, N, cb, nullptr, partials, counter, G, env, vw, st);
+            else launch_env_fused<1, 2, 0>(tbar, c, N, cb, nullptr, partials, counter, G, env, vw, st);
         }
     }
     QM_CHECK_LAUNCH();

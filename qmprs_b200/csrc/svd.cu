@@ -156,7 +156,7 @@ constexpr size_t EIG_SMEM = 2ull * PMAX * GS * sizeof(cplx);   // g, q
 constexpr int NTE = 768;   // k_eig block: 256 threads update G, 512 update Q in the same pass
 __global__ void __launch_bounds__(NTE)
 k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, double tol2, int max_inner,
-      int cross_only, int round, int nbp, int single, int* __restrict__ notconv, int* __restrict__ rotated,
+      float cross_ratio, int cross_only, int round, int nbp, int single, int* __restrict__ notconv, int* __restrict__ rotated,
       double* __restrict__ sig2, const int* __restrict__ done) {
     if (done && *done) return;      // static (sync-free) mode: this SVD already converged
     extern __shared__ __align__(16) unsigned char eig_smem[];
@@ -233,7 +233,7 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
     __syncthreads();
     // cross-only schedule while the intra-block residual is well below the cross-block one
     const bool cross = cross_only && !single && n == PMAX &&
-                       (__int_as_float(s_mi) <= 1e-2f * __int_as_float(s_mc));
+                       (__int_as_float(s_mi) <= cross_ratio * __int_as_float(s_mc));
     const int nrounds = cross ? BSZ : ne - 1;
     if (s_off) {
         for (int sweep = 0; sweep < max_inner; sweep++) {
@@ -708,7 +708,10 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
     }
     // schedule knobs (defaults chosen from the sweep study in profiles/; env overrides for experiments)
     static int tune_inner0 = -1, tune_inner = 1, tune_cross = 1;
+    static float tune_ratio = 1e-2f;
     if (tune_inner0 < 0) {
+        const char* e3 = getenv("QM_SVD_CROSS_RATIO");
+        if (e3) tune_ratio = (float)atof(e3);
         const char* e0 = getenv("QM_SVD_INNER0");
         const char* e1 = getenv("QM_SVD_INNER");
         const char* e2 = getenv("QM_SVD_CROSS");
@@ -733,7 +736,7 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
                     w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, w.G, donep));
             }
             QM_LAUNCH(QM_CLS_SVD_EIG, st, k_eig<<<g.npairs, NTE, EIG_SMEM, st>>>(
-                w.G, g.single ? 0 : ncg, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, cross_only, r, g.nbp, g.single, w.notconv,
+                w.G, g.single ? 0 : ncg, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, tune_ratio, cross_only, r, g.nbp, g.single, w.notconv,
                 w.rotated, w.sig2, donep));
             if (g.single) {
                 QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply<<<dim3(nca, g.npairs), NT, 0, st>>>(

@@ -272,12 +272,13 @@ def optimize_layers(K, target, gates_all, kinds_per_layer, n_sites, num_sweeps, 
     stored_bytes = (len(sites) + 1) * 16 * (1 << n_sites)
     use_stored = stored and stored_bytes <= STORED_SWEEP_MAX_BYTES
     c = None
+    vwarm = K.zeros((len(sites), 16)) if use_stored else None      # warm start of the 4x4 polar, per gate
     for _ in range(num_sweeps):
         tbar = K.conj_scale_copy(target, conj=True)
         if use_stored:
             # every intermediate c_k stays in HBM; one fused pass per gate in the sweep
             c = K.circuit_states(n_sites, gates_all, sites, kinds, out=c)
-            K.sweep_stored(c, tbar, n_sites, gates_all, sites, kinds, envs)
+            K.sweep_stored(c, tbar, n_sites, gates_all, sites, kinds, envs, vwarm)
         else:
             c = K.circuit_state(n_sites, gates_all, sites, kinds, out=c)
             K.sweep(c, tbar, n_sites, gates_all, sites, kinds, envs)

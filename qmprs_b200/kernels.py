@@ -265,12 +265,12 @@ class CudaKernels:
                                                self._int_array(kinds), M, self._stream()), "qm_circuit_states")
         return cs
 
-    def sweep_stored(self, cs, tbar, n_sites, gates, sites, kinds, envs=None):
+    def sweep_stored(self, cs, tbar, n_sites, gates, sites, kinds, envs=None, vwarm=None):
         if self._sweep_work is None:
             self._sweep_work = torch.empty(int(self.lib.qm_sweep_work_bytes()), dtype=torch.uint8, device=self.device)
         self._check(self.lib.qm_sweep_stored(_p(cs), _p(tbar), n_sites, _p(gates), self._int_array(sites),
                                              self._int_array(kinds), len(sites), _p(self._sweep_work), _p(envs),
-                                             self._stream()), "qm_sweep_stored")
+                                             _p(vwarm), self._stream()), "qm_sweep_stored")
 
     # ---- instrumentation ------------------------------------------------------------
     def launch_count(self):

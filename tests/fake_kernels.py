@@ -228,7 +228,7 @@ class FakeKernels:
             self.apply_gate(cs[g + 1], n_sites, sites[g], kinds[g], gates[g], 0)
         return cs
 
-    def sweep_stored(self, cs, tbar, n_sites, gates, sites, kinds, envs=None):
+    def sweep_stored(self, cs, tbar, n_sites, gates, sites, kinds, envs=None, vwarm=None):
         N = n_sites
         for g in range(len(sites) - 1, -1, -1):
             site, kind = sites[g], kinds[g]
