@@ -98,3 +98,56 @@ def test_prepare_mps_does_not_modify_caller_mps(K):
     before = mps.mps.to_dense()
     Sequential(GateListCircuit).prepare_mps(mps, num_layers=2, num_sweeps=1)
     assert np.abs(mps.mps.to_dense() - before).max() == 0.0
+
+
+def _rand_state(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.random(2 ** n) + 1j * rng.random(2 ** n)
+    return v / np.linalg.norm(v)
+
+
+def test_reference_inequalities_through_public_api(K):
+    """The reference's own integration tests (tests/synthesis/mps_encoding/test_sequential_encoding.py)
+    run against the CUDA path: infidelity < 1e-2 at 8 qubits / 32 layers (:50-67), the
+    partial-entanglement depth bound (:91-121), 4-qubit one-sweep case (:123-155), monotone
+    improvement in layers (:157-181) and sweeps (:183-207)."""
+    from qmprs.synthesis.mps_encoding import Sequential
+    from qmprs_b200 import GateListCircuit
+    enc = Sequential(GateListCircuit)
+    psi = _rand_state(8, 0)
+    circ = enc.prepare_state(psi, 32, num_layers=32)
+    assert 1 - abs(np.vdot(psi, circ.get_statevector())) < 1e-2
+    # H(0) CX(0,3) H(4) H(5) CX(5,7)
+    n = 8
+    st = np.zeros(2 ** n, dtype=complex)
+    for b0 in (0, 1):
+        for b4 in (0, 1):
+            for b5 in (0, 1):
+                bits = [0] * n
+                bits[0] = b0; bits[3] = b0; bits[4] = b4; bits[5] = b5; bits[7] = b5
+                st[sum(b << q for q, b in enumerate(bits))] = 1
+    st /= np.linalg.norm(st)
+    circ = enc.prepare_state(st, 32, num_layers=1)
+    assert abs(np.vdot(st, circ.get_statevector())) > 0.99
+    assert circ.count_ops() == {"unitary1": 3, "unitary2": 5}
+    assert circ.get_depth() <= 20
+    # 4 qubits, 1 layer, 1 sweep
+    st = np.zeros(16, dtype=complex)
+    for b in (0, 1):
+        for h in (0, 1):
+            st[b | (b << 1) | (b << 2) | (h << 3)] = 1
+    st /= np.linalg.norm(st)
+    circ = enc.prepare_state(st, 16, num_layers=1, num_sweeps=1)
+    assert abs(np.vdot(st, circ.get_statevector())) > 0.99 and circ.get_depth() <= 7
+    # monotone in layers and sweeps
+    psi = _rand_state(8, 1)
+    prev = 0.0
+    for L in range(1, 7):
+        f = abs(np.vdot(psi, enc.prepare_state(psi, 64, num_layers=L).get_statevector()))
+        assert f >= prev - 1e-9
+        prev = f
+    prev = 0.0
+    for S in range(1, 6):
+        f = abs(np.vdot(psi, enc.prepare_state(psi, 64, num_layers=6, num_sweeps=S).get_statevector()))
+        assert f >= prev - 1e-9
+        prev = f
