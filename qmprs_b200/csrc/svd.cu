@@ -19,6 +19,7 @@
 //   m <  n :  A = J^H Sigma Z          U = J^H,  Vh = Z
 //   m >= n :  A = Z^T Sigma conj(J)    U = Z^T,  Vh = conj(J)
 #include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "qmprs_b200.h"
 
@@ -329,7 +330,13 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
     if (tid < n) sig2[pair_row(tid, pair, round, nbp, single)] = g[tid * GS + tid].x;
     if (tid == 0) {
         rotated[pair] = s_any;
-        if (s_off) atomicAdd(notconv, 1);
+        if (s_off) {
+            atomicAdd(notconv, 1);
+            // largest relative off-diagonal^2 met in this sweep (fresh Gram): lets the host skip the
+            // verification sweep when the quadratically convergent last sweep started below 1e-9
+            int mx = s_mc > s_mi ? s_mc : s_mi;
+            atomicMax(notconv + 2, mx);
+        }
     }
 }
 
@@ -602,9 +609,12 @@ __global__ void k_sort(const double* __restrict__ sig2, int nv, double* __restri
 }
 
 // static mode bookkeeping: end of a sweep / end of the SVD
-__global__ void k_sweep_end(int* __restrict__ nc) {
-    if (nc[0] == 0) nc[1] = 1;
+__global__ void k_sweep_end(int* __restrict__ nc, float early2) {
+    // converged: nothing above tol in this sweep, or everything already below the early threshold
+    // (the rotations just applied take it to ~early2, i.e. far below tol)
+    if (nc[0] == 0 || __int_as_float(nc[2]) <= early2) nc[1] = 1;
     nc[0] = 0;
+    nc[2] = 0;
 }
 __global__ void k_static_check(const int* __restrict__ nc, int* __restrict__ mismatch) {
     if (!nc[1]) mismatch[0] = 1;
@@ -628,7 +638,7 @@ Work carve(const Geom& g, void* base) {
     w.rotated = (int*)(b + off); off += align_up((size_t)g.npairs * sizeof(int));
     w.sig2 = (double*)(b + off); off += align_up((size_t)g.nvp * sizeof(double));
     w.perm = (int*)(b + off); off += align_up((size_t)g.nvp * sizeof(int));
-    w.notconv = (int*)(b + off); off += align_up(2 * sizeof(int));   // [0] not-converged count, [1] done flag
+    w.notconv = (int*)(b + off); off += align_up(4 * sizeof(int));   // [0] not-converged count, [1] done flag, [2] max rel off-diag^2 (float bits)
     w.total = off;
     return w;
 }
@@ -723,7 +733,8 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
     const bool is_static = fixed_sweeps > 0;
     const int* donep = is_static ? w.notconv + 1 : nullptr;
     if (is_static) max_sweeps = fixed_sweeps;
-    QM_CUDA(cudaMemsetAsync(w.notconv, 0, 2 * sizeof(int), st));
+    QM_CUDA(cudaMemsetAsync(w.notconv, 0, 4 * sizeof(int), st));
+    const float early2 = 1e-18f;     // (1e-9)^2
     for (; sweeps < max_sweeps;) {
         const int max_inner = (sweeps == 0) ? tune_inner0 : tune_inner;
         const int cross_only = (sweeps > 0 && tune_cross) ? 1 : 0;
@@ -753,14 +764,16 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         sweeps++;
         if (is_static) {
             // no host round trip: the remaining sweeps become empty launches once `done` is set
-            QM_LAUNCH(QM_CLS_SMALL, st, k_sweep_end<<<1, 1, 0, st>>>(w.notconv));
+            QM_LAUNCH(QM_CLS_SMALL, st, k_sweep_end<<<1, 1, 0, st>>>(w.notconv, early2));
             continue;
         }
-        int h = 0;
-        QM_CUDA(cudaMemcpyAsync(&h, w.notconv, sizeof(int), cudaMemcpyDeviceToHost, st));
+        int h[4] = {0, 0, 0, 0};
+        QM_CUDA(cudaMemcpyAsync(h, w.notconv, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         QM_CUDA(cudaStreamSynchronize(st));
-        QM_CUDA(cudaMemsetAsync(w.notconv, 0, sizeof(int), st));
-        if (h == 0) { converged = 1; break; }
+        QM_CUDA(cudaMemsetAsync(w.notconv, 0, 4 * sizeof(int), st));
+        float mx;
+        memcpy(&mx, &h[2], sizeof(float));
+        if (h[0] == 0 || mx <= early2) { converged = 1; break; }
     }
     if (is_static && mismatch) QM_LAUNCH(QM_CLS_SMALL, st, k_static_check<<<1, 1, 0, st>>>(w.notconv, mismatch));
     if (info_host) { info_host[0] = sweeps; info_host[1] = converged; }
