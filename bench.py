@@ -330,13 +330,23 @@ def run_batch(args, wl, K, dev, world, rank, sync_all, max_over_ranks):
     value = args.steps * B / (ms * 1e-3)
     if rank == 0:
         fid = float(np.mean([r["fidelity"] for r in recs]))
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import qmprs_oracle as O
+            t0 = time.perf_counter()
+            nref = 4
+            for s in range(nref):
+                O.prepare(states[s], n, chi, L, S, gauge="verbatim")
+            dt = (time.perf_counter() - t0) / nref
+            cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                   "sample": f"numpy oracle, {nref} states of the batch run one after the other (BLAS threads as configured)"}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "c128", "data": "synthetic",
             "config": {"workload": wl["name"], "n_qubits": n, "chi": chi, "layers": L, "sweeps": S, "batch": B,
                        "parallelism": f"states sharded over {world} GPU(s), one all-gather of records"},
-            "fidelity_mean": fid,
+            "fidelity_mean": fid, "cpu_baseline": cpu,
             "gpu_launches": int(K.launch_count() - l0 + (prep.replays * prep.nodes_per_graph if prep else 0)),
             "graph": ({"lanes": args.lanes, "kernel_nodes_per_state": prep.nodes_per_graph,
                        "eager_fallbacks": prep.fallbacks} if prep else None),
