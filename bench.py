@@ -277,6 +277,12 @@ def run_ours(args, wl):
             roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                     "traffic": None,
                     "peak_source": "FP64: cuBLAS ZGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)"}
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, cold cache)
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+            roof["traffic"] = traffic
+        except Exception:
+            pass
         roof.update({"kernel": dom, "launches": d_cnt, "avg_launch_us": 1e3 * d_ms / max(d_cnt, 1),
                      "share_of_kernel_time": d_ms / tot_ms, "latency_bound_classes": latency,
                      "classes": {k: {"ms": round(v[0], 3), "launches": v[1], "work": v[2]} for k, v in prof.items()}})
@@ -320,6 +326,7 @@ def run_batch(args, wl, K, dev, world, rank, sync_all, max_over_ranks):
         qb.prepare_state_batch(states[: 2 * world * max(args.lanes, 1)], chi, L, S, kernels=K, preparer=prep)
     sync_all()
     l0 = K.launch_count()
+    r0 = prep.replays if prep else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -347,7 +354,7 @@ def run_batch(args, wl, K, dev, world, rank, sync_all, max_over_ranks):
             "config": {"workload": wl["name"], "n_qubits": n, "chi": chi, "layers": L, "sweeps": S, "batch": B,
                        "parallelism": f"states sharded over {world} GPU(s), one all-gather of records"},
             "fidelity_mean": fid, "cpu_baseline": cpu,
-            "gpu_launches": int(K.launch_count() - l0 + (prep.replays * prep.nodes_per_graph if prep else 0)),
+            "gpu_launches": int(K.launch_count() - l0 + ((prep.replays - r0) * prep.nodes_per_graph if prep else 0)),
             "graph": ({"lanes": args.lanes, "kernel_nodes_per_state": prep.nodes_per_graph,
                        "eager_fallbacks": prep.fallbacks} if prep else None),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(B * 16 * 2 ** n // world),

@@ -509,66 +509,6 @@ k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int 
     env_epilogue<CD>(acc, partials, counter, gate_out, env_out, vwarm);
 }
 
-// Two threads per group for the dominant case (current 2-qubit gate on local bits (2,1), pending
-// 2-qubit gate on (1,0)): thread h owns the half bit2 = h of the 8-amplitude group.  The pending
-// gate acts inside each half, and the rows o = (bit2, bit1) of E split by half, so each thread
-// loads 4 tbar + 8 c values and keeps 16 accumulators: ~half the registers of the one-thread
-// version (2 CTAs/SM instead of 1) and twice the threads, i.e. 4x the warps to hide load latency.
-__global__ void __launch_bounds__(NT, 2)
-k_env_fused344_split(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int q0,
-                     const cplx* __restrict__ Gpend, cplx* __restrict__ partials,
-                     unsigned int* __restrict__ counter, cplx* __restrict__ gate_out, cplx* __restrict__ env_out,
-                     cplx* __restrict__ vwarm) {
-    __shared__ cplx Pm[16];
-    if (threadIdx.x < 16) {
-        int a = threadIdx.x / 4, b = threadIdx.x % 4;
-        Pm[threadIdx.x] = Gpend[b * 4 + a];                   // G^T
-    }
-    __syncthreads();
-    double acc16[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) acc16[i] = 0.0;
-    const long long ngroups = 1LL << (nbits - 3);
-    const long long stride = 1LL << q0;
-    const long long lowmask = stride - 1;
-    const int h = threadIdx.x & 1;
-    for (long long tt = (long long)blockIdx.x * blockDim.x + threadIdx.x; tt < 2 * ngroups;
-         tt += (long long)gridDim.x * blockDim.x) {
-        const long long t = tt >> 1;
-        const long long base = ((t >> q0) << (q0 + 3)) | (t & lowmask);
-        cplx tv[4], cv[8];
-#pragma unroll
-        for (int j = 0; j < 4; j++) tv[j] = tbar[base + (4 * h + j) * stride];
-#pragma unroll
-        for (int j = 0; j < 8; j++) cv[j] = c[base + j * stride];
-        cplx y[4];
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-            cplx sacc = mk(0.0, 0.0);
-#pragma unroll
-            for (int b = 0; b < 4; b++) cfma(sacc, Pm[a * 4 + b], tv[b]);
-            y[a] = sacc;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) tbar[base + (4 * h + j) * stride] = y[j];
-        // rows o = 2h + oo of E: tbar index (o<<1)|lo = 4h + 2*oo + lo
-#pragma unroll
-        for (int oo = 0; oo < 2; oo++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                cplx e = mk(acc16[2 * (oo * 4 + b)], acc16[2 * (oo * 4 + b) + 1]);
-                cfma(e, y[2 * oo], cv[2 * b]);
-                cfma(e, y[2 * oo + 1], cv[2 * b + 1]);
-                acc16[2 * (oo * 4 + b)] = e.x;
-                acc16[2 * (oo * 4 + b) + 1] = e.y;
-            }
-    }
-    double acc[32];
-#pragma unroll
-    for (int i = 0; i < 16; i++) { acc[i] = h ? 0.0 : acc16[i]; acc[16 + i] = h ? acc16[i] : 0.0; }
-    env_epilogue<4>(acc, partials, counter, gate_out, env_out, vwarm);
-}
-
 __global__ void k_basis_state(cplx* __restrict__ x, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x)
@@ -678,10 +618,8 @@ extern "C" int qm_sweep_stored(const void* cs_, void* tbar_, int n_sites, void* 
             const int pb = (pk == 2) ? N - 2 - sites[g + 1] : N - 1 - sites[g + 1];
             const int ptop = pb + (pk == 2 ? 1 : 0);                          // highest bit of the pending gate
             if (ck == 2 && pk == 2 && ptop == cb) {                          // overlap on one site
-                const long long nthreads = 2LL << (N - 3);
-                qm_prof_work(QM_CLS_ENV, 48.0 * (double)n);
-                QM_LAUNCH(QM_CLS_ENV, st, k_env_fused344_split<<<grid_groups(nthreads), NT, 0, st>>>(
-                    tbar, c, N, pb, Gp, partials, counter, G, env, vw));
+                // (a two-threads-per-group variant with half the registers measured slower: 50 vs 30 us at 20 qubits)
+                launch_env_fused<3, 4, 4>(tbar, c, N, pb, Gp, partials, counter, G, env, vw, st);
                 fused = true;
             } else if (ck == 2 && pk == 1 && pb == cb) {
                 launch_env_fused<2, 4, 2>(tbar, c, N, pb, Gp, partials, counter, G, env, vw, st);
