@@ -214,7 +214,7 @@ def run_ours(args, wl):
     fid = []
     for i in range(W):
         flush.fill_(i)
-        fid.append(host.prepare(K, dev_states[i], n, chi, L, S)["fidelity"])
+        fid.append(host.prepare(K, dev_states[i], n, chi, L, S, split=args.split)["fidelity"])
     clocks = ClockSampler(local)
     sync_all()
     clocks.start()
@@ -223,7 +223,7 @@ def run_ours(args, wl):
     e0.record()
     for i in range(W, W + Ksteps):
         flush.fill_(i)
-        fid.append(host.prepare(K, dev_states[i], n, chi, L, S)["fidelity"])
+        fid.append(host.prepare(K, dev_states[i], n, chi, L, S, split=args.split)["fidelity"])
     e1.record()
     sync_all()
     launches = K.launch_count() - l0
@@ -233,6 +233,7 @@ def run_ours(args, wl):
 
     # ---- end to end through the public API with host buffers ----
     enc = Sequential(GateListCircuit)
+    enc.gate_split = args.split
     pinned = [torch.from_numpy(s).pin_memory().numpy() for s in states[W:]]
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -252,8 +253,19 @@ def run_ours(args, wl):
         # ---- roofline of the dominant kernel: one extra instrumented step (CUDA events per launch) ----
         peak_tf = measure_fp64_peak(torch, dev)
         K.prof_begin()
-        host.prepare(K, dev_states[-1], n, chi, L, S)
+        host.prepare(K, dev_states[-1], n, chi, L, S, split=args.split)
         prof = K.prof_end()
+        # same workload with the opt-in SVD-free re-split (identical circuit), reported beside `value`
+        alt = None
+        if args.split == "svd":
+            host.prepare(K, dev_states[0], n, chi, L, S, split="exact")
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            falt = [host.prepare(K, dev_states[W + i], n, chi, L, S, split="exact")["fidelity"] for i in range(Ksteps)]
+            a1.record()
+            torch.cuda.synchronize(dev)
+            alt = {"split": "exact", "value": Ksteps / (a0.elapsed_time(a1) * 1e-3), "unit": UNIT,
+                   "max_abs_fidelity_diff_vs_svd": float(np.max(np.abs(np.array(falt) - np.array(fid[W:W + Ksteps]))))}
         tot_ms = sum(v[0] for v in prof.values())
         # dominant kernel with a throughput roofline; latency-bound classes (no algorithmic-work model:
         # the 32x32 shared-memory eigen-solve, per-column Householder vectors, small kernels) are reported
@@ -280,7 +292,8 @@ def run_ours(args, wl):
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, cold cache)
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
-            roof["traffic"] = traffic
+            roof["traffic"] = traffic["bytes"] if traffic else None
+            roof["traffic_note"] = traffic.get("note") if traffic else None
         except Exception:
             pass
         roof.update({"kernel": dom, "launches": d_cnt, "avg_launch_us": 1e3 * d_ms / max(d_cnt, 1),
@@ -298,12 +311,13 @@ def run_ours(args, wl):
             "ms_per_step": ms / Ksteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "c128", "data": "synthetic",
             "config": {"workload": wl["name"], "n_qubits": n, "chi": chi, "layers": L, "sweeps": S,
-                       "states_per_step_per_gpu": 1, "l2": "256 MiB buffer rewritten between steps",
+                       "states_per_step_per_gpu": 1, "gate_split": args.split, "l2": "256 MiB buffer rewritten between steps",
                        "parallelism": f"{world} independent states (one per GPU), no data-path collective"},
             "s_per_state": ms * 1e-3 / Ksteps,
             "fidelity_mean": float(np.mean(fid[W:])),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(16 * 2 ** n), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "alt_exact_split": alt,
         }
         print(json.dumps(line))
     if world > 1:
@@ -375,6 +389,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split", default="svd", choices=["svd", "exact"],
+                    help="two-site re-split: 'svd' = reference arithmetic (default), 'exact' = gauge-free, no SVD")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

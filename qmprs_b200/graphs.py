@@ -21,7 +21,7 @@ from qmprs_b200.kernels import CudaKernels, get_kernels
 
 
 class _Lane:
-    def __init__(self, device, n, chi, L, S, threshold, sample_state):
+    def __init__(self, device, n, chi, L, S, threshold, sample_state, split="svd"):
         self.n, self.chi, self.L, self.S, self.threshold = n, chi, L, S, threshold
         self.K = CudaKernels(device)                      # private workspaces
         self.stream = torch.cuda.Stream(device)
@@ -32,14 +32,14 @@ class _Lane:
         with torch.cuda.stream(self.stream):
             # eager warm-up on this lane: lazy initialisation, attribute calls, workspace growth
             self.psi_in.copy_(torch.from_numpy(sample_state))
-            host.prepare_device(K, self.psi_in, n, chi, L, S, threshold)
+            host.prepare_device(K, self.psi_in, n, chi, L, S, threshold, split=split)
         self.stream.synchronize()
         n0 = K.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=self.stream):
             K.begin_static()
             work = K.scale_copy(self.psi_in.reshape(-1, 1)).reshape(-1)
-            gates, kinds, ov, _, _ = host.prepare_device(K, work, n, chi, L, S, threshold)
+            gates, kinds, ov, _, _ = host.prepare_device(K, work, n, chi, L, S, threshold, split=split)
             K.end_static()
         self.nodes = K.launch_count() - n0
         self.gates, self.kinds, self.ov, self.mismatch = gates, kinds, ov, K.mismatch
@@ -79,7 +79,7 @@ class GraphedPreparer:
     """``prepare_state`` for a stream of equally sized states through captured CUDA graphs."""
 
     def __init__(self, n_qubits, bond_dimension, num_layers=1, num_sweeps=0, threshold=1 - 1e-6, lanes=4,
-                 device=None):
+                 device=None, split="svd"):
         if not isinstance(num_layers, int) or num_layers < 1:
             raise ValueError("The number of layers must be a positive integer.")
         if device is None:
@@ -89,7 +89,8 @@ class GraphedPreparer:
         rng = np.random.default_rng(12345)
         sample = rng.random(2 ** n_qubits) + 1j * rng.random(2 ** n_qubits)
         sample /= np.linalg.norm(sample)
-        self.lanes = [_Lane(device, *self.cfg, sample) for _ in range(int(lanes))]
+        self.split = split
+        self.lanes = [_Lane(device, *self.cfg, sample, split=split) for _ in range(int(lanes))]
         self.eager = get_kernels(device)
         self.fallbacks = 0
         self.replays = 0
@@ -102,7 +103,7 @@ class GraphedPreparer:
         tag, res, state = lane.collect()
         if res is None:                                   # an assumption failed: eager path, exact semantics
             n, chi, L, S, thr = self.cfg
-            res = host.prepare(self.eager, state, n, chi, L, S, thr)
+            res = host.prepare(self.eager, state, n, chi, L, S, thr, split=self.split)
             res.pop("mps", None)
             self.fallbacks += 1
         out[tag] = res

@@ -208,10 +208,18 @@ def blocks_from_kinds(kinds):
 # --------------------------------------------------------------------------------------
 # A6  inverse layer application       mps.py:933-971 (quimb gate_ / gate_split_)
 # --------------------------------------------------------------------------------------
-def apply_inverse_layer(K, B, gates, kinds, spectra=None, inverse=True):
+def apply_inverse_layer(K, B, gates, kinds, spectra=None, inverse=True, split="svd"):
     """In place on the list ``B``.  theta = G^H (A_i A_{i+1}); SVD, cutoff 1e-10 'rsum2'
     with Frobenius renorm, sqrt(s) to both sides, no max_bond.  ``inverse=False`` is the
-    forward application (mps.py:893-931): G itself, sites in ascending order."""
+    forward application (mps.py:893-931): G itself, sites in ascending order.
+
+    ``split="exact"`` (opt-in, not the reference's arithmetic): the reference never truncates
+    here (cutoff only), and everything downstream -- the chi=2 truncation through left
+    environments, the |0..0> overlap, the next contraction -- depends on the STATE, not on the
+    gauge of the two site tensors.  So theta is re-split trivially, theta = theta . 1 or 1 . theta
+    with bond min(2l, 2r) (the rank a generic state has anyway): no SVD, identical gates.  Not
+    available: gate-split spectra, and the 1e-10 rank cut for low-rank (structured) states, whose
+    bonds then grow to min(2l, 2r)."""
     for s, e in blocks_from_kinds(kinds):
         order = range(e, s - 1, -1) if inverse else range(s, e + 1)
         for i in order:
@@ -224,6 +232,14 @@ def apply_inverse_layer(K, B, gates, kinds, spectra=None, inverse=True):
                 _, _, r = B[i + 1].shape
                 X = K.gemm(B[i].reshape(l * 2, b), B[i + 1].reshape(b, 2 * r))
                 K.theta_gate(X, l, r, G, dagger=inverse)
+                if split == "exact":
+                    if 2 * l <= 2 * r:
+                        B[i] = K.eye(2 * l).reshape(l, 2, 2 * l)
+                        B[i + 1] = X.reshape(2 * l, 2, r)
+                    else:
+                        B[i] = X.reshape(l, 2, 2 * r)
+                        B[i + 1] = K.eye(2 * r).reshape(2 * r, 2, r)
+                    continue
                 U, S, Vh = K.svd(X)
                 k = S.shape[0]
                 if spectra is not None:
@@ -325,7 +341,7 @@ def build_mps(K, psi, n_sites, chi, record=None, fused=True):
     return canonicalize_truncate(K, A, chi, rec.setdefault("truncate", []))
 
 
-def disentangle(K, A, num_layers, threshold, record=None):
+def disentangle(K, A, num_layers, threshold, record=None, split="svd"):
     """``_get_unitary_layers`` (sequential.py:330-398).  Returns (gates_all [L*N,16] in
     application order, kinds_per_layer, overlaps)."""
     import torch
@@ -340,7 +356,7 @@ def disentangle(K, A, num_layers, threshold, record=None):
     for _ in range(num_layers):
         gates, kinds = chi2_layer(K, B)                               # mps.py:849-891
         sp = []
-        apply_inverse_layer(K, B, gates, kinds, sp)                   # sequential.py:326
+        apply_inverse_layer(K, B, gates, kinds, sp, split=split)      # sequential.py:326
         rec.setdefault("gate_split", []).append(sp)
         layer_gates.append(gates)
         layer_kinds.append(kinds)
@@ -355,14 +371,15 @@ def disentangle(K, A, num_layers, threshold, record=None):
     return gates_all, layer_kinds, overlaps
 
 
-def prepare_device(K, psi, n_sites, chi, num_layers, num_sweeps, threshold=1 - 1e-6, record=None, fused=True):
+def prepare_device(K, psi, n_sites, chi, num_layers, num_sweeps, threshold=1 - 1e-6, record=None, fused=True,
+                   split="svd"):
     """Device-to-device core of :func:`prepare`: ``psi`` is a device vector (overwritten by its
     normalised copy), returns device tensors (gates_all [L*N,16], kinds per layer, overlap [2] =
     <psi|circuit> as (re, im), overlaps list).  No host transfer; this is what graphs.py captures."""
     N = int(n_sites)
     K.div_sqrt(psi, K.vdot(psi, psi))                                 # quick Ket normalisation
     A = build_mps(K, psi, N, chi, record, fused)
-    gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record)
+    gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record, split)
     if num_sweeps > 0:
         target = to_dense(K, A)                                       # sequential.py:440 (mps.mps)
         optimize_layers(K, target, gates_all, layer_kinds, N, num_sweeps)
@@ -372,7 +389,7 @@ def prepare_device(K, psi, n_sites, chi, num_layers, num_sweeps, threshold=1 - 1
 
 
 def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 - 1e-6, record=None,
-            mps=None, fused=True):
+            mps=None, fused=True, split="svd"):
     """Whole path on the device.  ``psi_host``: complex128 numpy vector or device tensor.
     Returns dict(gates [L,N,16] numpy, kinds [L][N], n_layers, overlaps, fidelity)."""
     N = int(n_sites)
@@ -382,10 +399,10 @@ def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 -
         psi = K.from_host(np.asarray(psi_host, dtype=np.complex128).reshape(-1))
     if mps is None:
         gates_all, layer_kinds, ovt, overlaps, A = prepare_device(K, psi, N, chi, num_layers, num_sweeps,
-                                                                  threshold, record, fused)
+                                                                  threshold, record, fused, split)
     else:
         A = mps
-        gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record)
+        gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record, split)
         if num_sweeps > 0:
             optimize_layers(K, to_dense(K, A), gates_all, layer_kinds, N, num_sweeps)
         sites, kinds = flat_schedule(layer_kinds, N)

@@ -60,6 +60,9 @@ class CudaKernels:
     def zeros(self, shape, dtype=C128):
         return torch.zeros(shape, dtype=dtype, device=self.device)
 
+    def eye(self, n, dtype=C128):
+        return torch.eye(n, dtype=dtype, device=self.device)
+
     def from_host(self, arr, dtype=C128):
         return torch.as_tensor(np.ascontiguousarray(arr)).to(dtype).to(self.device)
 

@@ -19,6 +19,10 @@ class Sequential(MPSEncoder):
         super().__init__(circuit_framework)
         self._fidelity_threshold = 1 - 1e-6          # sequential.py:120
         self.last_result = None                      # diagnostics of the last call (not in the reference)
+        # "svd": re-split every two-site gate application by a truncated SVD as the reference does
+        # (mps.py:968-971).  "exact": gauge-free trivial re-split, identical circuit, no SVD
+        # (qmprs_b200.host.apply_inverse_layer); opt-in.
+        self.gate_split = "svd"
 
     @property
     def fidelity_threshold(self) -> float:
@@ -54,7 +58,10 @@ class Sequential(MPSEncoder):
         A = mps.mps.tensors
         N = mps.num_sites
         record = {}
-        gates_all, layer_kinds, overlaps = host.disentangle(K, A, num_layers, self._fidelity_threshold, record)
+        if self.gate_split not in ("svd", "exact"):
+            raise ValueError("`gate_split` must be 'svd' or 'exact'.")
+        gates_all, layer_kinds, overlaps = host.disentangle(K, A, num_layers, self._fidelity_threshold, record,
+                                                            split=self.gate_split)
         if num_sweeps > 0:
             target = host.to_dense(K, A)
             host.optimize_layers(K, target, gates_all, layer_kinds, N, num_sweeps)

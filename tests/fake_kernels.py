@@ -39,6 +39,9 @@ class FakeKernels:
     def zeros(self, shape, dtype=C128):
         return torch.zeros(shape, dtype=dtype)
 
+    def eye(self, n, dtype=C128):
+        return torch.eye(n, dtype=dtype)
+
     def from_host(self, arr, dtype=C128):
         return torch.as_tensor(np.ascontiguousarray(arr)).to(dtype).clone()
 

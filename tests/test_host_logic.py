@@ -80,3 +80,15 @@ def test_mirror_roundtrip():
     M = host.mirror(K, host.mirror(K, A))
     for a, b in zip(A, M):
         assert a.shape == b.shape and np.abs(K.to_host(a) - K.to_host(b)).max() == 0.0
+
+
+@pytest.mark.parametrize("n,chi,L,S", [(6, 64, 4, 2), (8, 4, 4, 1), (10, 512, 8, 0)])
+def test_exact_split_gives_the_same_circuit(n, chi, L, S):
+    """split="exact" (no SVD when re-splitting theta) changes only the gauge of the working MPS:
+    gates, layer count and fidelity equal the SVD mode."""
+    psi = O.random_state(n, 21)
+    a = host.prepare(FakeKernels(), psi, n, chi, L, S, split="svd")
+    b = host.prepare(FakeKernels(), psi, n, chi, L, S, split="exact")
+    assert a["n_layers"] == b["n_layers"] and a["kinds"] == b["kinds"]
+    assert np.abs(a["gates"] - b["gates"]).max() < 1e-7
+    assert abs(a["fidelity"] - b["fidelity"]) < 1e-10

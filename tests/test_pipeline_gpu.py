@@ -171,3 +171,15 @@ def test_fused_build_equals_two_pass(K, n, chi, L, S):
     g = rd["gates"].reshape(-1, 16)
     for idx, (_, _, _, _, G) in enumerate(flat):
         assert np.abs(g[idx][: G.size] - G.reshape(-1)).max() <= 1e-6
+
+
+@pytest.mark.parametrize("n,chi,L,S", [(8, 32, 5, 2), (10, 8, 4, 1), (12, 64, 6, 0)])
+def test_exact_split_matches_svd_split(K, n, chi, L, S):
+    """Opt-in gauge-free re-split of theta (no SVD) vs the reference's truncated-SVD re-split:
+    identical layer structure, gates within 1e-7, fidelity within 1e-9."""
+    psi = O.random_state(n, 17)
+    a = host.prepare(K, psi, n, chi, L, S, split="svd")
+    b = host.prepare(K, psi, n, chi, L, S, split="exact")
+    assert a["n_layers"] == b["n_layers"] and a["kinds"] == b["kinds"]
+    assert np.abs(a["gates"] - b["gates"]).max() <= 1e-7
+    assert abs(a["fidelity"] - b["fidelity"]) <= 1e-9
