@@ -177,8 +177,9 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
         const double* Gp = G + (long long)pair * nchunks * PMAX * PMAX * 2;
         for (int e = tid; e < n * n; e += NTE) {
             double re = 0.0, im = 0.0;
-            for (int c = 0; c < nchunks; c++) {
-                const double2 v = *(const double2*)(Gp + (long long)c * PMAX * PMAX * 2 + 2 * e);
+#pragma unroll 4
+            for (int c = 0; c < nchunks; c++) {            // independent L2 loads, fixed summation order
+                const double2 v = __ldcg((const double2*)(Gp + (long long)c * PMAX * PMAX * 2 + 2 * e));
                 re += v.x; im += v.y;
             }
             int i = e / n, j = e % n;
@@ -201,8 +202,15 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
         sched[2 * e + 1] = (unsigned char)b;
     }
     // per-thread work items of the update phase do not depend on the round
-    // threads [0,256): one 2x2 block of G each (np*np <= 256); threads [256,768): one (pair, column) item of Q
-    const int blk_k = tid / np, blk_l = tid % np;
+    // threads [0, np(np+1)/2): one upper 2x2 block (k <= l) of the Hermitian G each, mirrored on store;
+    // threads [256,768): one (pair, column) item of Q
+    int blk_k = 0, blk_l = 0;
+    const int nblk = np * (np + 1) / 2;
+    if (tid < nblk) {
+        int k = 0, rem = tid;
+        while (rem >= np - k) { rem -= np - k; k++; }
+        blk_k = k; blk_l = k + rem;
+    }
     const int qt = tid - 256;
     const int q_k0 = qt >= 0 ? qt / n : np, q_c0 = qt >= 0 ? qt % n : 0;
     if (tid == 0) { s_any = 0; s_off = 0; s_mc = 0; s_mi = 0; }
@@ -277,7 +285,7 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
                 if (s_round) {
                     // G' = R G R^H by 2x2 blocks: block (k,l) = rows {p_k,q_k} x cols {p_l,q_l} depends only
                     // on the same block of G (4 loads, 4 stores).  In place: every block is owned by one thread.
-                    if (tid < np * np) {
+                    if (tid < nblk) {
                         const int k = blk_k, l = blk_l;
                         const int pk = rpp[k], qk = rqq[k], pl = rpp[l], ql = rqq[l];
                         const bool vk = qk < n, vl = ql < n;           // dummy partner (odd n): single row/col
@@ -305,6 +313,12 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
                         if (vl) g[pk * GS + ql] = b01;
                         if (vk) g[qk * GS + pl] = b10;
                         if (vk && vl) g[qk * GS + ql] = b11;
+                        if (k != l) {                       // mirror block (l,k) = (block (k,l))^H
+                            g[pl * GS + pk] = cconj(b00);
+                            if (vl) g[ql * GS + pk] = cconj(b01);
+                            if (vk) g[pl * GS + qk] = cconj(b10);
+                            if (vk && vl) g[ql * GS + qk] = cconj(b11);
+                        }
                     }
                     // Q' = R Q : rows p_k, q_k
                     {
