@@ -202,15 +202,10 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
         sched[2 * e + 1] = (unsigned char)b;
     }
     // per-thread work items of the update phase do not depend on the round
-    // threads [0, np(np+1)/2): one upper 2x2 block (k <= l) of the Hermitian G each, mirrored on store;
-    // threads [256,768): one (pair, column) item of Q
-    int blk_k = 0, blk_l = 0;
-    const int nblk = np * (np + 1) / 2;
-    if (tid < nblk) {
-        int k = 0, rem = tid;
-        while (rem >= np - k) { rem -= np - k; k++; }
-        blk_k = k; blk_l = k + rem;
-    }
+    // threads [0,256): one 2x2 block of G each (np*np <= 256); threads [256,768): one (pair, column) item of Q.
+    // (updating only the upper blocks k <= l and mirroring them was measured slightly slower)
+    const int blk_k = tid / np, blk_l = tid % np;
+    const int nblk = np * np;
     const int qt = tid - 256;
     const int q_k0 = qt >= 0 ? qt / n : np, q_c0 = qt >= 0 ? qt % n : 0;
     if (tid == 0) { s_any = 0; s_off = 0; s_mc = 0; s_mi = 0; }
@@ -313,12 +308,6 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
                         if (vl) g[pk * GS + ql] = b01;
                         if (vk) g[qk * GS + pl] = b10;
                         if (vk && vl) g[qk * GS + ql] = b11;
-                        if (k != l) {                       // mirror block (l,k) = (block (k,l))^H
-                            g[pl * GS + pk] = cconj(b00);
-                            if (vl) g[ql * GS + pk] = cconj(b01);
-                            if (vk) g[pl * GS + qk] = cconj(b10);
-                            if (vk && vl) g[ql * GS + qk] = cconj(b11);
-                        }
                     }
                     // Q' = R Q : rows p_k, q_k
                     {
