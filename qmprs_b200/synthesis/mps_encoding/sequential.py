@@ -23,6 +23,11 @@ class Sequential(MPSEncoder):
         # (mps.py:968-971).  "exact": gauge-free trivial re-split, identical circuit, no SVD
         # (qmprs_b200.host.apply_inverse_layer); opt-in.
         self.gate_split = "svd"
+        # CUDA-graph replay for small registers (qmprs_b200.graphs): "auto" captures the pipeline the
+        # second time the same (n, chi, layers, sweeps) is requested with n <= 16; True / False force it.
+        self.use_cuda_graphs = "auto"
+        self._graph_cache = {}
+        self._graph_seen = {}
 
     @property
     def fidelity_threshold(self) -> float:
@@ -70,6 +75,38 @@ class Sequential(MPSEncoder):
         self.last_result = {"gates": gates, "kinds": layer_kinds, "n_layers": L, "overlaps": overlaps,
                             "gates_device": gates_all}
         return self._circuit_from_unitary_layers(N, gates, layer_kinds)
+
+    def prepare_state(self, statevector, bond_dimension, compression_percentage=0.0, index_type="row", **kwargs):
+        """base.py:58-106.  Same contract; small registers requested repeatedly are served by a captured
+        CUDA graph (static shapes validated on the device, eager re-run when an assumption fails)."""
+        num_layers = kwargs.get("num_layers", 1)
+        num_sweeps = kwargs.get("num_sweeps", 0)
+        if not isinstance(num_layers, int) or num_layers < 1:
+            raise ValueError("The number of layers must be a positive integer.")
+        from qmprs_b200.ket import Ket
+        if not isinstance(statevector, Ket):
+            statevector = Ket(statevector)
+        n = statevector.num_qubits
+        key = (n, int(bond_dimension), num_layers, int(num_sweeps), float(self._fidelity_threshold), self.gate_split)
+        want = self.use_cuda_graphs
+        plain = compression_percentage == 0.0 and index_type == "row" and n >= 2
+        if want and plain and (want is True or (n <= 16 and self._graph_seen.get(key, 0) >= 1)):
+            prep = self._graph_cache.get(key)
+            if prep is None:
+                try:
+                    from qmprs_b200.graphs import GraphedPreparer
+                    prep = GraphedPreparer(n, int(bond_dimension), num_layers, int(num_sweeps),
+                                           float(self._fidelity_threshold), lanes=1, split=self.gate_split)
+                except Exception:                          # capture not possible here: stay on the eager path
+                    prep = False
+                self._graph_cache[key] = prep
+            if prep:
+                res = prep.run(np.asarray(statevector.data, dtype=np.complex128).reshape(1, -1))[0]
+                self.last_result = {"gates": res["gates"], "kinds": res["kinds"], "n_layers": res["n_layers"],
+                                    "overlaps": res.get("overlaps"), "graph": True}
+                return self._circuit_from_unitary_layers(n, res["gates"], res["kinds"])
+        self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
+        return super().prepare_state(statevector, bond_dimension, compression_percentage, index_type, **kwargs)
 
     def prepare_mps(self, mps: MPS, **kwargs):
         num_layers = kwargs.get("num_layers", 1)

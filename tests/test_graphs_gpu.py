@@ -46,3 +46,20 @@ def test_graph_falls_back_when_assumptions_fail(K):
     assert host.blocks_from_kinds(out[0]["kinds"][0]) == [(i, i) for i in range(n)]
     assert out[1]["n_layers"] == 2
     assert out[2]["fidelity"] > 1 - 1e-9
+
+
+def test_sequential_switches_to_graph_on_repeat(K):
+    """Sequential.prepare_state serves the second and later requests of the same small configuration
+    from a captured graph; circuits are identical to the eager ones."""
+    from qmprs.synthesis.mps_encoding import Sequential
+    from qmprs_b200 import GateListCircuit
+    enc = Sequential(GateListCircuit)
+    eager = Sequential(GateListCircuit)
+    eager.use_cuda_graphs = False
+    for s in range(3):
+        psi = O.random_state(8, 300 + s)
+        c1 = enc.prepare_state(psi, 32, num_layers=3, num_sweeps=2)
+        c2 = eager.prepare_state(psi, 32, num_layers=3, num_sweeps=2)
+        assert bool(enc.last_result.get("graph")) == (s >= 1)
+        assert [q for _, q in c1.gates] == [q for _, q in c2.gates]
+        assert max(np.abs(a - b).max() for (a, _), (b, _) in zip(c1.gates, c2.gates)) <= 1e-9
