@@ -44,6 +44,12 @@ int qm_svd_static(int m, int n, const void* A, long long lda, void* U, long long
                   long long ldvh, void* work, long long work_bytes, double tol, int fixed_sweeps, void* mismatch,
                   void* stream);
 
+/* out (cols x rows) = in^T (optionally conjugated): the coalesced reshape/transposed-store kernels
+ * that stream the statevector in the TT-SVD (quimb from_dense reshapes, mps.py:242), exposed for
+ * tests and HBM-bandwidth measurement (32*rows*cols bytes per call). */
+int qm_transpose(void* out, long long ldo, const void* in, long long ldi, long long rows, long long cols, int conj,
+                 void* stream);
+
 /* Householder QR (LAPACK zgeqr2 layout), explicit thin Q, and R with non-negative
  * diagonal.  Replaces quimb qr_stabilized behind left_canonize / right_canonize /
  * tensor_compress_bond: mps.py:396-398, :451-453. */

@@ -25,6 +25,7 @@ SIGNATURES = {
     "qm_svd_static": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _d, _i, _vp, _vp]),
     "qm_expect_ints": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "qm_expect_not_close": (_i, [_vp, _d, _vp, _vp]),
+    "qm_transpose": (_i, [_vp, _ll, _vp, _ll, _ll, _ll, _i, _vp]),
     "qm_qr": (_i, [_i, _i, _vp, _ll, _vp, _vp]),
     "qm_qr_formq": (_i, [_i, _i, _vp, _ll, _vp, _vp, _ll, _vp]),
     "qm_qr_finish": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp]),

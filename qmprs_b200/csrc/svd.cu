@@ -580,6 +580,116 @@ __global__ void k_transpose(cplx* __restrict__ out, long long ldo, const cplx* _
     }
 }
 
+// Narrow variants of the transpose for the skinny TT-SVD splits (2^i x 2r with 2r <= 32): the
+// 32x32 tile kernel would use 2r of 32 tile columns.  Here one thread owns one long-axis index, so
+// both sides are coalesced: the narrow side is contiguous per thread (and per warp when the leading
+// dimension equals the width), the long side is contiguous across the warp.
+// out[a][j] = f(in[perm[j]][a]),  j < nsel (long, one thread each),  a < len <= 32
+__global__ void k_transpose_narrow_in(cplx* __restrict__ out, long long ldo, const cplx* __restrict__ in,
+                                      long long ldi, const int* __restrict__ perm, const double* __restrict__ S,
+                                      int conj, long long nsel, int len) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nsel;
+         j += (long long)gridDim.x * blockDim.x) {
+        const long long src = perm ? perm[j] : j;
+        double sc = 1.0;
+        if (S) { double sv = S[j]; sc = (sv > 0.0) ? 1.0 / sv : 0.0; }
+        const cplx* p = in + src * ldi;
+        for (int a = 0; a < len; a++) {
+            cplx v = p[a];
+            if (conj) v.y = -v.y;
+            out[(long long)a * ldo + j] = cscale(v, sc);
+        }
+    }
+}
+// out[a][j] = f(in[perm[j]][a]),  j < nsel <= 32,  a < len (long, one thread each)
+__global__ void k_transpose_narrow_out(cplx* __restrict__ out, long long ldo, const cplx* __restrict__ in,
+                                       long long ldi, const int* __restrict__ perm, const double* __restrict__ S,
+                                       int conj, int nsel, long long len) {
+    __shared__ long long srow[32];
+    __shared__ double ssc[32];
+    if (threadIdx.x < nsel) {
+        srow[threadIdx.x] = (long long)(perm ? perm[threadIdx.x] : threadIdx.x) * ldi;
+        double sc = 1.0;
+        if (S) { double sv = S[threadIdx.x]; sc = (sv > 0.0) ? 1.0 / sv : 0.0; }
+        ssc[threadIdx.x] = sc;
+    }
+    __syncthreads();
+    for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < len;
+         a += (long long)gridDim.x * blockDim.x) {
+        cplx* q = out + a * ldo;
+        for (int j = 0; j < nsel; j++) {
+            cplx v = in[srow[j] + a];
+            if (conj) v.y = -v.y;
+            q[j] = cscale(v, ssc[j]);
+        }
+    }
+}
+
+// Skinny Gram / update for <= 4 short vectors (first TT-SVD splits: 2 or 4 rows of 2^22..2^23
+// amplitudes): one column per thread, everything in registers, one pass over W at HBM speed.
+__global__ void __launch_bounds__(NT)
+k_gram_skinny(const cplx* __restrict__ W, long long ldw, long long len, int nrows, double* __restrict__ G,
+              const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double red[NT / 32][32];
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) acc[i] = 0.0;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < len;
+         c += (long long)gridDim.x * blockDim.x) {
+        cplx w[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) w[r] = (r < nrows) ? W[(long long)r * ldw + c] : mk(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                acc[2 * (i * 4 + j)] += w[i].x * w[j].x + w[i].y * w[j].y;        // w_i conj(w_j)
+                acc[2 * (i * 4 + j) + 1] += w[i].y * w[j].x - w[i].x * w[j].y;
+            }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 32; i++) acc[i] = warp_sum(acc[i]);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < 32; i++) red[warp][i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double ssum = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < NT / 32; w2++) ssum += red[w2][threadIdx.x];
+        int e = threadIdx.x >> 1, i = e >> 2, j = e & 3;
+        if (i < nrows && j < nrows) atomicAdd(&G[2 * (i * nrows + j) + (threadIdx.x & 1)], ssum);
+    }
+}
+
+__global__ void __launch_bounds__(NT)
+k_apply_skinny(cplx* __restrict__ W, long long ldw, long long lenx, int nrows, const cplx* __restrict__ Q,
+               const int* __restrict__ rotated, const int* __restrict__ done) {
+    if (done && *done) return;
+    if (!rotated[0]) return;
+    __shared__ cplx qs[16];
+    if (threadIdx.x < nrows * nrows) qs[(threadIdx.x / nrows) * 4 + (threadIdx.x % nrows)] = Q[threadIdx.x];
+    __syncthreads();
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < lenx;
+         c += (long long)gridDim.x * blockDim.x) {
+        cplx w[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) w[r] = (r < nrows) ? W[(long long)r * ldw + c] : mk(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (i < nrows) {
+                cplx a = mk(0.0, 0.0);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (j < nrows) cfma(a, qs[i * 4 + j], w[j]);
+                W[(long long)i * ldw + c] = a;
+            }
+        }
+    }
+}
+
 // identity block of Wext and zero padding rows
 __global__ void k_init_ext(cplx* __restrict__ W, long long ldw, int nv, int nvp, int len) {
     int r = blockIdx.y;
@@ -676,9 +786,15 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         // W[j][a] = A[a][j]: transpose of the m x n input
         // k_transpose maps in[perm[j]][a] -> out[a][j]; here "in" = A, out = W (n x m):
         // W[c][r] = A[r][c]  =>  nsel = m (rows of A), len = n (cols of A)
-        int na = ceil_div(n, 32);
-        QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose<<<(unsigned)((long long)na * ceil_div(m, 32)), dim3(32, 8), 0, st>>>(
-            w.W, g.ldw, A, lda, nullptr, nullptr, 0, m, n, na));
+        if (n <= 32) {
+            int nb = ceil_div(m, 256) > 148 * 16 ? 148 * 16 : ceil_div(m, 256);
+            QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose_narrow_in<<<nb, 256, 0, st>>>(
+                w.W, g.ldw, A, lda, nullptr, nullptr, 0, (long long)m, n));
+        } else {
+            int na = ceil_div(n, 32);
+            QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose<<<(unsigned)((long long)na * ceil_div(m, 32)), dim3(32, 8), 0, st>>>(
+                w.W, g.ldw, A, lda, nullptr, nullptr, 0, m, n, na));
+        }
     }
     QM_CHECK_LAUNCH();
     {
@@ -742,7 +858,11 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         const int max_inner = (sweeps == 0) ? tune_inner0 : tune_inner;
         const int cross_only = (sweeps > 0 && tune_cross) ? 1 : 0;
         for (int r = 0; r < g.rounds; r++) {
-            if (g.single) {
+            if (g.single && g.nrows <= 4 && g.len >= 4096) {
+                int nb = ceil_div(g.len, NT) > 148 * 4 ? 148 * 4 : ceil_div(g.len, NT);
+                QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram_skinny<<<nb, NT, 0, st>>>(w.W, g.ldw, (long long)g.len, g.nrows,
+                                                                              w.G, donep));
+            } else if (g.single) {
                 QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram<<<dim3(ncg, g.npairs), NT, 0, st>>>(
                     w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, g.single, g.nrows, w.G, donep));
             } else {
@@ -752,7 +872,11 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
             QM_LAUNCH(QM_CLS_SVD_EIG, st, k_eig<<<g.npairs, NTE, EIG_SMEM, st>>>(
                 w.G, g.single ? 0 : ncg, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, tune_ratio, cross_only, r, g.nbp, g.single, w.notconv,
                 w.rotated, w.sig2, donep));
-            if (g.single) {
+            if (g.single && g.nrows <= 4 && g.len >= 4096) {
+                int nb = ceil_div(lenx, NT) > 148 * 8 ? 148 * 8 : ceil_div(lenx, NT);
+                QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply_skinny<<<nb, NT, 0, st>>>(w.W, g.ldw, lenx, g.nrows, w.Q,
+                                                                                w.rotated, donep));
+            } else if (g.single) {
                 QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply<<<dim3(nca, g.npairs), NT, 0, st>>>(
                     w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, g.single, g.nrows, w.Q, w.rotated, donep));
             } else {
@@ -798,7 +922,11 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         }
     } else {
         // U[a][j] = W[perm[j]][a] / S[j];  Vh[j][c] = conj(J[perm[j]][c])
-        if (U)
+        if (U && k <= 32) {
+            int nb = ceil_div(m, 256) > 148 * 16 ? 148 * 16 : ceil_div(m, 256);
+            QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose_narrow_out<<<nb, 256, 0, st>>>(
+                U, ldu, w.W, g.ldw, w.perm, S, 0, k, (long long)m));
+        } else if (U)
             QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose<<<(unsigned)((long long)ceil_div(m, 32) * ceil_div(k, 32)), dim3(32, 8), 0, st>>>(
                 U, ldu, w.W, g.ldw, w.perm, S, 0, k, m, ceil_div(m, 32)));
         if (Vh) {
@@ -825,4 +953,28 @@ extern "C" int qm_svd_static(int m, int n, const void* A, long long lda, void* U
                              void* mismatch, void* stream) {
     return svd_impl(m, n, A, lda, U, ldu, S, Vh, ldvh, work, work_bytes, tol, fixed_sweeps, nullptr,
                     fixed_sweeps, (int*)mismatch, stream);
+}
+
+// out (cols x rows, ldo) = transpose of in (rows x cols, ldi), optionally conjugated.  The layout
+// kernels of the TT-SVD, exposed for tests and bandwidth measurements.
+extern "C" int qm_transpose(void* out, long long ldo, const void* in, long long ldi, long long rows, long long cols,
+                            int conj, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows <= 0 || cols <= 0) return 0;
+    if (cols <= 32) {
+        int nb = ceil_div(rows, 256) > 148 * 16 ? 148 * 16 : ceil_div(rows, 256);
+        QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose_narrow_in<<<nb, 256, 0, st>>>(
+            (cplx*)out, ldo, (const cplx*)in, ldi, nullptr, nullptr, conj, rows, (int)cols));
+    } else if (rows <= 32) {
+        int nb = ceil_div(cols, 256) > 148 * 16 ? 148 * 16 : ceil_div(cols, 256);
+        QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose_narrow_out<<<nb, 256, 0, st>>>(
+            (cplx*)out, ldo, (const cplx*)in, ldi, nullptr, nullptr, conj, (int)rows, cols));
+    } else {
+        int na = ceil_div(cols, 32);
+        QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose<<<(unsigned)((long long)na * ceil_div(rows, 32)), dim3(32, 8), 0, st>>>(
+            (cplx*)out, ldo, (const cplx*)in, ldi, nullptr, nullptr, conj, (int)rows, cols, na));
+    }
+    qm_prof_work(QM_CLS_SVD_LAYOUT, 32.0 * (double)rows * (double)cols);
+    QM_CHECK_LAUNCH();
+    return 0;
 }

@@ -159,6 +159,13 @@ class CudaKernels:
         self.svd_sweeps += info[0]
         return U, S, Vh
 
+    def transpose(self, A, conj=False):
+        rows, cols = A.shape
+        out = self.empty((cols, rows))
+        self._check(self.lib.qm_transpose(_p(out), rows, _p(A), self._ld(A), rows, cols, 1 if conj else 0,
+                                          self._stream()), "qm_transpose")
+        return out
+
     def qr(self, A, want_q=True):
         """Reduced QR with non-negative diag(R).  Returns (Q or None, R)."""
         m, n = A.shape

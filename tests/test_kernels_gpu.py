@@ -274,3 +274,21 @@ def test_sweep_stored_matches_recompute(K):
         fa = K.to_host(K.circuit_state(N, Ga, sites, kinds))
         fb = K.to_host(K.circuit_state(N, Gb, sites, kinds))
         assert np.abs(fa - fb).max() <= 1e-11, sweep
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (5000, 2), (4097, 31), (2, 5000), (32, 300), (100, 70), (33, 4099)])
+def test_transpose_layout_kernels(K, rows, cols):
+    rng = np.random.default_rng(rows + cols)
+    a = crand(rng, rows, cols)
+    for conj in (False, True):
+        out = K.to_host(K.transpose(K.from_host(a), conj=conj))
+        ref = np.conj(a).T if conj else a.T
+        assert np.array_equal(out, ref)
+
+
+def test_svd_skinny_paths(K):
+    """First TT-SVD splits: 2^i x 2 and 2^i x 4 (register-resident skinny Gram/update kernels and the
+    narrow transposes)."""
+    rng = np.random.default_rng(5)
+    for m, n in [(1 << 14, 2), (1 << 13, 4), (6000, 3), (2, 1 << 14), (4, 9000)]:
+        check_svd(K, rng.random((m, n)) + 1j * rng.random((m, n)))
