@@ -44,6 +44,8 @@ void qm_prof_post(int cls, cudaStream_t st) {
 
 void qm_prof_work(int cls, double work) { g_cls_work[cls] += work; }
 
+bool qm_prof_active() { return g_enabled; }
+
 extern "C" int qm_version(void) { return 100; }
 
 extern "C" long long qm_launch_count(void) { return g_launches; }

@@ -12,6 +12,8 @@ void qm_prof_pre(int cls, cudaStream_t st);
 void qm_prof_post(int cls, cudaStream_t st);
 // algorithmic work of the launches of a class (flops for compute kernels, bytes for streaming ones)
 void qm_prof_work(int cls, double work);
+// true while the event profiler brackets every launch (multi-stream schedules fall back to one stream)
+bool qm_prof_active();
 // every kernel launch of the library goes through this macro
 #define QM_LAUNCH(cls, st, ...)          \
     do {                                 \

@@ -73,6 +73,21 @@ __device__ __forceinline__ int pair_row(int i, int pair, int round, int nbp, int
     return i < BSZ ? bi * BSZ + i : bj * BSZ + (i - BSZ);
 }
 
+// Which block pair a CTA works on.  mode 0: slot p of round r of the circle tournament over the n blocks
+// [off_a, off_a + n);  mode 1: cross pairs between two disjoint groups of n blocks, (off_a + p, off_b + (p + r) % n).
+// The grouped schedule (svd_impl) builds a sweep from two half-size tournaments followed by two rounds of
+// quarter x quarter cross products, so that two independent pair streams exist at every moment.
+struct PairSpec { int mode, r, n, off_a, off_b; };
+__device__ __forceinline__ void get_pair(const PairSpec& ps, int p, int& bi, int& bj) {
+    if (ps.mode == 0) {
+        circle_pair(ps.r, p, ps.n, bi, bj);
+        bi += ps.off_a; bj += ps.off_a;
+    } else {
+        bi = ps.off_a + p;
+        bj = ps.off_b + (p + ps.r) % ps.n;
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // (1) Gram matrices.  grid = (nchunks, npairs).  G is accumulated with atomics and is
 // expected to be zero on entry (k_eig re-zeroes it after loading).
@@ -157,8 +172,8 @@ constexpr size_t EIG_SMEM = 2ull * PMAX * GS * sizeof(cplx);   // g, q
 constexpr int NTE = 768;   // k_eig block: 256 threads update G, 512 update Q in the same pass
 __global__ void __launch_bounds__(NTE)
 k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, double tol2, int max_inner,
-      float cross_ratio, int cross_only, int round, int nbp, int single, int* __restrict__ notconv, int* __restrict__ rotated,
-      double* __restrict__ sig2, const int* __restrict__ done) {
+      float cross_ratio, int cross_only, PairSpec ps, int slot_base, int single, int* __restrict__ notconv,
+      int* __restrict__ rotated, double* __restrict__ sig2, const int* __restrict__ done) {
     if (done && *done) return;      // static (sync-free) mode: this SVD already converged
     extern __shared__ __align__(16) unsigned char eig_smem[];
     cplx* g = (cplx*)eig_smem;                            // [PMAX][GS]
@@ -168,7 +183,7 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
     __shared__ int rpp[PMAX / 2], rqq[PMAX / 2], ract[PMAX / 2];
     __shared__ int s_any, s_sweep, s_off, s_mc, s_mi, s_round;
     __shared__ unsigned char sched[(PMAX - 1) * (PMAX / 2) * 2];     // round-robin schedule (p,q) per round/slot
-    const int tid = threadIdx.x, pair = blockIdx.x;
+    const int tid = threadIdx.x, pair = slot_base + blockIdx.x;   // workspace slot of this pair
     const int n = nrows, ne = n + (n & 1), np = ne / 2;
     // nchunks > 0: G holds per-chunk partial Gram matrices [pair][chunk][PMAX*PMAX*2] written with plain
     // stores by k_gram_mma (summed here in fixed order); nchunks == 0: one atomically accumulated matrix
@@ -330,7 +345,15 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
     }
     cplx* Qp = Qout + (long long)pair * PMAX * PMAX;
     for (int e = tid; e < n * n; e += NTE) Qp[e] = q[(e / n) * GS + (e % n)];
-    if (tid < n) sig2[pair_row(tid, pair, round, nbp, single)] = g[tid * GS + tid].x;
+    if (tid < n) {
+        int row = tid;
+        if (!single) {
+            int bi, bj;
+            get_pair(ps, blockIdx.x, bi, bj);
+            row = tid < BSZ ? bi * BSZ + tid : bj * BSZ + (tid - BSZ);
+        }
+        sig2[row] = g[tid * GS + tid].x;
+    }
     if (tid == 0) {
         rotated[pair] = s_any;
         if (s_off) {
@@ -358,13 +381,13 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // cross-warp reduction: the warp stores its tiles straight into the chunk's partial slab, which
 // k_eig sums over chunks.  A lane's 16-byte load W[row][k] is both an A and a B operand.
 __global__ void __launch_bounds__(NT)
-k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, int round, int nbp,
+k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, PairSpec ps, int slot_base,
            double* __restrict__ G, const int* __restrict__ done) {
     if (done && *done) return;      // static (sync-free) mode: this SVD already converged
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = slot_base + blockIdx.y;
     const int g = lane >> 2, t = lane & 3;
     int bi, bj;
-    circle_pair(round, pair, nbp, bi, bj);
+    get_pair(ps, blockIdx.y, bi, bj);
     const int mt = warp >> 1, nt0 = (warp & 1) * 2;
     auto rowptr = [&](int r) { return W + (long long)(r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ)) * ldw; };
     const cplx* pa = rowptr(mt * 8 + g);
@@ -416,17 +439,17 @@ k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, int ro
 // Wext[rows] <- Q Wext[rows]: each warp owns 8-column strips, loads the 32x8 strip as B
 // fragments, multiplies by Q (A fragments from padded shared planes) and stores in place.
 __global__ void __launch_bounds__(NT, 2)
-k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, int round, int nbp,
+k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, PairSpec ps, int slot_base,
             const cplx* __restrict__ Q, const int* __restrict__ rotated, const int* __restrict__ done) {
     if (done && *done) return;      // static (sync-free) mode: this SVD already converged
-    const int pair = blockIdx.y;
+    const int pair = slot_base + blockIdx.y;
     if (!rotated[pair]) return;
     constexpr int QS = PMAX + 4;
     __shared__ double qr[PMAX * QS], qi[PMAX * QS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     int bi, bj;
-    circle_pair(round, pair, nbp, bi, bj);
+    get_pair(ps, blockIdx.y, bi, bj);
     const cplx* Qp = Q + (long long)pair * PMAX * PMAX;
     for (int e = tid; e < PMAX * PMAX; e += NT) {
         cplx v = Qp[e];
@@ -816,19 +839,21 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         chunk = (chunk + TC - 1) / TC * TC;
         return chunk;
     };
-    // DMMA kernels: aim at ~3 CTAs per SM in flight; chunks in units of one CTA step (32 / 64 columns)
-    auto pick_chunk_mma = [&](long long cols, int unit) {
-        long long want = (3LL * 148 + g.npairs - 1) / g.npairs;
+    // DMMA kernels: aim at ~3 CTAs per SM in flight for a launch of `npl` pairs; chunks in units of one
+    // CTA step (32 / 64 columns)
+    auto pick_chunk_mma = [&](long long cols, int unit, int npl) {
+        long long want = (3LL * 148 + npl - 1) / npl;
         long long chunk = (cols + want - 1) / want;
         chunk = (chunk + unit - 1) / unit * unit;
         if (chunk < unit) chunk = unit;
         return chunk;
     };
-    long long chunk_g = g.single ? pick_chunk(g.len) : pick_chunk_mma(g.len, 32);
-    if (!g.single && chunk_g < 64) chunk_g = 64;
-    if (!g.single && (g.len + chunk_g - 1) / chunk_g > MAXCH) chunk_g = ((g.len + MAXCH - 1) / MAXCH + 31) / 32 * 32;
-    const long long chunk_a = g.single ? pick_chunk(lenx) : pick_chunk_mma(lenx, 64);
-    const int ncg = ceil_div(g.len, chunk_g), nca = ceil_div(lenx, chunk_a);
+    auto gram_chunk = [&](int npl) {
+        long long c = pick_chunk_mma(g.len, 32, npl);
+        if (c < 64) c = 64;
+        if ((g.len + c - 1) / c > MAXCH) c = ((g.len + MAXCH - 1) / MAXCH + 31) / 32 * 32;
+        return c;
+    };
     const double tol2 = tol * tol;
     static bool eig_attr_set = false;
     if (!eig_attr_set) {
@@ -836,7 +861,7 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         eig_attr_set = true;
     }
     // schedule knobs (defaults chosen from the sweep study in profiles/; env overrides for experiments)
-    static int tune_inner0 = -1, tune_inner = 1, tune_cross = 1;
+    static int tune_inner0 = -1, tune_inner = 1, tune_cross = 1, tune_groups = 1;
     static float tune_ratio = 1e-2f;
     if (tune_inner0 < 0) {
         const char* e3 = getenv("QM_SVD_CROSS_RATIO");
@@ -844,9 +869,11 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         const char* e0 = getenv("QM_SVD_INNER0");
         const char* e1 = getenv("QM_SVD_INNER");
         const char* e2 = getenv("QM_SVD_CROSS");
+        const char* e4 = getenv("QM_SVD_GROUPS");
         tune_inner0 = e0 ? atoi(e0) : 2;
         tune_inner = e1 ? atoi(e1) : 1;
         tune_cross = e2 ? atoi(e2) : 1;
+        tune_groups = e4 ? atoi(e4) : 1;
     }
     int sweeps = 0, converged = 0;
     const bool is_static = fixed_sweeps > 0;
@@ -854,34 +881,128 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
     if (is_static) max_sweeps = fixed_sweeps;
     QM_CUDA(cudaMemsetAsync(w.notconv, 0, 4 * sizeof(int), st));
     const float early2 = 1e-18f;     // (1e-9)^2
+
+    // Grouped schedule (multi-block, eager mode): the eigen-solve of a round is latency bound on npairs SMs
+    // (~35 us) while the Gram / update kernels fill the GPU.  The block set is split so that two independent
+    // pair streams A and B exist (PairSpec); all DMMA kernels run in order on the caller's stream as
+    //   gram_A(r), apply_B(r-1), gram_B(r), apply_A(r), gram_A(r+1), ...
+    // and the eigen-solves run on side streams, each hidden behind the other groups' DMMA work (2 or 4 groups).  Not used
+    // under the event profiler (kernel classes are timed in isolation there) nor in the static / graph mode.
+    constexpr int MAXG = 4;
+    static cudaStream_t side[MAXG] = {nullptr, nullptr, nullptr, nullptr};
+    static cudaEvent_t evG[MAXG], evE[MAXG];
+    // 4 streams need nbp % 8 == 0 (even quarter groups that split into halves), 2 streams nbp % 4 == 0
+    int NG = 0;
+    if (tune_groups && !g.single && !is_static && !qm_prof_active()) {
+        if (tune_groups >= 4 && g.nbp >= 64 && (g.nbp % 8) == 0) NG = 4;
+        else if (g.nbp >= 32 && (g.nbp % 4) == 0) NG = 2;
+    }
+    const bool grouped = NG > 0;
+    if (grouped && !side[0]) {
+        for (int i = 0; i < MAXG; i++) {
+            QM_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+            QM_CUDA(cudaEventCreateWithFlags(&evG[i], cudaEventDisableTiming));
+            QM_CUDA(cudaEventCreateWithFlags(&evE[i], cudaEventDisableTiming));
+        }
+    }
+    struct Phase { int mode, n, rounds, np, offa[MAXG], offb[MAXG]; };
+    Phase phases[7];
+    int nphases = 0;
+    if (NG == 2) {
+        const int h = g.nbp / 2, q = h / 2;
+        phases[0] = {0, h, h - 1, h / 2, {0, h, 0, 0}, {0, 0, 0, 0}};
+        phases[1] = {1, q, q, q, {0, q, 0, 0}, {h, h + q, 0, 0}};
+        phases[2] = {1, q, q, q, {0, q, 0, 0}, {h + q, h, 0, 0}};
+        nphases = 3;
+    } else if (NG == 4) {
+        // four quarter groups: their own tournaments, then the three pairings of the quarters, each pairing
+        // as two rounds of half x half cross products
+        const int s4 = g.nbp / 4, q = s4 / 2;
+        phases[nphases++] = {0, s4, s4 - 1, s4 / 2, {0, s4, 2 * s4, 3 * s4}, {0, 0, 0, 0}};
+        const int pairing[3][4] = {{0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2}};   // (a1,b1), (a2,b2)
+        for (int t = 0; t < 3; t++) {
+            const int a1 = pairing[t][0] * s4, b1 = pairing[t][1] * s4, a2 = pairing[t][2] * s4, b2 = pairing[t][3] * s4;
+            phases[nphases++] = {1, q, q, q, {a1, a1 + q, a2, a2 + q}, {b1, b1 + q, b2, b2 + q}};
+            phases[nphases++] = {1, q, q, q, {a1, a1 + q, a2, a2 + q}, {b1 + q, b1, b2 + q, b2}};
+        }
+    }
+    const int npl = grouped ? g.npairs / NG : g.npairs;         // pairs per DMMA launch
+    const long long chunk_g = g.single ? pick_chunk(g.len) : gram_chunk(npl);
+    const long long chunk_a = g.single ? pick_chunk(lenx) : pick_chunk_mma(lenx, 64, npl);
+    const int ncg = ceil_div(g.len, chunk_g), nca = ceil_div(lenx, chunk_a);
+
     for (; sweeps < max_sweeps;) {
         const int max_inner = (sweeps == 0) ? tune_inner0 : tune_inner;
         const int cross_only = (sweeps > 0 && tune_cross) ? 1 : 0;
-        for (int r = 0; r < g.rounds; r++) {
-            if (g.single && g.nrows <= 4 && g.len >= 4096) {
-                int nb = ceil_div(g.len, NT) > 148 * 4 ? 148 * 4 : ceil_div(g.len, NT);
-                QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram_skinny<<<nb, NT, 0, st>>>(w.W, g.ldw, (long long)g.len, g.nrows,
-                                                                              w.G, donep));
-            } else if (g.single) {
-                QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram<<<dim3(ncg, g.npairs), NT, 0, st>>>(
-                    w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, g.single, g.nrows, w.G, donep));
-            } else {
-                QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram_mma<<<dim3(ncg, g.npairs), NT, 0, st>>>(
-                    w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, w.G, donep));
+        auto launch_gram = [&](const PairSpec& ps, int np, int slot, cudaStream_t s) {
+            QM_LAUNCH(QM_CLS_SVD_GRAM, s, k_gram_mma<<<dim3(ncg, np), NT, 0, s>>>(
+                w.W, g.ldw, g.len, (int)chunk_g, ps, slot, w.G, donep));
+        };
+        auto launch_eig = [&](const PairSpec& ps, int np, int slot, cudaStream_t s) {
+            QM_LAUNCH(QM_CLS_SVD_EIG, s, k_eig<<<np, NTE, EIG_SMEM, s>>>(
+                w.G, g.single ? 0 : ncg, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, tune_ratio, cross_only, ps, slot,
+                g.single, w.notconv, w.rotated, w.sig2, donep));
+        };
+        auto launch_apply = [&](const PairSpec& ps, int np, int slot, cudaStream_t s) {
+            QM_LAUNCH(QM_CLS_SVD_APPLY, s, k_apply_mma<<<dim3(nca, np), NT, 0, s>>>(
+                w.W, g.ldw, lenx, (int)chunk_a, ps, slot, w.Q, w.rotated, donep));
+        };
+        if (grouped) {
+            for (int ph = 0; ph < nphases; ph++) {
+                const Phase& P = phases[ph];
+                bool pending[MAXG] = {false, false, false, false};
+                PairSpec pspec[MAXG];
+                for (int r = 0; r < P.rounds; r++) {
+                    for (int grp = 0; grp < NG; grp++) {
+                        const PairSpec ps = {P.mode, r, P.n, P.offa[grp], P.offb[grp]};
+                        const int slot = grp * P.np;
+                        launch_gram(ps, P.np, slot, st);
+                        QM_CUDA(cudaEventRecord(evG[grp], st));
+                        QM_CUDA(cudaStreamWaitEvent(side[grp], evG[grp], 0));
+                        launch_eig(ps, P.np, slot, side[grp]);
+                        QM_CUDA(cudaEventRecord(evE[grp], side[grp]));
+                        const int o = (grp + 1) % NG;           // the oldest pending update fills the wait
+                        if (pending[o]) {
+                            QM_CUDA(cudaStreamWaitEvent(st, evE[o], 0));
+                            launch_apply(pspec[o], P.np, o * P.np, st);
+                            pending[o] = false;
+                        }
+                        pending[grp] = true;
+                        pspec[grp] = ps;
+                    }
+                }
+                for (int k = 0; k < NG; k++) {
+                    const int grp = (k + 1) % NG;               // same order as inside the loop
+                    if (pending[grp]) {
+                        QM_CUDA(cudaStreamWaitEvent(st, evE[grp], 0));
+                        launch_apply(pspec[grp], P.np, grp * P.np, st);
+                    }
+                }
             }
-            QM_LAUNCH(QM_CLS_SVD_EIG, st, k_eig<<<g.npairs, NTE, EIG_SMEM, st>>>(
-                w.G, g.single ? 0 : ncg, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, tune_ratio, cross_only, r, g.nbp, g.single, w.notconv,
-                w.rotated, w.sig2, donep));
-            if (g.single && g.nrows <= 4 && g.len >= 4096) {
-                int nb = ceil_div(lenx, NT) > 148 * 8 ? 148 * 8 : ceil_div(lenx, NT);
-                QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply_skinny<<<nb, NT, 0, st>>>(w.W, g.ldw, lenx, g.nrows, w.Q,
-                                                                                w.rotated, donep));
-            } else if (g.single) {
-                QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply<<<dim3(nca, g.npairs), NT, 0, st>>>(
-                    w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, g.single, g.nrows, w.Q, w.rotated, donep));
-            } else {
-                QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply_mma<<<dim3(nca, g.npairs), NT, 0, st>>>(
-                    w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, w.Q, w.rotated, donep));
+        } else {
+            for (int r = 0; r < g.rounds; r++) {
+                const PairSpec ps = {0, r, g.nbp, 0, 0};
+                if (g.single && g.nrows <= 4 && g.len >= 4096) {
+                    int nb = ceil_div(g.len, NT) > 148 * 4 ? 148 * 4 : ceil_div(g.len, NT);
+                    QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram_skinny<<<nb, NT, 0, st>>>(w.W, g.ldw, (long long)g.len, g.nrows,
+                                                                                  w.G, donep));
+                } else if (g.single) {
+                    QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram<<<dim3(ncg, g.npairs), NT, 0, st>>>(
+                        w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, g.single, g.nrows, w.G, donep));
+                } else {
+                    launch_gram(ps, g.npairs, 0, st);
+                }
+                launch_eig(ps, g.npairs, 0, st);
+                if (g.single && g.nrows <= 4 && g.len >= 4096) {
+                    int nb = ceil_div(lenx, NT) > 148 * 8 ? 148 * 8 : ceil_div(lenx, NT);
+                    QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply_skinny<<<nb, NT, 0, st>>>(w.W, g.ldw, lenx, g.nrows, w.Q,
+                                                                                    w.rotated, donep));
+                } else if (g.single) {
+                    QM_LAUNCH(QM_CLS_SVD_APPLY, st, k_apply<<<dim3(nca, g.npairs), NT, 0, st>>>(
+                        w.W, g.ldw, lenx, (int)chunk_a, r, g.nbp, g.single, g.nrows, w.Q, w.rotated, donep));
+                } else {
+                    launch_apply(ps, g.npairs, 0, st);
+                }
             }
         }
         // complex MAC = 8 flops: Gram nrows^2 x len, update nrows^2 x lenx, per pair and round

@@ -1,17 +1,22 @@
-"""One complex128 SVD of the gate_split shape (GPU box; used under ncu)."""
+"""Complex128 SVDs of the gate_split shapes (GPU box; also used under ncu).
+usage: svd_probe.py m n [m n ...]   (QM_EIG_OLD=1 selects the previous eigen-solve kernel)"""
 import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from qmprs_b200.kernels import get_kernels
-m = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+args = [int(x) for x in sys.argv[1:]] or [1024, 1024]
 K = get_kernels("cuda:0")
 rng = np.random.default_rng(0)
-a = rng.random((m, n)) + 1j * rng.random((m, n))
-A = K.from_host(a)
-K.svd(K.from_host(a[:64, :64]))
-torch.cuda.synchronize(); t0 = time.perf_counter()
-U, S, Vh = K.svd(A)
-torch.cuda.synchronize(); t1 = time.perf_counter()
-print(f"svd {m}x{n}: {1e3*(t1-t0):.2f} ms, sweeps {K.svd_sweeps}")
+K.svd(K.from_host(rng.random((64, 64)) + 0j))
+for m, n in zip(args[0::2], args[1::2]):
+    a = rng.random((m, n)) + 1j * rng.random((m, n))
+    A = K.from_host(a)
+    best = 1e9
+    for rep in range(3):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        U, S, Vh = K.svd(A, _plain=True)
+        torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
+    s = K.to_host(S)
+    sref = np.linalg.svd(a, compute_uv=False)
+    print(f"svd {m}x{n}: {1e3*best:.2f} ms, sweeps {K.svd_sweeps}, max|s-sref|/s0 {np.abs(s-sref).max()/sref[0]:.2e}", flush=True)

@@ -292,3 +292,15 @@ def test_svd_skinny_paths(K):
     rng = np.random.default_rng(5)
     for m, n in [(1 << 14, 2), (1 << 13, 4), (6000, 3), (2, 1 << 14), (4, 9000)]:
         check_svd(K, rng.random((m, n)) + 1j * rng.random((m, n)))
+
+
+@pytest.mark.parametrize("m,n", [(4096, 64), (64, 4096), (8192, 128), (2000, 100)])
+def test_svd_tall_preconditioned(K, m, n):
+    """Aspect ratio >= 8: Gram pre-conditioning + full-accuracy Jacobi polish (kernels._svd_preconditioned)."""
+    rng = np.random.default_rng(m + n)
+    check_svd(K, rng.random((m, n)) + 1j * rng.random((m, n)))
+    # graded spectrum: the polish must restore what the squared Gram matrix loses
+    q1, _ = np.linalg.qr(crand(rng, max(m, n), min(m, n)))
+    q2, _ = np.linalg.qr(crand(rng, min(m, n), min(m, n)))
+    a = (q1 * np.logspace(0, -7, min(m, n))[None, :]) @ q2
+    check_svd(K, a if m >= n else a.T.copy())
