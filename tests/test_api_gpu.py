@@ -30,6 +30,20 @@ def test_golden_fixtures_through_public_api(K):
         assert np.abs(g - z[key + "_gates"]).max() <= 1e-6
 
 
+def test_readme_depth_and_op_counts_in_u3_cx_basis(K):
+    """README.md:59-70 / notebook cell 27: 10 qubits, 15 layers -> depth 223, 405 CX, 1095 U3
+    (sweeps change the gates, not the structure; 2 sweeps keep the test short)."""
+    from qmprs.synthesis.mps_encoding import Sequential
+    from qmprs_b200 import GateListCircuit, U3CXCircuit
+    psi = O.random_state(10, 0)
+    enc = Sequential(U3CXCircuit)
+    circ = enc.prepare_state(psi, 512, num_layers=15, num_sweeps=2)
+    ops = circ.count_ops()
+    assert circ.get_depth() == 223 and (ops["CX"], ops["U3"]) == (405, 1095)
+    ref = Sequential(GateListCircuit).prepare_state(psi, 512, num_layers=15, num_sweeps=2)
+    assert np.abs(circ.get_statevector() - ref.get_statevector()).max() < 1e-9
+
+
 def test_mps_wrapper_methods(K):
     """tests/primitives/test_mps.py:115-214 of the reference, on the device MPS."""
     from qmprs.primitives import MPS
