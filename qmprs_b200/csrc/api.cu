@@ -1,5 +1,6 @@
 // Library identification, launch counter and the optional per-kernel-class event profiler
 // used by bench.py to time the dominant kernel live (CUDA events on the launching stream).
+#include <cstdlib>
 #include <vector>
 #include "common.cuh"
 #include "qmprs_b200.h"
@@ -45,6 +46,13 @@ void qm_prof_post(int cls, cudaStream_t st) {
 void qm_prof_work(int cls, double work) { g_cls_work[cls] += work; }
 
 bool qm_prof_active() { return g_enabled; }
+
+// QM_PDL=0 turns programmatic dependent launch off (A/B runs); never used under the event profiler
+// (events between launches serialise them anyway and the classes are timed in isolation there).
+bool qm_pdl_enabled() {
+    static const bool on = !(getenv("QM_PDL") && atoi(getenv("QM_PDL")) == 0);
+    return on && !g_enabled;
+}
 
 extern "C" int qm_version(void) { return 100; }
 

@@ -84,4 +84,34 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return red[32];
 }
 
+
+// Programmatic dependent launch (sm_90+): a kernel launched through qm_launch_dep may start (CTA
+// scheduling, parameter setup) while its predecessor in the stream is still draining; pdl_wait()
+// blocks until the predecessor has completed and its writes are visible, so it must precede every
+// global-memory access of the kernel.  pdl_trigger() lets the NEXT kernel begin its own launch.
+// The dependent chains of this library (gram -> eig -> update per Jacobi round, one environment
+// kernel per gate-step) are thousands of short kernels: the launch latency is what this hides.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool qm_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t qm_launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 0;
+    if (qm_pdl_enabled()) {                      // plain launch while the stream is being captured into a graph
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -32,6 +32,8 @@ __device__ __forceinline__ void load_mat(const cplx* __restrict__ G, int dim, in
 // state <- M applied on the two bits (q+1, q).  One thread per group of 4 amplitudes.
 __global__ void __launch_bounds__(NT)
 k_gate2(const cplx* xin, cplx* x, int nbits, int q, const cplx* __restrict__ G, int op) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ cplx Ms[16];
     if (threadIdx.x == 0) load_mat(G, 4, op, Ms);
     __syncthreads();
@@ -61,6 +63,8 @@ k_gate2(const cplx* xin, cplx* x, int nbits, int q, const cplx* __restrict__ G, 
 // state <- M applied on bit q.
 __global__ void __launch_bounds__(NT)
 k_gate1(const cplx* xin, cplx* x, int nbits, int q, const cplx* __restrict__ G, int op) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ cplx Ms[4];
     if (threadIdx.x == 0) load_mat(G, 2, op, Ms);
     __syncthreads();
@@ -458,6 +462,21 @@ k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int 
     __shared__ cplx Pm[16];
     __shared__ double wsum[NT / 32][32];
     __shared__ int s_last;
+    const long long ngroups = 1LL << (nbits - NU);
+    const long long stride = 1LL << q0;
+    const long long lowmask = stride - 1;
+    // The stored circuit state c_k was written by the forward pass, long before the predecessor of this
+    // kernel started (the predecessor triggers only after its own wait): its loads can be in flight while
+    // the predecessor finishes its reduction and polar update.  tbar and the pending gate cannot.
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    cplx cv[GSZ];
+    if (t < ngroups) {
+        const long long base = ((t >> q0) << (q0 + NU)) | (t & lowmask);
+#pragma unroll
+        for (int j = 0; j < GSZ; j++) cv[j] = c[base + j * stride];
+    }
+    pdl_wait();
+    pdl_trigger();
     if (PD > 0 && threadIdx.x < PD * PD) {
         int a = threadIdx.x / PD, b = threadIdx.x % PD;
         Pm[threadIdx.x] = Gpend[b * PD + a];                  // M = G^T : tbar'[b] = sum_o G[o][b] tbar[o]
@@ -467,17 +486,17 @@ k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int 
     double acc[32];
 #pragma unroll
     for (int i = 0; i < 32; i++) acc[i] = 0.0;
-    const long long ngroups = 1LL << (nbits - NU);
-    const long long stride = 1LL << q0;
-    const long long lowmask = stride - 1;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ngroups;
-         t += (long long)gridDim.x * blockDim.x) {
+    bool first = true;
+    for (; t < ngroups; t += (long long)gridDim.x * blockDim.x) {
         const long long base = ((t >> q0) << (q0 + NU)) | (t & lowmask);
-        cplx tv[GSZ], cv[GSZ];
+        cplx tv[GSZ];
 #pragma unroll
         for (int j = 0; j < GSZ; j++) tv[j] = tbar[base + j * stride];
+        if (!first) {
 #pragma unroll
-        for (int j = 0; j < GSZ; j++) cv[j] = c[base + j * stride];
+            for (int j = 0; j < GSZ; j++) cv[j] = c[base + j * stride];
+        }
+        first = false;
         if (PD > 0) {
 #pragma unroll
             for (int h = 0; h < GSZ / PD; h++) {
@@ -529,10 +548,12 @@ int launch_gate(cplx* x, int nbits, int site, int kind, const cplx* G, int op, c
     qm_prof_work(QM_CLS_GATE, 32.0 * (double)(1LL << nbits));      // read + write every amplitude
     if (kind == 2) {
         int q = nbits - 2 - site;
-        QM_LAUNCH(QM_CLS_GATE, st, k_gate2<<<grid_groups(1LL << (nbits - 2)), NT, 0, st>>>(xin, x, nbits, q, G, op));
+        QM_LAUNCH(QM_CLS_GATE, st, qm_launch_dep(k_gate2, dim3(grid_groups(1LL << (nbits - 2))), dim3(NT), 0, st,
+                                                 xin, x, nbits, q, G, op));
     } else {
         int q = nbits - 1 - site;
-        QM_LAUNCH(QM_CLS_GATE, st, k_gate1<<<grid_groups(1LL << (nbits - 1)), NT, 0, st>>>(xin, x, nbits, q, G, op));
+        QM_LAUNCH(QM_CLS_GATE, st, qm_launch_dep(k_gate1, dim3(grid_groups(1LL << (nbits - 1))), dim3(NT), 0, st,
+                                                 xin, x, nbits, q, G, op));
     }
     return (int)cudaGetLastError();
 }
@@ -584,8 +605,8 @@ void launch_env_fused(cplx* tbar, const cplx* c, int nbits, int q0, const cplx* 
     qm_prof_work(QM_CLS_ENV, (PD > 0 ? 48.0 : 32.0) * (double)(1LL << nbits));
     // one group per thread (a 148-CTA persistent grid measured slower: 35 vs 30 us at 20 qubits, the
     // per-iteration load latency is not overlapped at 1 CTA/SM)
-    QM_LAUNCH(QM_CLS_ENV, st, (k_env_fused<NU, CD, PD><<<grid_groups(ngroups), NT, 0, st>>>(
-        tbar, c, nbits, q0, Gpend, partials, counter, gate_out, env_out, vwarm)));
+    QM_LAUNCH(QM_CLS_ENV, st, qm_launch_dep(k_env_fused<NU, CD, PD>, dim3(grid_groups(ngroups)), dim3(NT), 0, st,
+                                            tbar, c, nbits, q0, Gpend, partials, counter, gate_out, env_out, vwarm));
 }
 }  // namespace
 

@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(NTE)
 k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, double tol2, int max_inner,
       float cross_ratio, int cross_only, PairSpec ps, int slot_base, int single, int* __restrict__ notconv,
       int* __restrict__ rotated, double* __restrict__ sig2, const int* __restrict__ done) {
+    pdl_wait();
+    pdl_trigger();
     if (done && *done) return;      // static (sync-free) mode: this SVD already converged
     extern __shared__ __align__(16) unsigned char eig_smem[];
     cplx* g = (cplx*)eig_smem;                            // [PMAX][GS]
@@ -383,6 +385,8 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 __global__ void __launch_bounds__(NT)
 k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, PairSpec ps, int slot_base,
            double* __restrict__ G, const int* __restrict__ done) {
+    pdl_wait();
+    pdl_trigger();
     if (done && *done) return;      // static (sync-free) mode: this SVD already converged
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = slot_base + blockIdx.y;
     const int g = lane >> 2, t = lane & 3;
@@ -441,6 +445,8 @@ k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, PairSp
 __global__ void __launch_bounds__(NT, 2)
 k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, PairSpec ps, int slot_base,
             const cplx* __restrict__ Q, const int* __restrict__ rotated, const int* __restrict__ done) {
+    pdl_wait();
+    pdl_trigger();
     if (done && *done) return;      // static (sync-free) mode: this SVD already converged
     const int pair = slot_base + blockIdx.y;
     if (!rotated[pair]) return;
@@ -880,7 +886,10 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
     const int* donep = is_static ? w.notconv + 1 : nullptr;
     if (is_static) max_sweeps = fixed_sweeps;
     QM_CUDA(cudaMemsetAsync(w.notconv, 0, 4 * sizeof(int), st));
-    const float early2 = 1e-18f;     // (1e-9)^2
+    // a sweep that STARTS below `early` (largest |cos| between rows) ends near early^2 (quadratic regime): no
+    // verification sweep after it.  QM_SVD_EARLY overrides for experiments.
+    static const float early = getenv("QM_SVD_EARLY") ? (float)atof(getenv("QM_SVD_EARLY")) : 1e-9f;
+    const float early2 = early * early;
 
     // Grouped schedule (multi-block, eager mode): the eigen-solve of a round is latency bound on npairs SMs
     // (~35 us) while the Gram / update kernels fill the GPU.  The block set is split so that two independent
@@ -935,16 +944,23 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         const int max_inner = (sweeps == 0) ? tune_inner0 : tune_inner;
         const int cross_only = (sweeps > 0 && tune_cross) ? 1 : 0;
         auto launch_gram = [&](const PairSpec& ps, int np, int slot, cudaStream_t s) {
-            QM_LAUNCH(QM_CLS_SVD_GRAM, s, k_gram_mma<<<dim3(ncg, np), NT, 0, s>>>(
+            if (is_static) QM_LAUNCH(QM_CLS_SVD_GRAM, s, k_gram_mma<<<dim3(ncg, np), NT, 0, s>>>(
+                w.W, g.ldw, g.len, (int)chunk_g, ps, slot, w.G, donep));
+            else QM_LAUNCH(QM_CLS_SVD_GRAM, s, qm_launch_dep(k_gram_mma, dim3(ncg, np), dim3(NT), 0, s,
                 w.W, g.ldw, g.len, (int)chunk_g, ps, slot, w.G, donep));
         };
         auto launch_eig = [&](const PairSpec& ps, int np, int slot, cudaStream_t s) {
-            QM_LAUNCH(QM_CLS_SVD_EIG, s, k_eig<<<np, NTE, EIG_SMEM, s>>>(
+            if (is_static) QM_LAUNCH(QM_CLS_SVD_EIG, s, k_eig<<<np, NTE, EIG_SMEM, s>>>(
+                w.G, g.single ? 0 : ncg, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, tune_ratio, cross_only, ps, slot,
+                g.single, w.notconv, w.rotated, w.sig2, donep));
+            else QM_LAUNCH(QM_CLS_SVD_EIG, s, qm_launch_dep(k_eig, dim3(np), dim3(NTE), EIG_SMEM, s,
                 w.G, g.single ? 0 : ncg, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, tune_ratio, cross_only, ps, slot,
                 g.single, w.notconv, w.rotated, w.sig2, donep));
         };
         auto launch_apply = [&](const PairSpec& ps, int np, int slot, cudaStream_t s) {
-            QM_LAUNCH(QM_CLS_SVD_APPLY, s, k_apply_mma<<<dim3(nca, np), NT, 0, s>>>(
+            if (is_static) QM_LAUNCH(QM_CLS_SVD_APPLY, s, k_apply_mma<<<dim3(nca, np), NT, 0, s>>>(
+                w.W, g.ldw, lenx, (int)chunk_a, ps, slot, w.Q, w.rotated, donep));
+            else QM_LAUNCH(QM_CLS_SVD_APPLY, s, qm_launch_dep(k_apply_mma, dim3(nca, np), dim3(NT), 0, s,
                 w.W, g.ldw, lenx, (int)chunk_a, ps, slot, w.Q, w.rotated, donep));
         };
         if (grouped) {
