@@ -137,6 +137,15 @@ int qm_circuit_states(void* cs, int n_sites, const void* gates, const int* sites
 int qm_sweep_stored(const void* cs, void* tbar, int n_sites, void* gates, const int* sites, const int* kinds,
                     int n_gates, void* work, void* envs, void* vwarm, void* stream);
 
+/* Small registers (n_sites <= 12, n_gates <= 256): ALL `num_sweeps` optimisation sweeps of `batch`
+ * independent states in one launch, one CTA per state with both dense vectors and the gates in
+ * shared memory (same arithmetic as qm_circuit_state + qm_sweep per sweep; sequential.py:443-505,
+ * 509-541).  targets: [batch][2^N] (not conjugated); gates: [batch][n_gates][16], updated in place;
+ * sites_dev / kinds_dev: DEVICE int[n_gates], one schedule for the batch; envs: optional
+ * [batch][n_gates][16], environments of the last sweep.  Returns -3 if the state does not fit. */
+int qm_sweeps_small(const void* targets, int n_sites, void* gates, const int* sites_dev, const int* kinds_dev,
+                    int n_gates, int num_sweeps, int batch, void* envs, void* stream);
+
 /* Library identification: returns the compiled architecture number (100 for sm_100a). */
 int qm_version(void);
 

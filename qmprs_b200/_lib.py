@@ -46,6 +46,7 @@ SIGNATURES = {
     "qm_sweep": (_i, [_vp, _vp, _i, _vp, _ip, _ip, _i, _vp, _vp, _vp]),
     "qm_circuit_states": (_i, [_vp, _i, _vp, _ip, _ip, _i, _vp]),
     "qm_sweep_stored": (_i, [_vp, _vp, _i, _vp, _ip, _ip, _i, _vp, _vp, _vp, _vp]),
+    "qm_sweeps_small": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "qm_version": (_i, []),
     "qm_launch_count": (_ll, []),
     "qm_prof_num_classes": (_i, []),

@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "gemm.cu", "svd.cu", "qr.cu", "mps_ops.cu", "dense.cu")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "gemm.cu", "svd.cu", "qr.cu", "mps_ops.cu", "dense.cu", "dense_small.cu")]
 OUT = os.path.join(HERE, "libqmprs_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -22,7 +22,8 @@ def needs_build() -> bool:
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = SRC + [os.path.join(ROOT, "include", "qmprs_b200.h"), os.path.join(HERE, "csrc", "common.cuh")]
+    deps = SRC + [os.path.join(ROOT, "include", "qmprs_b200.h"), os.path.join(HERE, "csrc", "common.cuh"),
+            os.path.join(HERE, "csrc", "polar.cuh"), os.path.join(HERE, "csrc", "small_linalg.cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

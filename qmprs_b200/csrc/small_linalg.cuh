@@ -19,12 +19,13 @@ static __device__ void jacobi_cols(cplx A[4][4], cplx V[4][4], int d) {
                 double mag2 = cabs2(g);
                 if (!(a > 0.0 && b > 0.0) || mag2 <= tol2 * a * b) continue;
                 rot = 1;
-                double imag = rsqrt(mag2);
-                double zeta = 0.5 * (b - a) * imag;
-                double z1 = 1.0 + zeta * zeta;
-                double t = copysign(1.0, zeta) / (fabs(zeta) + z1 * rsqrt(z1));
-                double c = rsqrt(1.0 + t * t), s = c * t;
-                cplx se = mk(s * g.x * imag, s * g.y * imag), sec = cconj(se);   // s e^{+-i phi}
+                // overflow-free form (see polar_conj_warp in dense.cu): no division by |g|
+                double dd = 0.5 * (b - a);
+                double hh = fma(dd, dd, mag2);
+                double den = fabs(dd) + hh * rsqrt(hh);
+                double R = rsqrt(den * den + mag2);
+                double c = den * R, sR = copysign(R, dd);
+                cplx se = mk(sR * g.x, sR * g.y), sec = cconj(se);               // s e^{+-i phi}
                 // x' = c x - s e^{-i phi} y ; y' = s e^{i phi} x + c y
                 for (int i = 0; i < d; i++) {
                     cplx xx = A[i][p], yy = A[i][q];

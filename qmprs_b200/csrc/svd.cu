@@ -275,16 +275,16 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
                         cplx gpq = g[p * GS + qq];
                         double mag2 = cabs2(gpq);
                         if (a > 0.0 && b > 0.0 && mag2 > tol2 * a * b) {
-                            // reciprocal square roots instead of sqrt/div chains (latency-bound step)
-                            // t = sign/(|z| + sqrt(1+z^2)) =: sign/den;  c = den/sqrt(den^2+1), s = sign/sqrt(den^2+1)
-                            double imag = rsqrt(mag2);
-                            double zeta = 0.5 * (b - a) * imag;
-                            double z1 = 1.0 + zeta * zeta;
-                            double den = fabs(zeta) + z1 * rsqrt(z1);
-                            double wv = rsqrt(den * den + 1.0);
-                            c = den * wv;
-                            s = copysign(wv, zeta);
-                            u = mk(gpq.x * imag, gpq.y * imag);
+                            // overflow-free form without 1/|g| (a numerically null row shrinks geometrically under
+                            // repeated rotations; ((b-a)/2|g|)^2 can then overflow):  dd = (b-a)/2,
+                            // den = |dd| + sqrt(dd^2+|g|^2), R = 1/sqrt(den^2+|g|^2):  c = den R,  s u = sign(dd) R g
+                            const double dd = 0.5 * (b - a);
+                            const double hh = fma(dd, dd, mag2);
+                            const double den = fabs(dd) + hh * rsqrt(hh);      // hh > 0 (mag2 > 0); rsqrt is the cheaper chain
+                            const double R = rsqrt(fma(den, den, mag2));
+                            c = den * R;
+                            s = copysign(R, dd);
+                            u = gpq;
                             act = true;
                         }
                     }

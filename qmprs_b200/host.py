@@ -279,12 +279,16 @@ def flat_schedule(kinds_per_layer, n_sites):
 STORED_SWEEP_MAX_BYTES = 64 << 30      # intermediates kept in HBM up to 64 GiB (180 GB per B200)
 
 
-def optimize_layers(K, target, gates_all, kinds_per_layer, n_sites, num_sweeps, envs=None, stored=True):
+def optimize_layers(K, target, gates_all, kinds_per_layer, n_sites, num_sweeps, envs=None, stored=True, small=True):
     """``_optimize_unitary_layers``: per sweep rebuild the dense circuit state from the
     current gates (sequential.py:533, 443-447; the reference's full-rank re-compression
     of that state into an MPS is an identity and is skipped) and run one environment
     sweep (sequential.py:452-505).  ``gates_all``: [L*N, 16] in application order."""
     sites, kinds = flat_schedule(kinds_per_layer, n_sites)
+    if (small and num_sweeps > 0 and n_sites <= K.SMALL_SWEEP_MAX_SITES and len(sites) <= K.SMALL_SWEEP_MAX_GATES):
+        # both dense vectors fit one SM's shared memory: every sweep in a single launch
+        K.sweeps_small(target, n_sites, gates_all, sites, kinds, num_sweeps, 1, envs)
+        return gates_all
     stored_bytes = (len(sites) + 1) * 16 * (1 << n_sites)
     use_stored = stored and stored_bytes <= STORED_SWEEP_MAX_BYTES
     c = None

@@ -306,6 +306,22 @@ class CudaKernels:
                                              self._int_array(kinds), len(sites), _p(self._sweep_work), _p(envs),
                                              _p(vwarm), self._stream()), "qm_sweep_stored")
 
+    SMALL_SWEEP_MAX_SITES = 12
+    SMALL_SWEEP_MAX_GATES = 256
+
+    def sweeps_small(self, targets, n_sites, gates, sites, kinds, num_sweeps, batch=1, envs=None):
+        """All sweeps of `batch` small states in one launch (one CTA per state, vectors in shared memory).
+        ``targets``: [batch, 2^N] dense (not conjugated); ``gates``: [batch * M, 16], updated in place."""
+        key = (tuple(int(x) for x in sites), tuple(int(x) for x in kinds))
+        cache = self.__dict__.setdefault("_sched_cache", {})
+        dev = cache.get(key)
+        if dev is None:                      # created on first use (the eager warm-up precedes any graph capture)
+            dev = (torch.tensor(key[0], dtype=torch.int32, device=self.device),
+                   torch.tensor(key[1], dtype=torch.int32, device=self.device))
+            cache[key] = dev
+        self._check(self.lib.qm_sweeps_small(_p(targets), n_sites, _p(gates), _p(dev[0]), _p(dev[1]), len(sites),
+                                             int(num_sweeps), int(batch), _p(envs), self._stream()), "qm_sweeps_small")
+
     # ---- instrumentation ------------------------------------------------------------
     def launch_count(self):
         """Kernel launches issued by the library since load (counted in QM_LAUNCH)."""

@@ -245,6 +245,19 @@ class FakeKernels:
                 envs[g, : d * d] = torch.as_tensor(E.reshape(-1))
             self.apply_gate(tbar, N, site, kind, gates[g], 2)
 
+    SMALL_SWEEP_MAX_SITES = 12
+    SMALL_SWEEP_MAX_GATES = 256
+
+    def sweeps_small(self, targets, n_sites, gates, sites, kinds, num_sweeps, batch=1, envs=None):
+        M = len(sites)
+        targets = targets.reshape(batch, -1)
+        for b in range(batch):
+            g = gates[b * M:(b + 1) * M]
+            for _ in range(num_sweeps):
+                c = self.circuit_state(n_sites, g, sites, kinds)
+                tbar = torch.conj(targets[b]).clone()
+                self.sweep(c, tbar, n_sites, g, sites, kinds, None if envs is None else envs[b * M:(b + 1) * M])
+
     def sweep(self, c, tbar, n_sites, gates, sites, kinds, envs=None):
         N = n_sites
         for g in range(len(sites) - 1, -1, -1):

@@ -311,6 +311,48 @@ def test_sweep_stored_matches_recompute(K):
         assert np.abs(fa - fb).max() <= 1e-11, sweep
 
 
+@pytest.mark.parametrize("N,L,S,batch", [(7, 3, 3, 1), (12, 2, 2, 3), (2, 2, 2, 2), (5, 4, 4, 5)])
+def test_sweeps_small_matches_recompute_sweeps(K, N, L, S, batch):
+    """qm_sweeps_small (one CTA per state, all sweeps in one launch, vectors in shared memory) against
+    `S` rounds of qm_circuit_state + qm_sweep on the same gates and targets: same circuit states and
+    same environments of the last sweep, for every state of a batch; block boundaries and one-qubit
+    gates included."""
+    rng = np.random.default_rng(100 * N + L)
+    kinds_layer = ([2, 2, 1, 2, 1, 1, 1] * 2)[:N]
+    kinds_layer[-1] = 1
+    if N > 7:
+        kinds_layer = [2] * (N - 1) + [1]
+    kinds = kinds_layer * L
+    sites = list(range(N)) * L
+    M = len(kinds)
+    gates = np.zeros((batch, M, 16), dtype=np.complex128)
+    for b in range(batch):
+        for idx, k in enumerate(kinds):
+            d = 4 if k == 2 else 2
+            q, _ = np.linalg.qr(crand(rng, d, d))
+            gates[b, idx, : d * d] = q.reshape(-1)
+    targets = np.stack([crand(rng, 2 ** N) for _ in range(batch)])
+    Gs = K.from_host(gates.reshape(batch * M, 16))
+    envs_s = K.zeros((batch * M, 16))
+    K.sweeps_small(K.from_host(targets), N, Gs, sites, kinds, S, batch, envs_s)
+    gs, es = K.to_host(Gs).reshape(batch, M, 16), K.to_host(envs_s).reshape(batch, M, 16)
+    for b in range(batch):
+        Ga = K.from_host(gates[b])
+        T = K.from_host(targets[b])
+        envs_a = K.zeros((M, 16))
+        for sweep in range(S):
+            ca = K.circuit_state(N, Ga, sites, kinds)
+            K.sweep(ca, K.conj_scale_copy(T, conj=True), N, Ga, sites, kinds, envs_a)
+        fa = K.to_host(K.circuit_state(N, Ga, sites, kinds))
+        fb = K.to_host(K.circuit_state(N, K.from_host(gs[b]), sites, kinds))
+        assert np.abs(fa - fb).max() <= 1e-10, b
+        assert np.abs(K.to_host(envs_a) - es[b]).max() <= 1e-10, b
+        for idx, k in enumerate(kinds):
+            d = 4 if k == 2 else 2
+            u = gs[b, idx, : d * d].reshape(d, d)
+            assert np.abs(u @ u.conj().T - np.eye(d)).max() <= 1e-12
+
+
 @pytest.mark.parametrize("rows,cols", [(1, 1), (5000, 2), (4097, 31), (2, 5000), (32, 300), (100, 70), (33, 4099)])
 def test_transpose_layout_kernels(K, rows, cols):
     rng = np.random.default_rng(rows + cols)
