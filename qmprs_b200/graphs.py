@@ -9,7 +9,9 @@ pipeline is run SPECULATIVELY with static shapes and a fixed sweep budget, captu
 a CUDA graph per lane, and replayed per state; every assumption is validated on the device
 (``qm_expect_*``, ``qm_svd_static``) and a state whose flag comes back set is simply re-run
 through the eager path.  Several lanes (graph instance + private buffers + stream) run
-concurrently so that the one-CTA kernels of different states share the 148 SMs.
+concurrently so that the one-CTA kernels of different states share the 148 SMs.  Lanes are streams:
+they only overlap when each has its own hardware work queue (CUDA_DEVICE_MAX_CONNECTIONS, set to 32 in
+``qmprs_b200/__init__.py`` unless the user chose a value).
 """
 from __future__ import annotations
 
@@ -109,6 +111,8 @@ class GraphedPreparer:
         out[tag] = res
 
     def run(self, states):
+        """Round-robin the states over the lanes.  (Driving the lanes from several host threads was
+        measured: no gain -- the bound was the number of hardware work queues, not the host.)"""
         states = np.asarray(states, dtype=np.complex128)
         out = [None] * len(states)
         nl = len(self.lanes)
