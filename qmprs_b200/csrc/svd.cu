@@ -89,8 +89,8 @@ __device__ __forceinline__ void get_pair(const PairSpec& ps, int p, int& bi, int
 }
 
 // ---------------------------------------------------------------------------------
-// (1) Gram matrices.  grid = (nchunks, npairs).  G is accumulated with atomics and is
-// expected to be zero on entry (k_eig re-zeroes it after loading).
+// (1) Gram matrices.  grid = (nchunks, npairs).  Every CTA writes the partial Gram matrix of its column
+// chunk as a compact slab; k_eig sums the slabs in fixed order (no atomics: reproducible).
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT)
 k_gram(const cplx* __restrict__ W, long long ldw, int len, int chunk, int round, int nbp, int single,
@@ -140,6 +140,8 @@ k_gram(const cplx* __restrict__ W, long long ldw, int len, int chunk, int round,
         }
         __syncthreads();
     }
+    // no atomics: run-to-run reproducible.  Column slices of an entry are combined in fixed order through shared
+    // memory, and the CTA writes its own compact slab [E][2]; k_eig sums the slabs of all chunks in fixed order.
     if (ns == 1) {
 #pragma unroll
         for (int s = 0; s < 4; s++) {
@@ -147,12 +149,19 @@ k_gram(const cplx* __restrict__ W, long long ldw, int len, int chunk, int round,
             if (e < E) { gacc[2 * e] = acc[s].x; gacc[2 * e + 1] = acc[s].y; }
         }
     } else {
-        int e = tid % E, sl = tid / E;
-        if (sl < ns) { atomicAdd(&gacc[2 * e], acc[0].x); atomicAdd(&gacc[2 * e + 1], acc[0].y); }
+        cplx* part = tile;                               // the tile buffer is free now (>= NT entries)
+        __syncthreads();
+        part[tid] = (tid / E < ns) ? acc[0] : mk(0.0, 0.0);
+        __syncthreads();
+        if (tid < E) {
+            cplx t = mk(0.0, 0.0);
+            for (int sl = 0; sl < ns; sl++) t = cadd(t, part[sl * E + tid]);
+            gacc[2 * tid] = t.x; gacc[2 * tid + 1] = t.y;
+        }
     }
     __syncthreads();
-    double* Gp = G + (long long)pair * PMAX * PMAX * 2;
-    for (int i = tid; i < E * 2; i += NT) atomicAdd(&Gp[i], gacc[i]);
+    double* Gp = G + ((long long)pair * gridDim.x + blockIdx.x) * E * 2;
+    for (int i = tid; i < E * 2; i += NT) Gp[i] = gacc[i];
 }
 
 // ---------------------------------------------------------------------------------
@@ -188,8 +197,7 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
     const int tid = threadIdx.x, pair = slot_base + blockIdx.x;   // workspace slot of this pair
     const int n = nrows, ne = n + (n & 1), np = ne / 2;
     // nchunks > 0: G holds per-chunk partial Gram matrices [pair][chunk][PMAX*PMAX*2] written with plain
-    // stores by k_gram_mma (summed here in fixed order); nchunks == 0: one atomically accumulated matrix
-    // that is re-zeroed here (single-block path).
+    // stores by k_gram_mma (summed here in fixed order); nchunks < 0: single-block path, compact slabs.
     if (nchunks > 0) {
         const double* Gp = G + (long long)pair * nchunks * PMAX * PMAX * 2;
         for (int e = tid; e < n * n; e += NTE) {
@@ -204,13 +212,40 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
             q[i * GS + j] = mk(i == j ? 1.0 : 0.0, 0.0);
         }
     } else {
-        double* Gp = G + (long long)pair * PMAX * PMAX * 2;
-        for (int e = tid; e < n * n; e += NTE) {
-            int i = e / n, j = e % n;
-            g[i * GS + j] = mk(Gp[2 * e], Gp[2 * e + 1]);
-            Gp[2 * e] = 0.0; Gp[2 * e + 1] = 0.0;
-            q[i * GS + j] = mk(i == j ? 1.0 : 0.0, 0.0);
+        // single-block path: -nchunks compact slabs [2 n^2] written by the CTAs of k_gram / k_gram_skinny.
+        // Fixed-order sum: value v is summed over slabs sl, sl + nsl, ... by thread (sl, v), then over sl.
+        __shared__ double part[NTE];
+        const int ns_tot = -nchunks, E2 = 2 * n * n;
+        int nsl = NTE / E2;
+        if (nsl < 1) nsl = 1;
+        if (nsl > ns_tot) nsl = ns_tot;
+        const double* Gp = G + (long long)pair * ns_tot * E2;
+        double* gd = (double*)g;
+        if (nsl == 1) {
+            for (int v = tid; v < E2; v += NTE) {
+                double sacc = 0.0;
+#pragma unroll 8
+                for (int c = 0; c < ns_tot; c++) sacc += __ldcg(Gp + (long long)c * E2 + v);
+                const int e = v >> 1;
+                gd[2 * ((e / n) * GS + (e % n)) + (v & 1)] = sacc;
+            }
+        } else {
+            if (tid < E2 * nsl) {
+                const int v = tid % E2, sl = tid / E2;
+                double sacc = 0.0;
+#pragma unroll 8
+                for (int c = sl; c < ns_tot; c += nsl) sacc += __ldcg(Gp + (long long)c * E2 + v);
+                part[tid] = sacc;
+            }
+            __syncthreads();
+            for (int v = tid; v < E2; v += NTE) {
+                double sacc = 0.0;
+                for (int sl = 0; sl < nsl; sl++) sacc += part[sl * E2 + v];
+                const int e = v >> 1;
+                gd[2 * ((e / n) * GS + (e % n)) + (v & 1)] = sacc;
+            }
         }
+        for (int e = tid; e < n * n; e += NTE) q[(e / n) * GS + (e % n)] = mk((e / n) == (e % n) ? 1.0 : 0.0, 0.0);
     }
     for (int e = tid; e < (ne - 1) * np; e += NTE) {
         int r = e / np, k = e % np, a, b;
@@ -689,7 +724,8 @@ k_gram_skinny(const cplx* __restrict__ W, long long ldw, long long len, int nrow
 #pragma unroll
         for (int w2 = 0; w2 < NT / 32; w2++) ssum += red[w2][threadIdx.x];
         int e = threadIdx.x >> 1, i = e >> 2, j = e & 3;
-        if (i < nrows && j < nrows) atomicAdd(&G[2 * (i * nrows + j) + (threadIdx.x & 1)], ssum);
+        // compact slab of this CTA (summed in fixed order by k_eig)
+        if (i < nrows && j < nrows) G[(long long)blockIdx.x * 2 * nrows * nrows + 2 * (i * nrows + j) + (threadIdx.x & 1)] = ssum;
     }
 }
 
@@ -764,6 +800,7 @@ __global__ void k_static_check(const int* __restrict__ nc, int* __restrict__ mis
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 constexpr int MAXCH = 32;     // Gram partial slots per pair (DMMA path)
+constexpr int MAXCH1 = 64;    // Gram slabs of the single-block path
 
 struct Work {
     cplx* W; double* G; cplx* Q; int* rotated; double* sig2; int* perm; int* notconv;
@@ -775,7 +812,11 @@ Work carve(const Geom& g, void* base) {
     size_t off = 0;
     char* b = (char*)base;
     w.W = (cplx*)(b + off); off += align_up((size_t)g.nvp * g.ldw * sizeof(cplx));
-    w.G = (double*)(b + off); off += align_up((size_t)g.npairs * MAXCH * PMAX * PMAX * 2 * sizeof(double));
+    {   // multi-block: MAXCH slabs per pair; single block: up to MAXCH1 full slabs or 148*4 skinny ones
+        size_t slabs = (size_t)g.npairs * MAXCH;
+        if (slabs < (size_t)MAXCH1) slabs = MAXCH1;
+        w.G = (double*)(b + off); off += align_up(slabs * PMAX * PMAX * 2 * sizeof(double));
+    }
     w.Q = (cplx*)(b + off); off += align_up((size_t)g.npairs * PMAX * PMAX * sizeof(cplx));
     w.rotated = (int*)(b + off); off += align_up((size_t)g.npairs * sizeof(int));
     w.sig2 = (double*)(b + off); off += align_up((size_t)g.nvp * sizeof(double));
@@ -936,9 +977,13 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         }
     }
     const int npl = grouped ? g.npairs / NG : g.npairs;         // pairs per DMMA launch
-    const long long chunk_g = g.single ? pick_chunk(g.len) : gram_chunk(npl);
+    long long chunk_g = g.single ? pick_chunk(g.len) : gram_chunk(npl);
+    if (g.single && (g.len + chunk_g - 1) / chunk_g > MAXCH1) chunk_g = ((g.len + MAXCH1 - 1) / MAXCH1 + TC - 1) / TC * TC;
     const long long chunk_a = g.single ? pick_chunk(lenx) : pick_chunk_mma(lenx, 64, npl);
     const int ncg = ceil_div(g.len, chunk_g), nca = ceil_div(lenx, chunk_a);
+    const bool skinny = g.single && g.nrows <= 4 && g.len >= 4096;
+    const int nb_skinny = ceil_div(g.len, NT) > 148 * 4 ? 148 * 4 : ceil_div(g.len, NT);
+    const int eig_chunks = g.single ? -(skinny ? nb_skinny : ncg) : ncg;      // < 0: compact slabs of the single-block path
 
     for (; sweeps < max_sweeps;) {
         const int max_inner = (sweeps == 0) ? tune_inner0 : tune_inner;
@@ -951,10 +996,10 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         };
         auto launch_eig = [&](const PairSpec& ps, int np, int slot, cudaStream_t s) {
             if (is_static) QM_LAUNCH(QM_CLS_SVD_EIG, s, k_eig<<<np, NTE, EIG_SMEM, s>>>(
-                w.G, g.single ? 0 : ncg, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, tune_ratio, cross_only, ps, slot,
+                w.G, eig_chunks, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, tune_ratio, cross_only, ps, slot,
                 g.single, w.notconv, w.rotated, w.sig2, donep));
             else QM_LAUNCH(QM_CLS_SVD_EIG, s, qm_launch_dep(k_eig, dim3(np), dim3(NTE), EIG_SMEM, s,
-                w.G, g.single ? 0 : ncg, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, tune_ratio, cross_only, ps, slot,
+                w.G, eig_chunks, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, tune_ratio, cross_only, ps, slot,
                 g.single, w.notconv, w.rotated, w.sig2, donep));
         };
         auto launch_apply = [&](const PairSpec& ps, int np, int slot, cudaStream_t s) {
@@ -998,10 +1043,9 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         } else {
             for (int r = 0; r < g.rounds; r++) {
                 const PairSpec ps = {0, r, g.nbp, 0, 0};
-                if (g.single && g.nrows <= 4 && g.len >= 4096) {
-                    int nb = ceil_div(g.len, NT) > 148 * 4 ? 148 * 4 : ceil_div(g.len, NT);
-                    QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram_skinny<<<nb, NT, 0, st>>>(w.W, g.ldw, (long long)g.len, g.nrows,
-                                                                                  w.G, donep));
+                if (skinny) {
+                    QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram_skinny<<<nb_skinny, NT, 0, st>>>(w.W, g.ldw, (long long)g.len, g.nrows,
+                                                                                         w.G, donep));
                 } else if (g.single) {
                     QM_LAUNCH(QM_CLS_SVD_GRAM, st, k_gram<<<dim3(ncg, g.npairs), NT, 0, st>>>(
                         w.W, g.ldw, g.len, (int)chunk_g, r, g.nbp, g.single, g.nrows, w.G, donep));
