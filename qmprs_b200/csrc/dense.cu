@@ -239,9 +239,8 @@ k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int 
     constexpr int GSZ = 1 << NU;
     constexpr int CSH = NU - (CD == 4 ? 2 : 1);
     constexpr int NLOW = 1 << CSH;
+    constexpr int PDD = PD > 0 ? PD : 1;     // divisor that is never zero in the PD == 0 instantiations
     __shared__ cplx Pm[16];
-    __shared__ double wsum[NT / 32][32];
-    __shared__ int s_last;
     const long long ngroups = 1LL << (nbits - NU);
     const long long stride = 1LL << q0;
     const long long lowmask = stride - 1;
@@ -258,7 +257,7 @@ k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int 
     pdl_wait();
     pdl_trigger();
     if (PD > 0 && threadIdx.x < PD * PD) {
-        int a = threadIdx.x / PD, b = threadIdx.x % PD;
+        int a = threadIdx.x / PDD, b = threadIdx.x % PDD;
         Pm[threadIdx.x] = Gpend[b * PD + a];                  // M = G^T : tbar'[b] = sum_o G[o][b] tbar[o]
     }
     __syncthreads();
@@ -279,7 +278,7 @@ k_env_fused(cplx* __restrict__ tbar, const cplx* __restrict__ c, int nbits, int 
         first = false;
         if (PD > 0) {
 #pragma unroll
-            for (int h = 0; h < GSZ / PD; h++) {
+            for (int h = 0; h < GSZ / PDD; h++) {
                 cplx y[PD > 0 ? PD : 1];
 #pragma unroll
                 for (int a = 0; a < PD; a++) {

@@ -183,3 +183,14 @@ def test_exact_split_matches_svd_split(K, n, chi, L, S):
     assert a["n_layers"] == b["n_layers"] and a["kinds"] == b["kinds"]
     assert np.abs(a["gates"] - b["gates"]).max() <= 1e-7
     assert abs(a["fidelity"] - b["fidelity"]) <= 1e-9
+
+
+def test_repeat_runs_are_bit_identical(K):
+    """No floating-point atomics on the path: the same input gives the same gate records bit for bit
+    (single-block and multi-block SVD paths, dense sweeps in shared memory and in HBM)."""
+    for n, chi, L, S in [(10, 32, 4, 3), (13, 64, 3, 2)]:
+        psi = O.random_state(n, 77)
+        a = host.prepare(K, psi, n, chi, L, S)
+        b = host.prepare(K, psi, n, chi, L, S)
+        assert np.array_equal(np.asarray(a["gates"]), np.asarray(b["gates"]))
+        assert a["kinds"] == b["kinds"]
