@@ -91,10 +91,21 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
+def use_all_host_threads():
+    """The CPU arm runs with every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    leave the BLAS behind numpy single-threaded; raise the pools back to the core count."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     setup = None
     totals = []
     for i in range(args.warmup + args.steps):
@@ -306,6 +317,7 @@ def run_ours(args, wl):
                      "classes": {k: {"ms": round(v[0], 3), "launches": v[1], "work": v[2]} for k, v in prof.items()}})
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            use_all_host_threads()
             tot, br, _ = cpu_sample(wl, 4242)
             cpu = {"value": 1.0 / tot, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
                    "sample": ("numpy oracle at full size: MPS build + 1 disentangling layer + 1 layer of sweep gate-steps, "
@@ -359,6 +371,7 @@ def run_batch(args, wl, K, dev, world, rank, sync_all, max_over_ranks):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import qmprs_oracle as O
+            use_all_host_threads()
             t0 = time.perf_counter()
             nref = 4
             for s in range(nref):
