@@ -137,8 +137,7 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
                 __syncwarp();
                 polar_conj_warp(Es, d, G, pol_scratch, warm ? vw + k * 16 : nullptr);
                 // the rank-deficient branch of the polar returns early in 31 lanes while lane 0 finishes the
-                // single-thread completion: reconverge before the block barrier (a partial-warp arrival at
-                // bar.sync is undefined and was observed to release the barrier early)
+                // single-thread completion: reconverge before the block barrier
                 __syncwarp();
                 if (envs && sweep == num_sweeps - 1 && lane < d * d) envs[k * 16 + lane] = Es[lane];
             }
