@@ -9,7 +9,9 @@ iteration (Higham 1986) and the agreement with u @ vh from the SVD.
 Result (10 qubits, 15 layers, 6 sweeps, seed 0): 810 4x4 environments, 60 of them rank-deficient (fresh |0> inputs:
 they take the canonical completion path whatever the solver); condition numbers median 43, 99th percentile 9.7e2,
 maximum 1.7e3; the scaled Newton iteration converges in 7 (median) to 8 (maximum) iterations and agrees with
-u @ vh to 1e-14.  At ~0.2-0.3 us per cofactor-inverse iteration that is ~2 us against the ~8 us of the Jacobi polar.
+u @ vh to 1e-14.  The warp-cooperative CUDA version of exactly this iteration was built and passed every GPU test, but
+measured no faster than the Jacobi polar (one warp, ~250 instructions per iteration; profiles/ncu_r01_summary.md), so
+the device code keeps the Jacobi polar; the study stays as the numerical reference for a wider formulation.
 
 usage: python scripts/polar_newton_study.py [n_qubits layers sweeps]
 """
