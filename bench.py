@@ -1,15 +1,21 @@
 #!/usr/bin/env python
-"""Benchmark of the qmprs MPS hot path on B200:  Sequential.prepare_state at the
-BASELINE.json headline configuration (20 qubits, chi=512, 15 layers, 50 sweeps).
+"""Benchmark of the qmprs MPS hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|c1|c2|c3|c5]
 
-A "step" is one prepare_state of a fresh synthetic random state (reference distribution,
-README.md:52-53).  Prints ONE JSON line (see the task contract): `value` = whole-job
-states/s with the input resident in HBM, `e2e` = the same through the public
-Sequential.prepare_state call with host buffers, `roofline` for the dominant kernel
-(timed live with CUDA events in one extra instrumented step), `cpu_baseline` = the numpy
-oracle on the host cores on a bounded sample.  `--impl reference` times the CPU path only.
+BASELINE.json's metric has two parts and `--workload auto` (default) picks by N:
+  N = 1   "prepare_state s/state at 20q chi=512 15 layers": Sequential.prepare_state at the headline
+          configuration C3 (20 qubits, chi=512, 15 layers, 50 sweeps).  A step = one prepare_state of a fresh
+          synthetic random state (reference distribution, README.md:52-53).  The same line carries, under
+          `batch_c5`, one pass of the sharded batch workload on this one GPU: the N = 1 point of the
+          multi-GPU curve.
+  N > 1   "batch states/sec 1-8 GPU": configuration C5, 4096 random 12-qubit states (chi=64, 10 layers,
+          20 sweeps) sharded by state over the N ranks, ending in the path's one collective
+          (all_gather_into_tensor of the gate records over NCCL).  A step = the whole batch; strong scaling.
+Prints ONE JSON line (task contract): `value` = whole-job states/s with the inputs resident in HBM, `e2e` =
+the same through the public call with host buffers, `roofline` for the dominant kernel (timed live with CUDA
+events in one extra instrumented step), `cpu_baseline` = the numpy oracle on the host cores on a bounded
+sample (N = 1 only).  `--impl reference` times the CPU path only (rank 0).
 """
 from __future__ import annotations
 
@@ -101,15 +107,101 @@ def use_all_host_threads():
         pass
 
 
+def _cpu_batch_worker(job):
+    """One host core: `verbatim` oracle on a few states of the batch, BLAS single-threaded."""
+    seeds, n, chi, L, S = job
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:
+        pass
+    from oracle import qmprs_oracle as O
+    t0 = time.perf_counter()
+    for sd in seeds:
+        O.prepare(rand_state(n, sd), n, chi, L, S, gauge="verbatim")
+    return time.perf_counter() - t0
+
+
+class CpuBatchPool:
+    """CPU arm of the batch workload: the states are independent, so the host runs one oracle process per
+    core (what a user of the reference would do with multiprocessing).  The pool is started (spawn: nothing
+    of this process's CUDA state is inherited) and warmed once; every sample times `per_core` states per core."""
+
+    def __init__(self, wl):
+        import concurrent.futures as cf
+        import multiprocessing as mp
+        self.wl = wl
+        self.cores = os.cpu_count() or 1
+        keep = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+        for k in keep:
+            os.environ[k] = "1"                            # inherited by the workers: single-threaded BLAS each
+        try:
+            self.ex = cf.ProcessPoolExecutor(max_workers=self.cores, mp_context=mp.get_context("spawn"))
+            cfg = (wl["n"], wl["chi"], wl["layers"], wl["sweeps"])
+            list(self.ex.map(_cpu_batch_worker, [([0], *cfg)] * self.cores))       # start-up + imports, untimed
+        finally:
+            for k, v in keep.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+    def sample(self, per_core=2, first_seed=0):
+        """Returns (states/s, cores, states timed, wall seconds)."""
+        wl = self.wl
+        cfg = (wl["n"], wl["chi"], wl["layers"], wl["sweeps"])
+        jobs = [([first_seed + c * per_core + j for j in range(per_core)], *cfg) for c in range(self.cores)]
+        t0 = time.perf_counter()
+        list(self.ex.map(_cpu_batch_worker, jobs))
+        wall = time.perf_counter() - t0
+        nst = self.cores * per_core
+        return nst / wall, self.cores, nst, wall
+
+    def close(self):
+        self.ex.shutdown()
+
+
+def run_reference_batch(args, wl):
+    vals = []
+    pool = CpuBatchPool(wl)
+    for i in range(args.warmup + args.steps):
+        v, cores, nst, wall = pool.sample(per_core=2, first_seed=1000 * (i + 1))
+        if i >= args.warmup:
+            vals.append(v)
+    pool.close()
+    val = float(np.mean(vals))
+    B = wl["batch"]
+    sample = (f"per step: {nst} states of the batch, one numpy-oracle process per host core ({cores} cores, BLAS "
+              f"single-threaded inside each), {wall:.1f} s wall; value = states timed / wall (the full batch of {B} is "
+              f"{B / val:.0f} s at this rate)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": B / val * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "c128", "data": "synthetic", "config": batch_config(wl, args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "measured_sample_s": wall,
+    }))
+
+
+def batch_config(wl, world):
+    return {"workload": wl["name"], "n_qubits": wl["n"], "chi": wl["chi"], "layers": wl["layers"],
+            "sweeps": wl["sweeps"], "batch": wl["batch"]}
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if "batch" in wl:
+        return run_reference_batch(args, wl)
     use_all_host_threads()
     setup = None
     totals = []
     for i in range(args.warmup + args.steps):
+        t_s = time.perf_counter()
         tot, br, setup = cpu_sample(wl, 1000 + i, setup)
+        t_s = time.perf_counter() - t_s
         if i >= args.warmup:
             totals.append(tot)
     sec = float(np.mean(totals))
@@ -127,6 +219,9 @@ def run_reference(args, wl):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # wall time of one step's bounded sample (ms_per_step is the EXTRAPOLATED full-workload time: it does
+        # not fit inside this process's run time by construction)
+        "measured_sample_s": t_s,
     }
     print(json.dumps(line))
 
@@ -188,23 +283,73 @@ def measure_fp64_peak(torch, dev):
     return 8.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def run_ours(args, wl):
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+SVD_STAGE = ("svd_gram", "svd_eig", "svd_apply", "svd_layout")
+
+
+def roofline_from_profile(prof, peak_tf):
+    """`prof`: {class: (ms, launches, algorithmic work)} of one instrumented step (CUDA events around every
+    launch).  Reports the TIME-DOMINANT part of the step.  The Jacobi SVD is three kernels per round
+    (k_gram_mma -> k_eig -> k_apply_mma) of which the 32x32 eigen-solve is latency bound and carries no flops
+    of its own, so the SVD is reported as a stage: algorithmic flops of its Gram + update GEMMs over the time
+    of all its kernels.  Streaming classes are reported against the measured HBM bandwidth."""
+    peaks = load_peaks()
+    tot_ms = sum(v[0] for v in prof.values())
+    svd_ms = sum(prof[k][0] for k in SVD_STAGE if k in prof)
+    svd_work = sum(prof[k][2] for k in SVD_STAGE if k in prof and k != "svd_layout")
+    groups = {"svd": (svd_ms, sum(prof[k][1] for k in SVD_STAGE if k in prof), svd_work)}
+    for k, v in prof.items():
+        if k not in SVD_STAGE:
+            groups[k] = v
+    dom = max(groups, key=lambda k: groups[k][0])
+    d_ms, d_cnt, d_work = groups[dom]
+    if dom in ("gate", "env_polar"):
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        ach = d_work / (d_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}
+    else:
+        ach = d_work / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": None,
+                "peak_source": "FP64: cuBLAS ZGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)"}
+    name = {"svd": "svd stage: k_gram_mma + k_eig + k_apply_mma (+ layout)", "zgemm": "k_zgemm_tma",
+            "env_polar": "k_env_fused", "gate": "k_gate2"}.get(dom, dom)
+    try:      # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, cold cache)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        t = tj.get("svd_apply" if dom == "svd" else dom)
+        roof["traffic"] = t["bytes"] if t else None
+        roof["traffic_note"] = t.get("note") if t else None
+    except Exception:
+        pass
+    def tf(k):
+        ms, cnt, work = prof[k]
+        return {"ms": round(ms, 3), "launches": cnt, "share": ms / tot_ms, "avg_launch_us": 1e3 * ms / max(cnt, 1),
+                "work": work, "rate": (work / (ms * 1e-3) / (1e9 if k in ("gate", "env_polar") else 1e12)) if ms > 0 and work > 0 else None}
+    roof.update({"kernel": name, "launches": d_cnt, "avg_launch_us": 1e3 * d_ms / max(d_cnt, 1),
+                 "share_of_kernel_time": d_ms / tot_ms,
+                 "classes": {k: tf(k) for k in prof if prof[k][0] > 0.0}})
+    return roof
+
+
+def bench_env(args):
     import torch
     import torch.distributed as dist
-    from qmprs_b200 import GateListCircuit, host
     from qmprs_b200.kernels import get_kernels
-    from qmprs.synthesis.mps_encoding import Sequential
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     K = get_kernels(str(dev))
-    n, chi, L, S = wl["n"], wl["chi"], wl["layers"], wl["sweeps"]
-    W, Ksteps = args.warmup, args.steps
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -218,8 +363,49 @@ def run_ours(args, wl):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    return dict(torch=torch, dist=dist, world=world, rank=rank, local=local, dev=dev, K=K, sync_all=sync_all,
+                max_over_ranks=max_over_ranks)
+
+
+def run_ours(args, wl):
+    env = bench_env(args)
+    torch, dist, world, rank, dev, K = env["torch"], env["dist"], env["world"], env["rank"], env["dev"], env["K"]
     if "batch" in wl:
-        return run_batch(args, wl, K, dev, world, rank, sync_all, max_over_ranks)
+        line = measure_batch(args, wl, env, args.steps, args.warmup, main_line=True)
+    else:
+        line = measure_single(args, wl, env)
+        if rank == 0 and args.workload == "auto" and world == 1:
+            # N = 1 point of the multi-GPU curve: one pass of the sharded batch workload on this GPU
+            try:
+                b = measure_batch(args, WORKLOADS["c5"], env, steps=1, warmup=1, main_line=False)
+                line["batch_c5"] = {k: b[k] for k in ("value", "unit", "ms_per_step", "config", "e2e", "gpu_launches",
+                                                      "graph", "fidelity_mean", "cpu_baseline", "scaling")}
+                try:
+                    json.dump({"value": b["value"], "e2e": b["e2e"]["value"], "when": time.time()},
+                              open(C5_N1_FILE, "w"))
+                except Exception:
+                    pass
+            except Exception as ex:                       # never lose the headline line to the extra pass
+                line["batch_c5"] = {"error": repr(ex)}
+    if rank == 0 and line is not None:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+C5_N1_FILE = "/tmp/qmprs_b200_bench_c5_n1.json"
+
+
+def measure_single(args, wl, env):
+    """One state per step per GPU (C1-C3): `value` with the state resident in HBM, `e2e` through
+    Sequential.prepare_state with a pinned host buffer in and the gate records out."""
+    torch, world, rank, local, dev, K = env["torch"], env["world"], env["rank"], env["local"], env["dev"], env["K"]
+    sync_all, max_over_ranks = env["sync_all"], env["max_over_ranks"]
+    from qmprs_b200 import GateListCircuit, host
+    from qmprs.synthesis.mps_encoding import Sequential
+    n, chi, L, S = wl["n"], wl["chi"], wl["layers"], wl["sweeps"]
+    W, Ksteps = args.warmup, args.steps
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     states = [rand_state(n, rank * 100003 + i) for i in range(W + Ksteps)]
     dev_states = [K.from_host(s) for s in states]
@@ -249,8 +435,7 @@ def run_ours(args, wl):
     enc = Sequential(GateListCircuit)
     enc.gate_split = args.split
     pinned = [torch.from_numpy(s).pin_memory().numpy() for s in states[W:]]
-    for s in states[:2]:      # untimed: lets small registers (n <= 16) switch to their captured graph (steady state)
-        enc.prepare_state(s, chi, num_layers=L, num_sweeps=S)
+    enc.prepare_state(states[0], chi, num_layers=L, num_sweeps=S)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -263,155 +448,157 @@ def run_ours(args, wl):
     sync_all()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e = world * Ksteps / (ms_e2e * 1e-3)
+    if rank != 0:
+        return None
 
-    line = None
-    if rank == 0:
-        # ---- roofline of the dominant kernel: one extra instrumented step (CUDA events per launch) ----
-        peak_tf = measure_fp64_peak(torch, dev)
-        K.prof_begin()
-        host.prepare(K, dev_states[-1], n, chi, L, S, split=args.split)
-        prof = K.prof_end()
-        # same workload with the opt-in SVD-free re-split (identical circuit), reported beside `value`
-        alt = None
-        if args.split == "svd":
-            host.prepare(K, dev_states[0], n, chi, L, S, split="exact")
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            falt = [host.prepare(K, dev_states[W + i], n, chi, L, S, split="exact")["fidelity"] for i in range(Ksteps)]
-            a1.record()
-            torch.cuda.synchronize(dev)
-            alt = {"split": "exact", "value": Ksteps / (a0.elapsed_time(a1) * 1e-3), "unit": UNIT,
-                   "max_abs_fidelity_diff_vs_svd": float(np.max(np.abs(np.array(falt) - np.array(fid[W:W + Ksteps]))))}
-        tot_ms = sum(v[0] for v in prof.values())
-        # dominant kernel with a throughput roofline; latency-bound classes (no algorithmic-work model:
-        # the 32x32 shared-memory eigen-solve, per-column Householder vectors, small kernels) are reported
-        # as time shares only ("latency/occupancy-bound, report as time only")
-        latency = {k: {"share": v[0] / tot_ms, "avg_launch_us": 1e3 * v[0] / max(v[1], 1)}
-                   for k, v in prof.items() if v[2] == 0.0 and v[0] > 0.0}
-        dom = max((k for k in prof if prof[k][2] > 0.0), key=lambda k: prof[k][0])
-        d_ms, d_cnt, d_work = prof[dom]
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        if dom in ("gate", "env_polar"):
-            hbm = peaks.get("hbm_gbs", 6650.0)
-            ach = d_work / (d_ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}
-        else:
-            ach = d_work / (d_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                    "traffic": None,
-                    "peak_source": "FP64: cuBLAS ZGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)"}
-        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, cold cache)
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
-            roof["traffic"] = traffic["bytes"] if traffic else None
-            roof["traffic_note"] = traffic.get("note") if traffic else None
-        except Exception:
-            pass
-        roof.update({"kernel": dom, "launches": d_cnt, "avg_launch_us": 1e3 * d_ms / max(d_cnt, 1),
-                     "share_of_kernel_time": d_ms / tot_ms, "latency_bound_classes": latency,
-                     "classes": {k: {"ms": round(v[0], 3), "launches": v[1], "work": v[2]} for k, v in prof.items()}})
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            use_all_host_threads()
-            tot, br, _ = cpu_sample(wl, 4242)
-            cpu = {"value": 1.0 / tot, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-                   "sample": ("numpy oracle at full size: MPS build + 1 disentangling layer + 1 layer of sweep gate-steps, "
-                              f"extrapolated t_mps + L*t_layer + S*L*t_sweep_layer = {br['t_mps']:.2f} + {L}*{br['t_layer']:.2f}"
-                              f" + {S}*{L}*{br['t_sweep_layer']:.2f} s")}
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Ksteps, "warmup": W,
-            "ms_per_step": ms / Ksteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "c128", "data": "synthetic",
-            "config": {"workload": wl["name"], "n_qubits": n, "chi": chi, "layers": L, "sweeps": S,
-                       "states_per_step_per_gpu": 1, "gate_split": args.split, "l2": "256 MiB buffer rewritten between steps",
-                       "parallelism": f"{world} independent states (one per GPU), no data-path collective"},
-            "s_per_state": ms * 1e-3 / Ksteps,
-            "fidelity_mean": float(np.mean(fid[W:])),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(16 * 2 ** n), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-            "alt_exact_split": alt,
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    # ---- roofline: one extra instrumented step (CUDA events per launch) ----
+    peak_tf = measure_fp64_peak(torch, dev)
+    K.prof_begin()
+    host.prepare(K, dev_states[-1], n, chi, L, S, split=args.split)
+    roof = roofline_from_profile(K.prof_end(), peak_tf)
+    # same workload with the opt-in SVD-free re-split (identical circuit), reported beside `value`
+    alt = None
+    if args.split == "svd":
+        host.prepare(K, dev_states[0], n, chi, L, S, split="exact")
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        na = min(Ksteps, 3)
+        falt = [host.prepare(K, dev_states[W + i], n, chi, L, S, split="exact")["fidelity"] for i in range(na)]
+        a1.record()
+        torch.cuda.synchronize(dev)
+        alt = {"split": "exact", "value": na / (a0.elapsed_time(a1) * 1e-3), "unit": UNIT,
+               "max_abs_fidelity_diff_vs_svd": float(np.max(np.abs(np.array(falt) - np.array(fid[W:W + na]))))}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        use_all_host_threads()
+        tot, br, _ = cpu_sample(wl, 4242)
+        cpu = {"value": 1.0 / tot, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+               "sample": ("numpy oracle at full size: MPS build + 1 disentangling layer + 1 layer of sweep gate-steps, "
+                          f"extrapolated t_mps + L*t_layer + S*L*t_sweep_layer = {br['t_mps']:.2f} + {L}*{br['t_layer']:.2f}"
+                          f" + {S}*{L}*{br['t_sweep_layer']:.2f} s")}
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Ksteps, "warmup": W,
+        "ms_per_step": ms / Ksteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "c128", "data": "synthetic",
+        "config": {"workload": wl["name"], "n_qubits": n, "chi": chi, "layers": L, "sweeps": S,
+                   "states_per_step_per_gpu": 1, "gate_split": args.split, "l2": "256 MiB buffer rewritten between steps",
+                   "parallelism": f"{world} independent states (one per GPU), no data-path collective"},
+        "s_per_state": ms * 1e-3 / Ksteps,
+        "fidelity_mean": float(np.mean(fid[W:])),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(16 * 2 ** n), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        "alt_exact_split": alt,
+    }
 
 
-def run_batch(args, wl, K, dev, world, rank, sync_all, max_over_ranks):
-    """Config 5: a step = one batch of `--batch` independent states sharded over the ranks
-    (state s -> rank s mod world) followed by the single all-gather of the gate records."""
-    import torch
-    import torch.distributed as dist
+def measure_batch(args, wl, env, steps, warmup, main_line):
+    """Config 5: a step = the whole batch of independent states sharded over the ranks (state s -> rank
+    s mod world), every state one CUDA-graph replay on one of `--lanes` concurrent lanes, followed by the
+    single all-gather of the gate records.  `value`: the rank's shard of the states is resident in HBM when
+    the timed region starts and the gathered records stay in HBM; `e2e`: numpy states in, list of records out
+    through qmprs_b200.batch.prepare_state_batch (pinned H2D of the shard, D2H of the gathered records)."""
+    torch, world, rank, local, dev, K = env["torch"], env["world"], env["rank"], env["local"], env["dev"], env["K"]
+    sync_all, max_over_ranks = env["sync_all"], env["max_over_ranks"]
     from qmprs_b200 import batch as qb
-    n, chi, L, S = wl["n"], wl["chi"], wl["layers"], wl["sweeps"]
-    B = args.batch
+    from qmprs_b200 import host
     from qmprs_b200.graphs import GraphedPreparer
+    n, chi, L, S = wl["n"], wl["chi"], wl["layers"], wl["sweeps"]
+    B = args.batch or wl["batch"]
     states = np.stack([rand_state(n, s) for s in range(B)])          # seed = state index (SURVEY 8d)
     prep = GraphedPreparer(n, chi, L, S, lanes=args.lanes, device=str(dev)) if args.lanes > 0 else None
-    for _ in range(max(args.warmup, 1)):
-        qb.prepare_state_batch(states[: 2 * world * max(args.lanes, 1)], chi, L, S, kernels=K, preparer=prep)
+    sdev = torch.from_numpy(states).to(dev)
+    small = 2 * world * max(args.lanes, 1)
+    for w in range(max(warmup, 1)):
+        # the first warm-up pass is a short one (lazy initialisation), later ones the full batch
+        qb.prepare_state_batch(sdev if w > 0 else sdev[:small], chi, L, S, kernels=K, preparer=prep, return_device=True)
+    clocks = ClockSampler(local)
     sync_all()
-    l0 = K.launch_count()
-    r0 = prep.replays if prep else 0
+    clocks.start()
+    l0, r0 = K.launch_count(), (prep.replays if prep else 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        recs = qb.prepare_state_batch(states, chi, L, S, kernels=K, preparer=prep)
+    for _ in range(steps):
+        recs_dev = qb.prepare_state_batch(sdev, chi, L, S, kernels=K, preparer=prep, return_device=True)
     e1.record()
     sync_all()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    value = args.steps * B / (ms * 1e-3)
-    if rank == 0:
-        fid = float(np.mean([r["fidelity"] for r in recs]))
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import qmprs_oracle as O
-            use_all_host_threads()
-            t0 = time.perf_counter()
-            nref = 4
-            for s in range(nref):
-                O.prepare(states[s], n, chi, L, S, gauge="verbatim")
-            dt = (time.perf_counter() - t0) / nref
-            cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-                   "sample": f"numpy oracle, {nref} states of the batch run one after the other (BLAS threads as configured)"}
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "c128", "data": "synthetic",
-            "config": {"workload": wl["name"], "n_qubits": n, "chi": chi, "layers": L, "sweeps": S, "batch": B,
-                       "parallelism": f"states sharded over {world} GPU(s), one all-gather of records"},
-            "fidelity_mean": fid, "cpu_baseline": cpu,
-            "gpu_launches": int(K.launch_count() - l0 + ((prep.replays - r0) * prep.nodes_per_graph if prep else 0)),
-            "graph": ({"lanes": args.lanes, "kernel_nodes_per_state": prep.nodes_per_graph,
-                       "eager_fallbacks": prep.fallbacks} if prep else None),
-            "value_note": "the batch workload is timed end to end only: host states in (pinned H2D per state), host gate records out",
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(B * 16 * 2 ** n // world),
-                    "d2h_bytes_per_step": int(B * qb.record_len(n, L) * 8)},
-        }))
+    clk = clocks.stop()
+    launches = int(K.launch_count() - l0 + ((prep.replays - r0) * prep.nodes_per_graph if prep else 0))
+    value = steps * B / (ms * 1e-3)
+    # ---- end to end: host states in, host records out ----
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        recs = qb.prepare_state_batch(states, chi, L, S, kernels=K, preparer=prep)
+    e1.record()
+    sync_all()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e = steps * B / (ms_e2e * 1e-3)
+    if rank != 0:
+        return None
+    rl = qb.record_len(n, L)
+    fid = float(np.mean([r["fidelity"] for r in recs]))
+    roof = None
+    cpu = None
+    if main_line:
+        # instrumented EAGER pass over a few states (graph replays bypass the per-launch events)
+        peak_tf = measure_fp64_peak(torch, dev)
+        K.prof_begin()
+        for s in range(4):
+            host.prepare(K, sdev[s], n, chi, L, S)
+        roof = roofline_from_profile(K.prof_end(), peak_tf)
+        roof["note"] = ("eager instrumented pass over 4 states; the timed region replays the same kernels from CUDA "
+                        "graphs, where launch latency (not any pipe) bounds a 12-qubit state")
+    if world == 1 and not args.no_cpu_baseline:
+        pool = CpuBatchPool(wl)
+        v, cores, nst, wall = pool.sample(per_core=2, first_seed=0)
+        pool.close()
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": (f"{nst} states of the batch, one numpy-oracle process per host core ({cores} cores, BLAS "
+                          f"single-threaded inside each), {wall:.1f} s wall")}
+    n1 = None
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        try:
+            j = json.load(open(C5_N1_FILE))
+            if time.time() - j["when"] < 4 * 3600:
+                n1 = {"value": j["value"], "e2e": j["e2e"], "source": "batch_c5 of this box's preceding --gpus 1 run"}
+        except Exception:
+            pass
+    cfg = batch_config(wl, world)
+    cfg.update({"batch": B, "graph_lanes_per_gpu": args.lanes, "l2": "inputs larger than L2: 256 MiB of states per batch",
+                "parallelism": f"states sharded over {world} GPU(s) (state s -> rank s mod {world}), "
+                               "one all_gather_into_tensor of the records (NCCL)"})
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "c128", "data": "synthetic", "config": cfg,
+        "fidelity_mean": fid, "cpu_baseline": cpu, "clocks": clk, "roofline": roof,
+        "gpu_launches": launches,
+        "graph": ({"lanes": args.lanes, "kernel_nodes_per_state": prep.nodes_per_graph,
+                   "eager_fallbacks": prep.fallbacks} if prep else None),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 16 * 2 ** n),
+                "d2h_bytes_per_step": int(world * ((B + world - 1) // world) * rl * 8)},
+        "n1_same_workload": n1,
+    }
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lanes", type=int, default=32, help="concurrent CUDA-graph lanes per GPU for --workload c5 (0 = eager)")
-    ap.add_argument("--batch", type=int, default=64, help="states per step for --workload c5 (config 5 uses 4096)")
+    ap.add_argument("--batch", type=int, default=0, help="states per step for the batch workload (default: config 5's 4096)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS),
+                    help="auto: c3 (headline single state) at --gpus 1, c5 (sharded batch + NCCL gather) at --gpus N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--split", default="svd", choices=["svd", "exact"],
                     help="two-site re-split: 'svd' = reference arithmetic (default), 'exact' = gauge-free, no SVD")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = WORKLOADS[("c3" if max(world, args.gpus) == 1 else "c5") if args.workload == "auto" else args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
     else:

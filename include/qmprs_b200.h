@@ -107,7 +107,10 @@ int qm_expect_not_close(const void* f, double tol, void* mismatch, void* stream)
 
 /* ---- vectors ------------------------------------------------------------------- */
 int qm_conj_scale_copy(void* out, const void* in, long long n, int conj, double scale, void* stream);
-int qm_vdot(const void* a, const void* b, long long n, void* out2 /* double[2] */, void* stream);
+/* out[0..1] = sum conj(a_i) b_i (re, im).  Reproducible: per-CTA partials are kept in out[2..] and added in
+ * fixed order by a second kernel, so `out` must hold qm_vdot_out_doubles() doubles. */
+int qm_vdot_out_doubles(void);
+int qm_vdot(const void* a, const void* b, long long n, void* out /* double[qm_vdot_out_doubles()] */, void* stream);
 int qm_div_sqrt(void* x, long long n, const void* nrm2 /* double[1] */, void* stream);
 
 /* ---- dense statevector path (optimisation sweeps) -------------------------------- */
@@ -148,6 +151,10 @@ int qm_sweeps_small(const void* targets, int n_sites, void* gates, const int* si
 
 /* Library identification: returns the compiled architecture number (100 for sm_100a). */
 int qm_version(void);
+
+/* Programmatic dependent launch of the dependent kernel chains (default on; env QM_PDL=0 turns it off).
+ * Returns the previous setting. */
+int qm_set_pdl(int on);
 
 /* Kernel launches issued by this library since load (every launch is counted). */
 long long qm_launch_count(void);

@@ -505,7 +505,20 @@ def prepare(psi, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 - 1e-6,
     rec.setdefault("chi2", [])
 
     A = compress_right(from_dense(psi, N, rec["tt_svd"]), max_bond=chi, spectra=rec["truncate"])
-    target = to_dense(A)
+    return prepare_mps(A, num_layers, num_sweeps, threshold, gauge, rec)
+
+
+def prepare_mps(A, num_layers=1, num_sweeps=0, threshold=1 - 1e-6, gauge="canonical", record=None):
+    """Restatement of ``Sequential.prepare_mps`` (sequential.py:588-600 -> :543-586) for an MPS given as
+    site tensors (l, 2, r) in ANY gauge; same result dict as :func:`prepare`."""
+    if not isinstance(num_layers, int) or num_layers < 1:
+        raise ValueError("The number of layers must be a positive integer.")
+    rec = record if record is not None else {}
+    rec.setdefault("gate_split", [])
+    rec.setdefault("chi2", [])
+    A = [np.asarray(a, dtype=np.complex128) for a in A]
+    N = len(A)
+    target = to_dense(A)                                               # sequential.py:440 (mps.mps, not normalised)
 
     # sequential.py:360-376
     B = [a.copy() for a in A]

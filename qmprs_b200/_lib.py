@@ -38,6 +38,7 @@ SIGNATURES = {
     "qm_complete_unitaries": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _vp]),
     "qm_reverse3": (_i, [_vp, _vp, _i, _i, _vp]),
     "qm_conj_scale_copy": (_i, [_vp, _vp, _ll, _i, _d, _vp]),
+    "qm_vdot_out_doubles": (_i, []),
     "qm_vdot": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "qm_div_sqrt": (_i, [_vp, _ll, _vp, _vp]),
     "qm_apply_gate": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
@@ -48,6 +49,7 @@ SIGNATURES = {
     "qm_sweep_stored": (_i, [_vp, _vp, _i, _vp, _ip, _ip, _i, _vp, _vp, _vp, _vp]),
     "qm_sweeps_small": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "qm_version": (_i, []),
+    "qm_set_pdl": (_i, [_i]),
     "qm_launch_count": (_ll, []),
     "qm_prof_num_classes": (_i, []),
     "qm_prof_class_name": (ctypes.c_char_p, [_i]),

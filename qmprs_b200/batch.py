@@ -3,7 +3,7 @@
 BASELINE.json config 5 / SURVEY.md section 8(e): state s goes to rank ``s mod world``;
 there is no communication while the states are compiled (each rank runs the single-state
 path on its own B200), and one final all-gather of fixed-size records
-``{gates[L][N][16], kinds[L][N], n_layers, fidelity}`` over NCCL (NVLink/NVSwitch) -- about
+``{gates[L][N][16], kinds[L][N], n_layers, overlap}`` over NCCL (NVLink/NVSwitch) -- about
 29 KB per 12-qubit / 10-layer state.  One process per GPU (torchrun); without an initialised
 process group the whole batch runs on the local device.
 """
@@ -20,17 +20,22 @@ def shard_indices(n_states: int, rank: int, world: int) -> list[int]:
 
 
 def record_len(n_sites: int, num_layers: int) -> int:
-    return num_layers * n_sites * 32 + num_layers * n_sites + 2
+    """doubles per record: gates (re, im interleaved), kinds, n_layers, overlap (re, im)."""
+    return num_layers * n_sites * 32 + num_layers * n_sites + 3
 
 
 def pack_record(res: dict, n_sites: int, num_layers: int) -> np.ndarray:
-    """float64 vector: gates (re,im interleaved, zero padded to num_layers), kinds, n_layers, fidelity."""
+    """float64 vector: gates (re,im interleaved, zero padded to num_layers), kinds, n_layers,
+    <psi|circuit> as (re, im) -- the fidelity is its modulus."""
     L = res["n_layers"]
     g = np.zeros((num_layers, n_sites, 16), dtype=np.complex128)
     k = np.zeros((num_layers, n_sites), dtype=np.float64)
     g[:L] = res["gates"]
     k[:L] = np.asarray(res["kinds"], dtype=np.float64)
-    return np.concatenate([g.view(np.float64).reshape(-1), k.reshape(-1), [float(L), float(res["fidelity"])]])
+    ov = res.get("overlap")
+    if ov is None:
+        ov = (float(res["fidelity"]), 0.0)
+    return np.concatenate([g.view(np.float64).reshape(-1), k.reshape(-1), [float(L), float(ov[0]), float(ov[1])]])
 
 
 def unpack_record(vec: np.ndarray, n_sites: int, num_layers: int) -> dict:
@@ -39,18 +44,28 @@ def unpack_record(vec: np.ndarray, n_sites: int, num_layers: int) -> dict:
     L = int(round(vec[ng + nk]))
     g = vec[:ng].view(np.complex128).reshape(num_layers, n_sites, 16)[:L].copy()
     k = vec[ng:ng + nk].reshape(num_layers, n_sites)[:L].astype(np.int32)
-    return {"gates": g, "kinds": [list(map(int, row)) for row in k], "n_layers": L, "fidelity": float(vec[ng + nk + 1])}
+    ov = (float(vec[ng + nk + 1]), float(vec[ng + nk + 2]))
+    return {"gates": g, "kinds": [list(map(int, row)) for row in k], "n_layers": L, "overlap": ov,
+            "fidelity": float(np.hypot(ov[0], ov[1]))}
 
 
 def prepare_state_batch(states, bond_dimension: int, num_layers: int = 1, num_sweeps: int = 0,
                         threshold: float = 1 - 1e-6, kernels=None, gather: bool = True, graph_lanes: int = 0,
-                        preparer=None):
-    """Compile every row of ``states`` (B x 2^n) and return the list of B result records
-    (on every rank when ``gather``).  ``kernels``: kernel handle (default: CUDA on the
-    local rank's device)."""
+                        preparer=None, return_device: bool = False):
+    """Compile every row of ``states`` (B x 2^n; a numpy array, or a tensor already resident on this rank's
+    GPU) and return the list of B result records (on every rank when ``gather``).  ``kernels``: kernel
+    handle (default: CUDA on the local rank's device).
+
+    Data path: the rank's shard of the states goes to HBM in one copy; with a ``preparer`` (captured CUDA
+    graphs, graphs.py) every state is one graph replay whose gate record is written into the rank's device
+    record block -- no host round trip per state; one ``all_gather_into_tensor`` of the fixed-size record
+    blocks over NCCL; one device->host copy of the gathered records.  ``return_device`` skips that last copy
+    and returns the gathered (world * per_rank, record_len) float64 tensor (rank-major, see shard_indices)."""
     import torch.distributed as dist
 
-    states = np.asarray(states, dtype=np.complex128)
+    on_device = hasattr(states, "data_ptr")
+    if not on_device:
+        states = np.asarray(states, dtype=np.complex128)
     B, dim = states.shape
     n = int(round(np.log2(dim)))
     if 2 ** n != dim:
@@ -62,35 +77,39 @@ def prepare_state_batch(states, bond_dimension: int, num_layers: int = 1, num_sw
     world = dist.get_world_size() if distributed else 1
     if kernels is None:
         from qmprs_b200.kernels import get_kernels
-        dev = f"cuda:{rank % max(torch.cuda.device_count(), 1)}"
-        kernels = get_kernels(dev)
+        kernels = get_kernels()
     K = kernels
     mine = shard_indices(B, rank, world)
     rl = record_len(n, num_layers)
     per_rank = (B + world - 1) // world
-    local = np.zeros((per_rank, rl), dtype=np.float64)
     if graph_lanes or preparer is not None:
         # small states: captured CUDA graphs replayed per state on several concurrent lanes (graphs.py)
         if preparer is None:
             from qmprs_b200.graphs import GraphedPreparer
             preparer = GraphedPreparer(n, bond_dimension, num_layers, num_sweeps, threshold, lanes=graph_lanes,
                                        device=str(K.device))
-        for slot, res in enumerate(preparer.run(states[mine])):
-            local[slot] = pack_record(res, n, num_layers)
+        local = torch.zeros((per_rank, rl), dtype=torch.float64, device=K.device)
+        preparer.run_into(states[rank::world] if world > 1 else states, local)
     else:
+        local_h = np.zeros((per_rank, rl), dtype=np.float64)
         for slot, s in enumerate(mine):
             res = host.prepare(K, states[s], n, bond_dimension, num_layers, num_sweeps, threshold)
-            local[slot] = pack_record(res, n, num_layers)
-    if not (distributed and gather) or world == 1:
-        return [unpack_record(local[slot], n, num_layers) for slot in range(len(mine))] if world == 1 else \
-               {s: unpack_record(local[slot], n, num_layers) for slot, s in enumerate(mine)}
-    # one collective: all-gather of the fixed-size record blocks
-    send = torch.from_numpy(local).to(K.device)
-    recv = torch.empty((world, per_rank, rl), dtype=torch.float64, device=K.device)
-    dist.all_gather_into_tensor(recv.view(world * per_rank, rl), send)
+            local_h[slot] = pack_record(res, n, num_layers)
+        local = torch.from_numpy(local_h).to(K.device)
+    if distributed and gather and world > 1:
+        # the one collective of the path: all-gather of the fixed-size record blocks
+        recv = torch.empty((world * per_rank, rl), dtype=torch.float64, device=K.device)
+        dist.all_gather_into_tensor(recv, local)
+    else:
+        recv = local
+    if return_device:
+        return recv
     allrec = recv.cpu().numpy()
+    if not (distributed and gather) or world == 1:
+        return [unpack_record(allrec[slot], n, num_layers) for slot in range(len(mine))] if world == 1 else \
+               {s: unpack_record(allrec[slot], n, num_layers) for slot, s in enumerate(mine)}
     out = [None] * B
     for r in range(world):
         for slot, s in enumerate(shard_indices(B, r, world)):
-            out[s] = unpack_record(allrec[r, slot], n, num_layers)
+            out[s] = unpack_record(allrec[r * per_rank + slot], n, num_layers)
     return out

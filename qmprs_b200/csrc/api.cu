@@ -49,9 +49,16 @@ bool qm_prof_active() { return g_enabled; }
 
 // QM_PDL=0 turns programmatic dependent launch off (A/B runs); never used under the event profiler
 // (events between launches serialise them anyway and the classes are timed in isolation there).
+static int g_pdl = -1;
 bool qm_pdl_enabled() {
-    static const bool on = !(getenv("QM_PDL") && atoi(getenv("QM_PDL")) == 0);
-    return on && !g_enabled;
+    if (g_pdl < 0) g_pdl = !(getenv("QM_PDL") && atoi(getenv("QM_PDL")) == 0);
+    return g_pdl && !g_enabled;
+}
+// run-time switch (tests run the same problem with and without programmatic dependent launch); returns the old value
+extern "C" int qm_set_pdl(int on) {
+    int old = g_pdl < 0 ? !(getenv("QM_PDL") && atoi(getenv("QM_PDL")) == 0) : g_pdl;
+    g_pdl = on ? 1 : 0;
+    return old;
 }
 
 extern "C" int qm_version(void) { return 100; }

@@ -325,8 +325,11 @@ __global__ void k_conj_scale_copy(cplx* __restrict__ out, const cplx* __restrict
     }
 }
 
-// out[0] += sum conj(a_i) b_i   (out must be zeroed by the caller); a == b gives the squared norm
-__global__ void k_vdot(const cplx* __restrict__ a, const cplx* __restrict__ b, long long n, double* __restrict__ out) {
+// sum conj(a_i) b_i, reproducible: every CTA writes its own partial (re, im) and a second single-CTA kernel adds
+// the partials in fixed order (no floating-point atomics: the norm of psi is the first number of every run and a
+// last-bit difference is amplified by the chi=2 truncations).  gridDim.x == 1 writes the result directly.
+__global__ void __launch_bounds__(256)
+k_vdot_partial(const cplx* __restrict__ a, const cplx* __restrict__ b, long long n, double* __restrict__ out) {
     __shared__ double red[33];
     cplx acc = mk(0.0, 0.0);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -334,7 +337,19 @@ __global__ void k_vdot(const cplx* __restrict__ a, const cplx* __restrict__ b, l
         ccfma(acc, a[i], b[i]);
     double re = block_sum(acc.x, red);
     double im = block_sum(acc.y, red);
-    if (threadIdx.x == 0) { atomicAdd(&out[0], re); atomicAdd(&out[1], im); }
+    if (threadIdx.x == 0) {
+        double* dst = (gridDim.x == 1) ? out : out + 2 + 2 * (long long)blockIdx.x;
+        dst[0] = re; dst[1] = im;
+    }
+}
+__global__ void __launch_bounds__(256)
+k_vdot_final(double* __restrict__ out, int nparts) {
+    __shared__ double red[33];
+    double re = 0.0, im = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) { re += out[2 + 2 * i]; im += out[3 + 2 * i]; }
+    re = block_sum(re, red);
+    im = block_sum(im, red);
+    if (threadIdx.x == 0) { out[0] = re; out[1] = im; }
 }
 
 // x <- x / sqrt(nrm2[0])
@@ -460,9 +475,16 @@ extern "C" int qm_conj_scale_copy(void* out, const void* in, long long n, int co
     return 0;
 }
 
-extern "C" int qm_vdot(const void* a, const void* b, long long n, void* out2, void* stream) {
-    QM_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), (cudaStream_t)stream));
-    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_vdot<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const cplx*)a, (const cplx*)b, n, (double*)out2));
+constexpr int VDOT_MAXG = 296;      // two CTAs per SM
+extern "C" int qm_vdot_out_doubles(void) { return 2 + 2 * VDOT_MAXG; }
+
+extern "C" int qm_vdot(const void* a, const void* b, long long n, void* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    long long g = (n + 2047) / 2048;             // >= 8 amplitudes per thread before a second CTA is worth it
+    if (g > VDOT_MAXG) g = VDOT_MAXG;
+    if (g < 1) g = 1;
+    QM_LAUNCH(QM_CLS_SMALL, st, k_vdot_partial<<<(int)g, 256, 0, st>>>((const cplx*)a, (const cplx*)b, n, (double*)out));
+    if (g > 1) QM_LAUNCH(QM_CLS_SMALL, st, k_vdot_final<<<1, 256, 0, st>>>((double*)out, (int)g));
     QM_CHECK_LAUNCH();
     return 0;
 }

@@ -110,6 +110,58 @@ class GraphedPreparer:
             self.fallbacks += 1
         out[tag] = res
 
+    def run_into(self, states, rec_dev):
+        """Batch form without a host round trip per state.  ``states``: (B, 2^n) numpy array (one pinned
+        host->device copy) or a tensor already on the device; ``rec_dev``: (>= B, record_len) float64 device
+        tensor that receives one record per state (layout of :func:`qmprs_b200.batch.pack_record`).
+        Every state is: device copy into the lane's input, graph replay, three small device copies
+        (gates, overlap, validity flag) -- all on the lane's stream.  The flags are read once at the end;
+        flagged states (a static assumption failed) are re-run through the eager path and their records
+        overwritten.  Returns the number of eager fallbacks of this call."""
+        from qmprs_b200 import batch as qb
+        n, chi, L, S, thr = self.cfg
+        dev = torch.device(self.device)
+        B = int(states.shape[0])
+        if B == 0:
+            return 0
+        main = torch.cuda.current_stream(dev)
+        host_states = None
+        if hasattr(states, "data_ptr") and states.is_cuda:
+            sdev = states
+        else:
+            host_states = np.ascontiguousarray(np.asarray(states, dtype=np.complex128))
+            sdev = torch.from_numpy(host_states).pin_memory().to(dev, non_blocking=True)
+        ng, nk = L * n * 32, L * n
+        # constant part of the records of the static pipeline: one block per layer, all layers used
+        tmpl = np.concatenate([np.tile(np.array([2.0] * (n - 1) + [1.0]), L), [float(L)]])
+        rec_dev[:B, ng:ng + nk + 1] = torch.from_numpy(tmpl).to(dev)
+        flags = torch.zeros(B, dtype=torch.int32, device=dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        nl = len(self.lanes)
+        for lane in self.lanes[:min(nl, B)]:
+            lane.stream.wait_event(ready)
+        for s in range(B):
+            lane = self.lanes[s % nl]
+            with torch.cuda.stream(lane.stream):
+                lane.psi_in.copy_(sdev[s], non_blocking=True)
+                lane.mismatch.zero_()
+                lane.graph.replay()
+                rec_dev[s, :ng].copy_(lane.gates.view(torch.float64).reshape(-1), non_blocking=True)
+                rec_dev[s, ng + nk + 1:ng + nk + 3].copy_(lane.ov, non_blocking=True)
+                flags[s:s + 1].copy_(lane.mismatch, non_blocking=True)
+        self.replays += B
+        for lane in self.lanes[:min(nl, B)]:
+            lane.done.record(lane.stream)
+            main.wait_event(lane.done)
+        bad = np.nonzero(flags.cpu().numpy())[0]
+        for s in bad:                                      # an assumption failed: eager path, exact semantics
+            st = host_states[s] if host_states is not None else sdev[s]
+            res = host.prepare(self.eager, st, n, chi, L, S, thr, split=self.split)
+            rec_dev[s].copy_(torch.from_numpy(qb.pack_record(res, n, L)).to(dev))
+        self.fallbacks += len(bad)
+        return len(bad)
+
     def run(self, states):
         """Round-robin the states over the lanes.  (Driving the lanes from several host threads was
         measured: no gain -- the bound was the number of hardware work queues, not the host.)"""

@@ -345,17 +345,25 @@ def build_mps(K, psi, n_sites, chi, record=None, fused=True):
     return canonicalize_truncate(K, A, chi, rec.setdefault("truncate", []))
 
 
-def disentangle(K, A, num_layers, threshold, record=None, split="svd"):
+def disentangle(K, A, num_layers, threshold, record=None, split="svd", preconditioned=True):
     """``_get_unitary_layers`` (sequential.py:330-398).  Returns (gates_all [L*N,16] in
-    application order, kinds_per_layer, overlaps)."""
+    application order, kinds_per_layer, overlaps).
+
+    ``preconditioned``: ``A`` is right-canonical with the 1e-10 'rel' cutoff already applied to every
+    bond (what :func:`build_mps` / ``MPS.compress`` return).  Only then is the reference's
+    pre-conditioning (sequential.py:360-376: copy, normalize, compress(mode="right"), permute,
+    canonicalize("right", normalize=True)) the same tensors with site 0 divided by its norm (the gauge
+    is unique up to bond phases).  For any other input -- left-canonical, mixed after
+    ``apply_unitary_layer``, built from raw arrays -- the QR sweep + cutoff-only SVD sweep are run:
+    they return the right-canonical form with the STATE norm on site 0, which is then normalised."""
     import torch
     rec = record if record is not None else {}
     N = len(A)
-    # sequential.py:360-376: copy, normalize, compress(mode="right"), permute, canonicalize.
-    # On the right-canonical Schmidt-gauge MPS built above this is the same tensors with
-    # site 0 normalised (the gauge is unique up to bond phases).
-    B = copy_mps(K, A)
-    normalize_site0(K, B)
+    if preconditioned:
+        B = copy_mps(K, A)
+    else:
+        B = canonicalize_truncate(K, A)                               # mps.py:451: left_canonize + right_compress
+    normalize_site0(K, B)                                             # mps.py:302-310, :398
     layer_gates, layer_kinds, overlaps = [], [], []
     for _ in range(num_layers):
         gates, kinds = chi2_layer(K, B)                               # mps.py:849-891
@@ -393,9 +401,11 @@ def prepare_device(K, psi, n_sites, chi, num_layers, num_sweeps, threshold=1 - 1
 
 
 def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 - 1e-6, record=None,
-            mps=None, fused=True, split="svd"):
+            mps=None, fused=True, split="svd", mps_preconditioned=False):
     """Whole path on the device.  ``psi_host``: complex128 numpy vector or device tensor.
-    Returns dict(gates [L,N,16] numpy, kinds [L][N], n_layers, overlaps, fidelity)."""
+    Returns dict(gates [L,N,16] numpy, kinds [L][N], n_layers, overlaps, fidelity).
+    ``mps``: start from these site tensors instead of building them (``prepare_mps``); any gauge unless
+    ``mps_preconditioned`` says they come from :func:`build_mps`."""
     N = int(n_sites)
     if hasattr(psi_host, "data_ptr"):                 # already a device tensor (bench: inputs resident in HBM)
         psi = K.scale_copy(psi_host.reshape(-1, 1)).reshape(-1)
@@ -406,7 +416,8 @@ def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 -
                                                                   threshold, record, fused, split)
     else:
         A = mps
-        gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record, split)
+        gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record, split,
+                                                       preconditioned=mps_preconditioned)
         if num_sweeps > 0:
             optimize_layers(K, to_dense(K, A), gates_all, layer_kinds, N, num_sweeps)
         sites, kinds = flat_schedule(layer_kinds, N)
@@ -419,6 +430,7 @@ def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 -
         "n_layers": L,
         "overlaps": overlaps,
         "fidelity": float(np.hypot(ov[0], ov[1])),
+        "overlap": (float(ov[0]), float(ov[1])),
         "n_sites": N,
         "mps": A,
     }

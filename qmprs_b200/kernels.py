@@ -28,19 +28,34 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+_process_device = None      # the library keeps per-process state (opt-in smem sizes, side streams, split-K workspace)
+
+
 class CudaKernels:
-    """One instance per device.  Methods take/return torch tensors on that device."""
+    """Kernel handle.  One DEVICE per process (one process per GPU under torchrun): the library's
+    function attributes, side streams and split-K workspaces are created once per process on the first
+    device used, so a handle for a second device in the same process is refused instead of failing at
+    launch time.  Methods take/return torch tensors on that device."""
 
     def __init__(self, device="cuda:0"):
+        global _process_device
         if not torch.cuda.is_available():
             raise RuntimeError("qmprs_b200 requires a CUDA device (B200, sm_100a); there is no CPU fallback.")
         self.lib = _lib.load()
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if _process_device is None:
+            _process_device = self.device
+        elif _process_device != self.device:
+            raise RuntimeError(f"qmprs_b200 drives one GPU per process: this process already uses {_process_device}, "
+                               f"refusing {self.device} (launch one process per GPU, e.g. torchrun)")
         torch.cuda.set_device(self.device)
         self._svd_work = None
         self._sweep_work = None
         self.launches = 0          # C-ABI calls issued (each launches >= 1 kernel)
         self.svd_sweeps = 0
+        self.svd_unconverged = 0
         self.svd_tol = 1e-14
         self.svd_max_sweeps = 30
         # speculative static-shape mode (graphs.py): no host read-backs; assumptions are validated on
@@ -181,6 +196,12 @@ class CudaKernels:
                                     self._svd_work.numel(), self.svd_tol, self.svd_max_sweeps, info,
                                     self._stream()), "qm_svd")
         self.svd_sweeps += info[0]
+        if not info[1]:
+            # a partially converged decomposition would silently drive rank cut-offs and gates
+            import warnings
+            self.svd_unconverged += 1
+            warnings.warn(f"qm_svd({m}x{n}) did not converge to tol={self.svd_tol} in {self.svd_max_sweeps} sweeps",
+                          RuntimeWarning, stacklevel=2)
         return U, S, Vh
 
     def transpose(self, A, conj=False):
@@ -259,9 +280,10 @@ class CudaKernels:
         return out
 
     def vdot(self, a, b):
-        out = self.empty((2,), F64)
+        """(re, im) of sum conj(a) b; reproducible (per-CTA partials live behind the result, fixed-order sum)."""
+        out = self.empty((int(self.lib.qm_vdot_out_doubles()),), F64)
         self._check(self.lib.qm_vdot(_p(a), _p(b), a.numel(), _p(out), self._stream()), "qm_vdot")
-        return out
+        return out[:2]
 
     def div_sqrt(self, x, nrm2):
         self._check(self.lib.qm_div_sqrt(_p(x), x.numel(), _p(nrm2), self._stream()), "qm_div_sqrt")
@@ -326,6 +348,10 @@ class CudaKernels:
     def launch_count(self):
         """Kernel launches issued by the library since load (counted in QM_LAUNCH)."""
         return int(self.lib.qm_launch_count())
+
+    def set_pdl(self, on):
+        """Programmatic dependent launch on/off; returns the previous setting."""
+        return bool(self.lib.qm_set_pdl(1 if on else 0))
 
     def prof_begin(self):
         self.lib.qm_prof_begin()

@@ -35,12 +35,16 @@ UnitaryLayer = list   # [UnitaryBlock]
 class DeviceMPS:
     """List of site tensors ``(l, 2, r)`` on the GPU (stand-in for quimb's
     ``MatrixProductState``).  ``form`` tracks the orthogonality centre:
-    "right" (centre on site 0), "left" (centre on site N-1) or None."""
+    "right" (centre on site 0), "left" (centre on site N-1) or None.  ``trimmed``: every bond
+    already went through the 1e-10 'rel' cutoff of ``compress`` in this gauge (set by
+    ``MPS.from_statevector`` / ``MPS.compress``); only a right-canonical trimmed MPS lets the
+    encoder skip the reference's pre-conditioning sweeps (sequential.py:360-376)."""
 
-    def __init__(self, tensors, K, form=None):
+    def __init__(self, tensors, K, form=None, trimmed=False):
         self.tensors = list(tensors)
         self.K = K
         self.form = form
+        self.trimmed = bool(trimmed)
 
     @property
     def num_tensors(self) -> int:
@@ -62,7 +66,7 @@ class DeviceMPS:
         return tuple(self.K.to_host(t) for t in self.tensors)
 
     def copy(self) -> "DeviceMPS":
-        return DeviceMPS(host.copy_mps(self.K, self.tensors), self.K, self.form)
+        return DeviceMPS(host.copy_mps(self.K, self.tensors), self.K, self.form, self.trimmed)
 
     def to_dense(self) -> np.ndarray:
         return self.K.to_host(host.to_dense(self.K, self.tensors))
@@ -142,7 +146,7 @@ class MPS:
         K = _default_kernels()
         psi = K.from_host(np.asarray(statevector.data, dtype=np.complex128).reshape(-1))
         A = host.build_mps(K, psi, statevector.num_qubits, max_bond_dimension, record)
-        return DeviceMPS(A, K, form="right")
+        return DeviceMPS(A, K, form="right", trimmed=True)
 
     @staticmethod
     def to_statevector(mps: DeviceMPS) -> Ket:
@@ -210,10 +214,10 @@ class MPS:
         if not (max_bond_dimension or mode):
             # quimb's default form; the state is identical, only the placement of the
             # singular values differs -- kept right-canonical here.
-            self.mps = DeviceMPS(host.canonicalize_truncate(K, self.mps.tensors), K, form="right")
+            self.mps = DeviceMPS(host.canonicalize_truncate(K, self.mps.tensors), K, form="right", trimmed=True)
         elif not mode and max_bond_dimension:
             self.mps = DeviceMPS(host.canonicalize_truncate(K, self.mps.tensors, max_bond_dimension), K,
-                                 form="right")
+                                 form="right", trimmed=True)
             self.bond_dimension = max_bond_dimension
         else:
             if mode in ["left", "right"]:
@@ -222,7 +226,7 @@ class MPS:
                 else:
                     A = host.mirror(K, host.canonicalize_truncate(K, host.mirror(K, self.mps.tensors),
                                                                   max_bond_dimension))
-                self.mps = DeviceMPS(A, K, form=mode)
+                self.mps = DeviceMPS(A, K, form=mode, trimmed=True)
                 if max_bond_dimension:
                     self.bond_dimension = max_bond_dimension
             else:
@@ -293,6 +297,7 @@ class MPS:
         gates, kinds = self._layer_to_device(unitary_layer)
         host.apply_inverse_layer(K, self.mps.tensors, gates, kinds, inverse=inverse)
         self.mps.form = None
+        self.mps.trimmed = False
 
     def apply_unitary_layers(self, unitary_layers: list, inverse: bool = False) -> None:
         """mps.py:997-1018 (layers are visited in reverse order in both directions)."""
@@ -314,6 +319,9 @@ class MPS:
         return self.num_sites
 
     def __eq__(self, other) -> bool:
-        if not isinstance(other, MPS) or other.num_sites != self.num_sites:
+        """mps.py:1117-1138: TypeError for a non-MPS operand; equal when both describe the same state."""
+        if not isinstance(other, MPS):
+            raise TypeError("`value` must be an instance of `qmprs.primitives.MPS`.")
+        if other.num_sites != self.num_sites:
             return False
         return bool(np.allclose(self.mps.to_dense(), other.mps.to_dense()))

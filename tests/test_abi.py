@@ -39,3 +39,13 @@ def test_sass_uses_fp64_tensor_pipe():
     out = subprocess.run(["cuobjdump", "-sass", build.OUT], capture_output=True, text=True).stdout
     assert out.count("DMMA") > 100          # zgemm + SVD gram/apply kernels
     assert "sm_100a" in out or "SM100" in out.upper() or "EF_CUDA_SM100" in out
+
+
+def test_sass_has_no_floating_point_atomics():
+    """Run-to-run reproducibility: no kernel may accumulate with floating-point
+    atomics -- integer tickets / flags (order independent) are the only RED/ATOM instructions allowed."""
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-sass", build.OUT], capture_output=True, text=True).stdout
+    bad = [ln.strip() for ln in out.splitlines()
+           if re.search(r"\b(RED|REDG|ATOM|ATOMG|ATOMS)\b", ln) and re.search(r"\.(F64|F32|F16)", ln)]
+    assert not bad, bad[:5]

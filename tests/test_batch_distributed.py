@@ -18,11 +18,11 @@ def test_shard_and_record_roundtrip():
     assert batch.shard_indices(7, 1, 3) == [1, 4]
     assert sorted(sum((batch.shard_indices(10, r, 4) for r in range(4)), [])) == list(range(10))
     res = {"gates": np.arange(2 * 3 * 16).reshape(2, 3, 16) * (1 + 2j), "kinds": [[2, 2, 1], [2, 1, 1]],
-           "n_layers": 2, "fidelity": 0.75}
+           "n_layers": 2, "fidelity": 1.25, "overlap": (0.75, -1.0)}
     vec = batch.pack_record(res, 3, 4)
     assert vec.shape == (batch.record_len(3, 4),)
     back = batch.unpack_record(vec, 3, 4)
-    assert back["n_layers"] == 2 and back["kinds"] == res["kinds"] and back["fidelity"] == 0.75
+    assert back["n_layers"] == 2 and back["kinds"] == res["kinds"] and back["fidelity"] == 1.25 and back["overlap"] == (0.75, -1.0)
     assert np.array_equal(back["gates"], res["gates"])
 
 

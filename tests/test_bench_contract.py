@@ -35,3 +35,20 @@ def test_reference_arm_other_ranks_do_nothing():
     res = run({"RANK": "1", "WORLD_SIZE": "2"})
     assert res.returncode == 0, res.stderr
     assert not [l for l in res.stdout.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_batch_workload_at_n_gt_1():
+    """--gpus N > 1 selects the sharded batch workload (config 5); its CPU arm runs one oracle process per
+    host core on rank 0."""
+    env = dict(os.environ)
+    env.update({"RANK": "0", "WORLD_SIZE": "2"})
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, env=env, timeout=900)
+    assert res.returncode == 0, res.stderr
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["scaling"] == "strong" and d["config"]["batch"] == 4096
+    assert d["config"]["n_qubits"] == 12 and d["config"]["layers"] == 10 and d["config"]["sweeps"] == 20
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -54,8 +54,9 @@ def test_sequential_switches_to_graph_on_repeat(K):
     from qmprs.synthesis.mps_encoding import Sequential
     from qmprs_b200 import GateListCircuit
     enc = Sequential(GateListCircuit)
+    assert enc.use_cuda_graphs is False                  # opt-in (the replayed pipeline is not bit-identical to eager)
+    enc.use_cuda_graphs = "auto"
     eager = Sequential(GateListCircuit)
-    eager.use_cuda_graphs = False
     for s in range(3):
         psi = O.random_state(8, 300 + s)
         c1 = enc.prepare_state(psi, 32, num_layers=3, num_sweeps=2)

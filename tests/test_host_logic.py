@@ -92,3 +92,42 @@ def test_exact_split_gives_the_same_circuit(n, chi, L, S):
     assert a["n_layers"] == b["n_layers"] and a["kinds"] == b["kinds"]
     assert np.abs(a["gates"] - b["gates"]).max() < 1e-7
     assert abs(a["fidelity"] - b["fidelity"]) < 1e-10
+
+
+def _gauge_scrambled(A, seed, scale=1.0):
+    """Same state (times ``scale``), random invertible matrices inserted on every bond."""
+    rng = np.random.default_rng(seed)
+    B = [a.copy() for a in A]
+    for i in range(len(B) - 1):
+        r = B[i].shape[2]
+        X = np.eye(r) + 0.3 * (rng.standard_normal((r, r)) + 1j * rng.standard_normal((r, r)))
+        B[i] = np.einsum("lpr,rs->lps", B[i], X)
+        B[i + 1] = np.einsum("sr,rpk->spk", np.linalg.inv(X), B[i + 1])
+    B[len(B) // 2] = B[len(B) // 2] * scale
+    return B
+
+
+@pytest.mark.parametrize("kind", ["left", "scrambled", "scaled"])
+def test_prepare_mps_any_gauge_matches_reference_preconditioning(kind):
+    """sequential.py:360-376: normalize + compress('right') + canonicalize('right', normalize=True) on
+    whatever gauge the caller's MPS is in.  The early-break overlaps (hence layer count and depth) and the
+    gates must not depend on the input gauge (a left-canonical input gave overlaps off by 1/sqrt 2)."""
+    n, chi, L, S = 7, 8, 4, 1
+    psi = O.random_state(n, 21)
+    A0 = O.compress_right(O.from_dense(psi, n), max_bond=chi)
+    if kind == "left":
+        A = O.left_canon([a.copy() for a in A0])
+    elif kind == "scrambled":
+        A = _gauge_scrambled(A0, 3)
+    else:
+        A = _gauge_scrambled(A0, 4, scale=2.5)            # not normalised either
+    ref = O.prepare_mps(A, L, S, gauge="canonical")
+    base = O.prepare_mps(A0, L, S, gauge="canonical")
+    K = FakeKernels(svd_phase_seed=5)
+    out = host.prepare(K, psi, n, chi, L, S, mps=[K.from_host(a) for a in A])
+    assert out["n_layers"] == ref["n_layers"] == base["n_layers"]
+    assert np.abs(np.array(out["overlaps"]) - np.array(ref["overlaps"])).max() < 1e-10
+    assert np.abs(np.array(out["overlaps"]) - np.array(base["overlaps"])).max() < 1e-10
+    g = out["gates"].reshape(-1, 16)
+    for idx, (_, _, _, site, G) in enumerate(gate_table(ref)):
+        assert np.abs(g[idx][: G.size] - G.reshape(-1)).max() < 1e-7

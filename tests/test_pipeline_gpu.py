@@ -32,6 +32,8 @@ def run_both(K, n, chi, L, S, seed=0, psi=None, fused=False):
 def test_layers_no_sweeps(K, n, chi, L):
     psi, ro, rd, rec_o, rec_d = run_both(K, n, chi, L, 0)
     assert rd["n_layers"] == ro["n_layers"]
+    # A7 (mps.py:1020-1039): the early-break overlaps <0..0|psi_k> after every layer, numerically
+    assert np.abs(np.array(rd["overlaps"]) - np.array(ro["overlaps"])).max() <= 1e-10
     flat = O.flatten_layers(ro["layers"])
     g = rd["gates"].reshape(-1, 16)
     kinds = [k for kl in rd["kinds"] for k in kl]
@@ -60,7 +62,8 @@ def test_layers_no_sweeps(K, n, chi, L):
         assert np.abs(sd - so).max() <= 1e-10 * so[0]
 
 
-@pytest.mark.parametrize("n,chi,L,S", [(4, 4, 1, 1), (6, 64, 3, 4), (8, 32, 6, 5), (10, 512, 15, 10)])
+@pytest.mark.parametrize("n,chi,L,S", [(4, 4, 1, 1), (6, 64, 3, 4), (8, 32, 6, 5), (10, 512, 15, 10),
+                                       (10, 512, 15, 50)])      # last: BASELINE config 1 (README) at full size
 def test_with_sweeps(K, n, chi, L, S):
     psi, ro, rd, _, _ = run_both(K, n, chi, L, S)
     assert rd["n_layers"] == ro["n_layers"]
@@ -185,12 +188,21 @@ def test_exact_split_matches_svd_split(K, n, chi, L, S):
     assert abs(a["fidelity"] - b["fidelity"]) <= 1e-9
 
 
-def test_repeat_runs_are_bit_identical(K):
-    """No floating-point atomics on the path: the same input gives the same gate records bit for bit
-    (single-block and multi-block SVD paths, dense sweeps in shared memory and in HBM)."""
-    for n, chi, L, S in [(10, 32, 4, 3), (13, 64, 3, 2)]:
-        psi = O.random_state(n, 77)
-        a = host.prepare(K, psi, n, chi, L, S)
-        b = host.prepare(K, psi, n, chi, L, S)
-        assert np.array_equal(np.asarray(a["gates"]), np.asarray(b["gates"]))
-        assert a["kinds"] == b["kinds"]
+@pytest.mark.parametrize("pdl", [True, False])
+def test_repeat_runs_are_bit_identical(K, pdl):
+    """No floating-point atomics on the path (tests/test_abi.py checks the SASS): the same input gives the
+    same gate records bit for bit, repeat after repeat, with and without programmatic dependent launch --
+    single-block and multi-block (two-stream) SVD paths, dense sweeps in shared memory and in HBM.
+    (Round 1: k_vdot summed its CTA partials with FP64 atomics; the last bit of the state norm moved from
+    run to run and the chi=2 truncations amplified it.)"""
+    old = K.set_pdl(pdl)
+    try:
+        for (n, chi, L, S), reps in [((10, 32, 4, 3), 20), ((13, 64, 3, 2), 20), ((16, 256, 3, 2), 8 if pdl else 4)]:
+            psi = O.random_state(n, 77)
+            a = host.prepare(K, psi, n, chi, L, S)
+            for _ in range(reps - 1):
+                b = host.prepare(K, psi, n, chi, L, S)
+                assert np.array_equal(np.asarray(a["gates"]), np.asarray(b["gates"]))
+                assert a["kinds"] == b["kinds"] and a["fidelity"] == b["fidelity"]
+    finally:
+        K.set_pdl(old)
