@@ -31,18 +31,25 @@ int qm_zgemm(int m, int n, int k, double alpha_re, double alpha_im, const void* 
 /* Thin SVD A = U diag(S) Vh by blocked one-sided Jacobi.  Replaces numpy/LAPACK zgesdd
  * behind quimb tensor_split: mps.py:242 (from_dense), :451-453, :928-931, :968-971;
  * sequential.py:443.  S is double[k], sorted descending, k = min(m,n).  U/Vh may be NULL.
- * info_host: host int[2] = {sweeps, converged} (may be NULL). */
+ * info_host: host int[2] = {sweeps, converged} (may be NULL).
+ * flags: QM_SVD_BACKMULT -- matrices with more than 32 short vectors only rotate W (no [W | I] extension
+ * that accumulates the rotations); the factor on the long side comes from the converged rows as before and the
+ * other one from a single ZGEMM against the input (U = A Z^H Sigma^-1 resp. Vh = Sigma^-1 U^H A): a third less
+ * tensor work per sweep on square matrices.  Column j of that factor is accurate to eps * sigma_max / sigma_j, which
+ * is what the MPS path needs (it multiplies the factor by sigma_j or sqrt(sigma_j) right away); the default (0)
+ * keeps both factors orthonormal to rounding whatever the spectrum. */
+#define QM_SVD_BACKMULT 1
 long long qm_svd_work_bytes(int m, int n);
 int qm_svd(int m, int n, const void* A, long long lda, void* U, long long ldu, void* S, void* Vh,
            long long ldvh, void* work, long long work_bytes, double tol, int max_sweeps, int* info_host,
-           void* stream);
+           int flags, void* stream);
 
 /* Sync-free SVD for CUDA-graph capture: exactly fixed_sweeps sweeps are enqueued (kernels return
  * immediately once a device-side flag says the iteration converged); mismatch[0] (int) is set to 1
  * if it had not converged, in which case the caller re-runs the problem through qm_svd. */
 int qm_svd_static(int m, int n, const void* A, long long lda, void* U, long long ldu, void* S, void* Vh,
                   long long ldvh, void* work, long long work_bytes, double tol, int fixed_sweeps, void* mismatch,
-                  void* stream);
+                  int flags, void* stream);
 
 /* out (cols x rows) = in^T (optionally conjugated): the coalesced reshape/transposed-store kernels
  * that stream the statevector in the TT-SVD (quimb from_dense reshapes, mps.py:242), exposed for
@@ -148,6 +155,17 @@ int qm_sweep_stored(const void* cs, void* tbar, int n_sites, void* gates, const 
  * [batch][n_gates][16], environments of the last sweep.  Returns -3 if the state does not fit. */
 int qm_sweeps_small(const void* targets, int n_sites, void* gates, const int* sites_dev, const int* kinds_dev,
                     int n_gates, int num_sweeps, int batch, void* envs, void* stream);
+
+/* Large registers: ALL `num_sweeps` optimisation sweeps (forward circuit states + backward environment
+ * sweep, sequential.py:509-541, :443-505) in one persistent cooperative launch, one CTA per SM and one grid
+ * barrier per gate-step; every CTA reduces the partial environments and updates the gate redundantly (bit-identical),
+ * so the new gate needs no broadcast.  cs: (n_gates+1) * 2^N amplitudes of scratch (stored circuit states); tbar:
+ * 2^N scratch; target: dense target (not conjugated); gates: [n_gates][16], updated in place; sites_dev /
+ * kinds_dev: DEVICE int[n_gates]; work: qm_sweeps_persist_work_bytes(n_gates) bytes; envs: optional
+ * [n_gates][16], environments of the last sweep.  Returns -3 if the grid cannot be co-scheduled. */
+long long qm_sweeps_persist_work_bytes(int n_gates);
+int qm_sweeps_persist(void* cs, void* tbar, const void* target, int n_sites, void* gates, const int* sites_dev,
+                      const int* kinds_dev, int n_gates, int num_sweeps, void* work, void* envs, void* stream);
 
 /* Library identification: returns the compiled architecture number (100 for sm_100a). */
 int qm_version(void);

@@ -21,8 +21,8 @@ _ip = ctypes.POINTER(ctypes.c_int)
 SIGNATURES = {
     "qm_zgemm": (_i, [_i, _i, _i, _d, _d, _vp, _ll, _vp, _ll, _d, _d, _vp, _ll, _i, _ll, _ll, _ll, _i, _vp]),
     "qm_svd_work_bytes": (_ll, [_i, _i]),
-    "qm_svd": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _d, _i, _ip, _vp]),
-    "qm_svd_static": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _d, _i, _vp, _vp]),
+    "qm_svd": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _d, _i, _ip, _i, _vp]),
+    "qm_svd_static": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _d, _i, _vp, _i, _vp]),
     "qm_expect_ints": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "qm_expect_not_close": (_i, [_vp, _d, _vp, _vp]),
     "qm_transpose": (_i, [_vp, _ll, _vp, _ll, _ll, _ll, _i, _vp]),
@@ -48,6 +48,8 @@ SIGNATURES = {
     "qm_circuit_states": (_i, [_vp, _i, _vp, _ip, _ip, _i, _vp]),
     "qm_sweep_stored": (_i, [_vp, _vp, _i, _vp, _ip, _ip, _i, _vp, _vp, _vp, _vp]),
     "qm_sweeps_small": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "qm_sweeps_persist_work_bytes": (_ll, [_i]),
+    "qm_sweeps_persist": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "qm_version": (_i, []),
     "qm_set_pdl": (_i, [_i]),
     "qm_launch_count": (_ll, []),

@@ -222,7 +222,7 @@ __device__ __forceinline__ void env_epilogue(double* acc, cplx* __restrict__ par
     __syncthreads();
     __shared__ cplx pol_scratch[32];
     if (threadIdx.x < 32) {
-        polar_conj_warp(Es, CD, gate_out, pol_scratch, vwarm);
+        polar_conj_warp(Es, CD, gate_out, pol_scratch, vwarm, vwarm);
         if (env_out && threadIdx.x < CD * CD) env_out[threadIdx.x] = Es[threadIdx.x];
         if (threadIdx.x == 0) {
             *counter = 0u;

@@ -135,7 +135,7 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
                 const double other = __shfl_xor_sync(0xffffffffu, ssum, 1);
                 if ((lane & 1) == 0 && (lane >> 1) < d * d) Es[lane >> 1] = mk(ssum, other);
                 __syncwarp();
-                polar_conj_warp(Es, d, G, pol_scratch, warm ? vw + k * 16 : nullptr);
+                polar_conj_warp(Es, d, G, pol_scratch, warm ? vw + k * 16 : nullptr, warm ? vw + k * 16 : nullptr);
                 // the rank-deficient branch of the polar returns early in 31 lanes while lane 0 finishes the
                 // single-thread completion: reconverge before the block barrier
                 __syncwarp();

@@ -133,8 +133,10 @@ __device__ __forceinline__ cplx shfl_xor_c(cplx v, int m) {
 // vwarm (optional, global, 16 cplx): right singular vectors found for this gate in the previous sweep.
 // The environments change little from sweep to sweep, so E V_prev already has nearly orthogonal
 // columns and the Jacobi iteration starts in its quadratic regime (2 sweeps instead of 5-6).
+// vwarm_out: where the vectors found now are stored (the same array in the per-gate kernels; a second buffer in the
+// persistent kernel, where every CTA reads the warm start while CTA 0 writes the new one; NULL = do not store).
 __device__ void polar_conj_warp(const cplx* Es, int d, cplx* gate_out, cplx* scratch /* smem, 32 cplx */,
-                                cplx* vwarm) {
+                                const cplx* vwarm, cplx* vwarm_out) {
     const int lane = threadIdx.x & 31;
     const int half = lane >> 4, i = (lane >> 2) & 3, j = lane & 3;
     cplx x;
@@ -203,10 +205,10 @@ __device__ void polar_conj_warp(const cplx* Es, int d, cplx* gate_out, cplx* scr
             polar_conj(E, d, P);
             for (int k = 0; k < d * d; k++) gate_out[k] = P[k];
         }
-        if (vwarm && half) vwarm[i * 4 + j] = mk(0.0, 0.0);
+        if (vwarm_out && half) vwarm_out[i * 4 + j] = mk(0.0, 0.0);
         return;
     }
-    if (vwarm && half) vwarm[i * 4 + j] = x;
+    if (vwarm_out && half) vwarm_out[i * 4 + j] = x;
     if (half == 0) x = cscale(x, 1.0 / sig);
     scratch[lane] = x;                                // [0..15] = U, [16..31] = V
     __syncwarp();

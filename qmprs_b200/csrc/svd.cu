@@ -31,11 +31,14 @@ constexpr int TC = 32;     // tile columns
 constexpr int NT = 256;
 
 struct Geom {
-    int nv, len, nvp, nbp, single, nrows, npairs, rounds;
+    int nv, len, nvp, nbp, single, nrows, npairs, rounds, ext;
     long long ldw;
 };
 
-Geom make_geom(int m, int n) {
+// ext = 1: Wext = [W | I] accumulates the rotations (both factors from the iteration).  ext = 0 (multi-block
+// only): W alone is rotated and the second factor is recovered at the end by one ZGEMM against the input
+// (QM_SVD_BACKMULT, see svd_impl): a third less tensor work per sweep on square matrices.
+Geom make_geom(int m, int n, int backmult = 0) {
     Geom g;
     g.nv = m < n ? m : n;
     g.len = m < n ? n : m;
@@ -48,7 +51,8 @@ Geom make_geom(int m, int n) {
         g.nvp = g.nbp * BSZ;
         g.nrows = PMAX; g.npairs = g.nbp / 2; g.rounds = g.nbp - 1;
     }
-    g.ldw = (long long)g.len + g.nvp;
+    g.ext = (backmult && !g.single) ? 0 : 1;
+    g.ldw = (long long)g.len + (g.ext ? g.nvp : 0);
     return g;
 }
 
@@ -404,6 +408,282 @@ k_eig(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, int nrows, d
 }
 
 // ---------------------------------------------------------------------------------
+// (2') Hermitian eigen-solve of a full 32 x 32 Gram matrix (multi-block mode), round-2 formulation.
+// Same arithmetic as k_eig (cyclic two-sided Jacobi, same rotation formula, same schedules, same convergence
+// rules); what changes is how a rotation round is laid out on the SM.  Measured on k_eig (ncu, round 1): ~2800
+// warp-instructions and ~1.5 us per round at ~1 warp-instruction per cycle -- FP64 issue bound -- with all
+// other warps waiting at a barrier while 16 threads compute the round's rotations.  Here
+//   * G is kept Hermitian by construction: only the 120 blocks above the diagonal of the 16 x 16 tiling into
+//     2 x 2 blocks are rotated (one thread each, 4 warps) and mirrored, plus the 16 diagonal blocks;
+//   * a round is ONE barrier: warp 0 rotates the diagonal blocks and the 16 blocks that hold the NEXT round's
+//     pivots, then (warp-synchronously) computes the next round's rotations from them, while four warps rotate
+//     the off-diagonal blocks and eleven warps apply the current rotations to Q;
+//   * G and the rotation table are double-buffered in shared memory (a round reads one copy and writes the
+//     other, so the pivot blocks can be rotated both by warp 0 and by their regular owner: identical values).
+// ---------------------------------------------------------------------------------
+constexpr int NTE3 = 512;
+constexpr int NOFF = (PMAX / 2) * (PMAX / 2 - 1) / 2;     // 120 blocks above the diagonal
+
+struct Eig3Smem {
+    cplx g[2][PMAX * GS];
+    cplx q[PMAX * GS];
+    double rc[2][PMAX / 2];
+    cplx ro[2][PMAX / 2];        // row p <- c x + o y ;  row q <- -conj(o) x + c y
+    int ract[2][PMAX / 2];
+    unsigned char sched[(PMAX - 1) * (PMAX / 2) * 2];     // full round-robin schedule: (p, q) per round / slot
+    unsigned char slot[(PMAX - 1) * PMAX];                // its inverse: pair slot of row i in round r
+    unsigned char blk[NOFF * 2];                          // (k, l), k < l
+    int s_off, s_mc, s_mi, s_stop, s_any;
+};
+
+// pair (p, q) of slot k in round r
+__device__ __forceinline__ void eig3_pair(const Eig3Smem& sm, bool cross, int r, int k, int& p, int& q) {
+    if (cross) { p = k; q = BSZ + ((k + r) & (BSZ - 1)); }
+    else { p = sm.sched[2 * (r * (PMAX / 2) + k)]; q = sm.sched[2 * (r * (PMAX / 2) + k) + 1]; }
+}
+// slot of row i in round r
+__device__ __forceinline__ int eig3_slot(const Eig3Smem& sm, bool cross, int r, int i) {
+    if (cross) return i < BSZ ? i : ((i - BSZ - r) & (BSZ - 1));
+    return sm.slot[r * PMAX + i];
+}
+
+// G' = R G R^H on block (k, l): rows {pk, qk} x cols {pl, ql}, read from gi, written to g; off-diagonal blocks also
+// write the conjugate-transposed block.
+__device__ __forceinline__ void eig3_block(const cplx* gi, cplx* g, int pk, int qk, int pl, int ql, double ck, cplx ok,
+                                           double cl, cplx ol, bool diag, bool act) {
+    const cplx g00 = gi[pk * GS + pl], g01 = gi[pk * GS + ql], g10 = gi[qk * GS + pl], g11 = gi[qk * GS + ql];
+    // rows: [x0;x1] = R_k [g0*; g1*]
+    const cplx a00 = cadd(cscale(g00, ck), cmul(ok, g10));
+    const cplx a01 = cadd(cscale(g01, ck), cmul(ok, g11));
+    const cplx a10 = csub(cscale(g10, ck), cmul(cconj(ok), g00));
+    const cplx a11 = csub(cscale(g11, ck), cmul(cconj(ok), g01));
+    // cols: [y0 y1] = [a*0 a*1] R_l^H :  y0 = cl a0 + conj(ol) a1 ; y1 = -ol a0 + cl a1
+    cplx b00 = cadd(cscale(a00, cl), cmulc(a01, ol));
+    cplx b01 = csub(cscale(a01, cl), cmul(ol, a00));
+    cplx b10 = cadd(cscale(a10, cl), cmulc(a11, ol));
+    cplx b11 = csub(cscale(a11, cl), cmul(ol, a10));
+    if (diag) {
+        b00.y = 0.0; b11.y = 0.0;
+        if (act) { b01 = mk(0.0, 0.0); b10 = mk(0.0, 0.0); }
+        g[pk * GS + pl] = b00; g[pk * GS + ql] = b01; g[qk * GS + pl] = b10; g[qk * GS + ql] = b11;
+    } else {
+        g[pk * GS + pl] = b00; g[pk * GS + ql] = b01; g[qk * GS + pl] = b10; g[qk * GS + ql] = b11;
+        g[pl * GS + pk] = cconj(b00); g[ql * GS + pk] = cconj(b01); g[pl * GS + qk] = cconj(b10); g[ql * GS + qk] = cconj(b11);
+    }
+}
+
+__global__ void __launch_bounds__(NTE3)
+k_eig3(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, double tol2, int max_inner, float cross_ratio,
+       int cross_only, PairSpec ps, int slot_base, int* __restrict__ notconv, int* __restrict__ rotated,
+       double* __restrict__ sig2, const int* __restrict__ done) {
+    pdl_wait();
+    pdl_trigger();
+    if (done && *done) return;      // static (sync-free) mode: this SVD already converged
+    extern __shared__ __align__(16) unsigned char eig_smem[];
+    Eig3Smem& sm = *reinterpret_cast<Eig3Smem*>(eig_smem);
+    cplx* g = sm.g[0];
+    cplx* q = sm.q;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = slot_base + blockIdx.x;
+    constexpr int n = PMAX, np = PMAX / 2;
+    // ---- load: sum of the per-chunk partial Gram matrices [pair][chunk][PMAX*PMAX*2] in fixed order ----
+    {
+        const double* Gp = G + (long long)pair * nchunks * PMAX * PMAX * 2;
+        constexpr int NE = PMAX * PMAX / NTE3;            // entries per thread
+        double re[NE], im[NE];
+#pragma unroll
+        for (int it = 0; it < NE; it++) { re[it] = 0.0; im[it] = 0.0; }
+#pragma unroll 8
+        for (int c = 0; c < nchunks; c++) {                // 2 x 8 independent L2 loads in flight per thread
+#pragma unroll
+            for (int it = 0; it < NE; it++) {
+                const double2 v = __ldcg((const double2*)(Gp + (long long)c * PMAX * PMAX * 2 + 2 * (tid + it * NTE3)));
+                re[it] += v.x; im[it] += v.y;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < NE; it++) {
+            const int e = tid + it * NTE3, i = e / PMAX, j = e % PMAX;
+            g[i * GS + j] = mk(re[it], im[it]);
+            q[i * GS + j] = mk(i == j ? 1.0 : 0.0, 0.0);
+        }
+    }
+    for (int e = tid; e < (n - 1) * np; e += NTE3) {
+        int r = e / np, k = e % np, a, b;
+        circle_pair(r, k, n, a, b);
+        sm.sched[2 * e] = (unsigned char)a;
+        sm.sched[2 * e + 1] = (unsigned char)b;
+        sm.slot[r * PMAX + a] = (unsigned char)k;
+        sm.slot[r * PMAX + b] = (unsigned char)k;
+    }
+    if (tid < NOFF) {
+        // t -> (k, l), k < l, row-major over the strict upper triangle of the 16 x 16 tiling
+        int k = 0, rem = tid;
+        while (rem >= np - 1 - k) { rem -= np - 1 - k; k++; }
+        sm.blk[2 * tid] = (unsigned char)k;
+        sm.blk[2 * tid + 1] = (unsigned char)(k + 1 + rem);
+    }
+    if (tid == 0) { sm.s_off = 0; sm.s_mc = 0; sm.s_mi = 0; sm.s_stop = 0; sm.s_any = 0; }
+    __syncthreads();
+    // Fresh Gram matrix: already diagonal to tolerance?  Largest relative off-diagonal
+    // |g_ij|^2/(g_ii g_jj) among cross-block and intra-block entries decides the schedule.
+    {
+        int offd = 0;
+        float mc = 0.f, mi = 0.f;
+        for (int e = tid; e < n * n; e += NTE3) {
+            const int i = e / n, j = e % n;
+            if (i < j) {
+                const double a = g[i * GS + i].x, b = g[j * GS + j].x;
+                if (a > 0.0 && b > 0.0) {
+                    const double m2 = cabs2(g[i * GS + j]);
+                    if (m2 > tol2 * a * b) {
+                        offd = 1;
+                        const float rel = (float)(m2 / (a * b));
+                        if ((i < BSZ) == (j < BSZ)) mi = fmaxf(mi, rel); else mc = fmaxf(mc, rel);
+                    }
+                }
+            }
+        }
+        if (offd) sm.s_off = 1;
+        // non-negative floats order like their bit patterns
+        if (mc > 0.f) atomicMax(&sm.s_mc, __float_as_int(mc));
+        if (mi > 0.f) atomicMax(&sm.s_mi, __float_as_int(mi));
+    }
+    __syncthreads();
+    // cross-only schedule while the intra-block residual is well below the cross-block one
+    const bool cross = cross_only && (__int_as_float(sm.s_mi) <= cross_ratio * __int_as_float(sm.s_mc));
+    const int nrounds = cross ? BSZ : n - 1;
+    const int total = sm.s_off ? max_inner * nrounds : 0;
+
+    // rotation of pair slot j for (global) round rr from the current G -> table[rr & 1]
+    auto make_rotation = [&](const cplx* gb, int rr, int j) -> int {
+        int p, qq;
+        eig3_pair(sm, cross, rr % nrounds, j, p, qq);
+        const double a = gb[p * GS + p].x, b = gb[qq * GS + qq].x;
+        const cplx gpq = gb[p * GS + qq];
+        const double mag2 = cabs2(gpq);
+        double c = 1.0;
+        cplx o = mk(0.0, 0.0);
+        int act = 0;
+        if (a > 0.0 && b > 0.0 && mag2 > tol2 * a * b) {
+            // overflow-free form without 1/|g| (see k_eig)
+            const double dd = 0.5 * (b - a);
+            const double hh = fma(dd, dd, mag2);
+            const double den = fabs(dd) + hh * rsqrt(hh);
+            const double R = rsqrt(fma(den, den, mag2));
+            const double s = copysign(R, dd);
+            c = den * R;
+            o = mk(-s * gpq.x, -s * gpq.y);
+            act = 1;
+        }
+        sm.rc[rr & 1][j] = c;
+        sm.ro[rr & 1][j] = o;
+        sm.ract[rr & 1][j] = act;
+        return act;
+    };
+
+    int sweep_any = 0;                                     // warp 0: a rotation was active in the current inner sweep
+    if (total > 0 && warp == 0) {
+        int act = 0;
+        if (lane < np) act = make_rotation(g, 0, lane);
+        sweep_any = __any_sync(0xffffffffu, act);
+    }
+    __syncthreads();
+    // warp roles: 0 = pivots + next rotations (alone on its scheduler but for Q warps); 1,2,3,5 = off-diagonal blocks;
+    // 4, 6..15 = Q
+    const int bw = warp == 5 ? 3 : warp - 1;
+    const bool is_blk = warp == 1 || warp == 2 || warp == 3 || warp == 5;
+    const int qtid = (warp == 4 ? 0 : warp - 5) * 32 + lane;
+    int rr = 0;
+    for (; rr < total; rr++) {
+        const int r = rr % nrounds, cur = rr & 1;
+        const cplx* gi = sm.g[cur];
+        cplx* go = sm.g[cur ^ 1];
+        if (warp == 0) {
+            // diagonal blocks (lanes 0-15) and the blocks holding the next round's pivots (lanes 16-31)
+            const bool have_next = rr + 1 < total;
+            int k, l;
+            bool diag = lane < np;
+            if (diag) { k = lane; l = lane; }
+            else {
+                int p2 = 0, q2 = 0;
+                eig3_pair(sm, cross, (rr + 1) % nrounds, lane - np, p2, q2);
+                const int k1 = eig3_slot(sm, cross, r, p2), k2 = eig3_slot(sm, cross, r, q2);
+                k = k1 < k2 ? k1 : k2;
+                l = k1 < k2 ? k2 : k1;
+            }
+            if (diag || (have_next && k != l)) {
+                int pk, qk, pl, ql;
+                eig3_pair(sm, cross, r, k, pk, qk);
+                eig3_pair(sm, cross, r, l, pl, ql);
+                eig3_block(gi, go, pk, qk, pl, ql, sm.rc[cur][k], sm.ro[cur][k], sm.rc[cur][l], sm.ro[cur][l], diag,
+                           sm.ract[cur][k] != 0);
+            }
+            __syncwarp();
+            if (have_next) {
+                if ((rr + 1) % nrounds == 0) {             // an inner sweep just ended
+                    if (!sweep_any) { if (lane == 0) sm.s_stop = 1; }
+                    sweep_any = 0;
+                }
+                int act = 0;
+                if (lane < np) act = make_rotation(go, rr + 1, lane);
+                sweep_any |= __any_sync(0xffffffffu, act);
+            }
+        } else if (is_blk) {
+            // the 120 blocks above the diagonal (the ones warp 0 also rotates get identical values twice)
+            const int t = bw * 32 + lane;
+            if (t < NOFF) {
+                const int k = sm.blk[2 * t], l = sm.blk[2 * t + 1];
+                int pk, qk, pl, ql;
+                eig3_pair(sm, cross, r, k, pk, qk);
+                eig3_pair(sm, cross, r, l, pl, ql);
+                eig3_block(gi, go, pk, qk, pl, ql, sm.rc[cur][k], sm.ro[cur][k], sm.rc[cur][l], sm.ro[cur][l], false, false);
+            }
+        } else {
+            // Q' = R Q: 16 pairs x 32 columns over the 352 threads of the eleven Q warps
+            for (int item = qtid; item < np * PMAX; item += 352) {
+                const int k = item >> 5, col = item & 31;
+                if (sm.ract[cur][k]) {
+                    int pk, qk;
+                    eig3_pair(sm, cross, r, k, pk, qk);
+                    const double ck = sm.rc[cur][k];
+                    const cplx ok = sm.ro[cur][k];
+                    const cplx x = q[pk * GS + col], y = q[qk * GS + col];
+                    q[pk * GS + col] = cadd(cscale(x, ck), cmul(ok, y));
+                    q[qk * GS + col] = csub(cscale(y, ck), cmul(cconj(ok), x));
+                }
+            }
+        }
+        if (tid == 0) {
+            int any = 0;
+#pragma unroll
+            for (int j = 0; j < np; j++) any |= sm.ract[cur][j];
+            if (any) sm.s_any = 1;
+        }
+        __syncthreads();
+        if (sm.s_stop) { rr++; break; }
+    }
+    g = sm.g[rr & 1];                                      // buffer written by the last executed round
+    cplx* Qp = Qout + (long long)pair * PMAX * PMAX;
+    for (int e = tid; e < n * n; e += NTE3) Qp[e] = q[(e / n) * GS + (e % n)];
+    if (tid < n) {
+        int bi, bj;
+        get_pair(ps, blockIdx.x, bi, bj);
+        const int row = tid < BSZ ? bi * BSZ + tid : bj * BSZ + (tid - BSZ);
+        sig2[row] = g[tid * GS + tid].x;
+    }
+    if (tid == 0) {
+        rotated[pair] = sm.s_any;
+        if (sm.s_off) {
+            atomicAdd(notconv, 1);
+            // largest relative off-diagonal^2 met in this sweep (fresh Gram): lets the host skip the
+            // verification sweep when the quadratically convergent last sweep started below 1e-9
+            const int mx = sm.s_mc > sm.s_mi ? sm.s_mc : sm.s_mi;
+            atomicMax(notconv + 2, mx);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // DMMA versions of (1) and (3) for full 32-row pairs (multi-block mode).  Fragments are
 // loaded straight from global memory: a lane's 16-byte load of W[row][col] carries the
 // re and im parts that serve as A and B operands of mma.sync.m8n8k4.f64.
@@ -617,9 +897,12 @@ __global__ void k_rowcopy(cplx* __restrict__ out, long long ldo, const cplx* __r
 }
 
 // out[a][j] = f(in[perm[j]][a]) * (S ? 1/S[j] : 1),  j < nsel, a < len
+// conj bit 1: conjugate; bit 2: scale by 1/S[j]^2 instead of 1/S[j]
 __global__ void k_transpose(cplx* __restrict__ out, long long ldo, const cplx* __restrict__ in, long long ldi,
                             const int* __restrict__ perm, const double* __restrict__ S, int conj, int nsel,
                             long long len, int na) {
+    const int ssq = conj & 2;
+    conj &= 1;
     __shared__ cplx tile[32][33];
     long long a0 = (long long)(blockIdx.x % na) * 32;
     int j0 = (int)(blockIdx.x / na) * 32;
@@ -632,7 +915,11 @@ __global__ void k_transpose(cplx* __restrict__ out, long long ldo, const cplx* _
             int src = perm ? perm[j] : j;
             v = in[(long long)src * ldi + a];
             if (conj) v.y = -v.y;
-            if (S) { double s = S[j]; v = cscale(v, (s > 0.0) ? 1.0 / s : 0.0); }
+            if (S) {
+                double s = S[j];
+                if (ssq) s *= s;
+                v = cscale(v, (s > 0.0) ? 1.0 / s : 0.0);
+            }
         }
         tile[jj][tx] = v;
     }
@@ -803,7 +1090,7 @@ constexpr int MAXCH = 32;     // Gram partial slots per pair (DMMA path)
 constexpr int MAXCH1 = 64;    // Gram slabs of the single-block path
 
 struct Work {
-    cplx* W; double* G; cplx* Q; int* rotated; double* sig2; int* perm; int* notconv;
+    cplx* W; double* G; cplx* Q; int* rotated; double* sig2; int* perm; int* notconv; cplx* T;
     size_t total;
 };
 
@@ -812,6 +1099,8 @@ Work carve(const Geom& g, void* base) {
     size_t off = 0;
     char* b = (char*)base;
     w.W = (cplx*)(b + off); off += align_up((size_t)g.nvp * g.ldw * sizeof(cplx));
+    w.T = nullptr;
+    if (!g.ext) { w.T = (cplx*)(b + off); off += align_up((size_t)g.len * g.nv * sizeof(cplx)); }   // back-multiplication operand
     {   // multi-block: MAXCH slabs per pair; single block: up to MAXCH1 full slabs or 148*4 skinny ones
         size_t slabs = (size_t)g.npairs * MAXCH;
         if (slabs < (size_t)MAXCH1) slabs = MAXCH1;
@@ -829,19 +1118,20 @@ Work carve(const Geom& g, void* base) {
 }  // namespace
 
 extern "C" long long qm_svd_work_bytes(int m, int n) {
-    Geom g = make_geom(m, n);
-    Work w = carve(g, nullptr);
-    return (long long)w.total;
+    Geom g0 = make_geom(m, n, 0), g1 = make_geom(m, n, 1);
+    Work w0 = carve(g0, nullptr), w1 = carve(g1, nullptr);
+    return (long long)(w0.total > w1.total ? w0.total : w1.total);
 }
 
 // A (m x n, row-major, lda) is not modified.  U: m x k (ldu), S: k, Vh: k x n (ldvh), k = min(m,n).
 // U or Vh may be NULL.  info_host (optional, host int[2]) receives {sweeps, converged}.
 static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long long ldu, void* S_, void* Vh_,
                     long long ldvh, void* work, long long work_bytes, double tol, int max_sweeps,
-                    int* info_host, int fixed_sweeps, int* mismatch, void* stream_) {
+                    int* info_host, int fixed_sweeps, int* mismatch, int flags, void* stream_) {
     if (m <= 0 || n <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream_;
-    Geom g = make_geom(m, n);
+    static const int force_acc = getenv("QM_SVD_ACC") ? atoi(getenv("QM_SVD_ACC")) : 0;   // A/B: 1 = always accumulate
+    Geom g = make_geom(m, n, ((flags & QM_SVD_BACKMULT) && !force_acc) ? 1 : 0);
     if (g.nv > 6144) return -2;   // k_sort shared memory bound (48 KB)
     Work w = carve(g, work);
     if ((long long)w.total > work_bytes) return -1;
@@ -869,7 +1159,7 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
     QM_CHECK_LAUNCH();
     {
         dim3 grid(ceil_div(g.nvp > 256 ? g.nvp : 256, 256), g.nvp);
-        QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_init_ext<<<grid, 256, 0, st>>>(w.W, g.ldw, g.nv, g.nvp, g.len));
+        QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_init_ext<<<grid, 256, 0, st>>>(w.W, g.ldw, g.nv, g.ext ? g.nvp : 0, g.len));
         QM_CHECK_LAUNCH();
     }
     QM_CUDA(cudaMemsetAsync(w.G, 0, (size_t)g.npairs * PMAX * PMAX * 2 * sizeof(double), st));
@@ -903,8 +1193,11 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
     };
     const double tol2 = tol * tol;
     static bool eig_attr_set = false;
+    static int eig_version = 3;        // QM_EIG=1 selects the first formulation for the 32-row pairs too (A/B runs)
     if (!eig_attr_set) {
         QM_CUDA(cudaFuncSetAttribute(k_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIG_SMEM));
+        QM_CUDA(cudaFuncSetAttribute(k_eig3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Eig3Smem)));
+        if (getenv("QM_EIG")) eig_version = atoi(getenv("QM_EIG"));
         eig_attr_set = true;
     }
     // schedule knobs (defaults chosen from the sweep study in profiles/; env overrides for experiments)
@@ -995,6 +1288,15 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
                 w.W, g.ldw, g.len, (int)chunk_g, ps, slot, w.G, donep));
         };
         auto launch_eig = [&](const PairSpec& ps, int np, int slot, cudaStream_t s) {
+            if (eig_version == 3 && !g.single) {
+                if (is_static) QM_LAUNCH(QM_CLS_SVD_EIG, s, k_eig3<<<np, NTE3, sizeof(Eig3Smem), s>>>(
+                    w.G, eig_chunks, w.Q, tol2, max_inner, tune_ratio, cross_only, ps, slot, w.notconv, w.rotated,
+                    w.sig2, donep));
+                else QM_LAUNCH(QM_CLS_SVD_EIG, s, qm_launch_dep(k_eig3, dim3(np), dim3(NTE3), sizeof(Eig3Smem), s,
+                    w.G, eig_chunks, w.Q, tol2, max_inner, tune_ratio, cross_only, ps, slot, w.notconv, w.rotated,
+                    w.sig2, donep));
+                return;
+            }
             if (is_static) QM_LAUNCH(QM_CLS_SVD_EIG, s, k_eig<<<np, NTE, EIG_SMEM, s>>>(
                 w.G, eig_chunks, w.Q, g.nrows, tol2, g.single ? 12 : max_inner, tune_ratio, cross_only, ps, slot,
                 g.single, w.notconv, w.rotated, w.sig2, donep));
@@ -1094,9 +1396,17 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
     cplx* Vh = (cplx*)Vh_;
     if (m < n) {
         // U[a][j] = conj(J[perm[j]][a]);  Vh[j][c] = W[perm[j]][c] / S[j]
-        if (U)
+        if (U && g.ext)
             QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose<<<(unsigned)((long long)ceil_div(m, 32) * ceil_div(k, 32)), dim3(32, 8), 0, st>>>(
                 U, ldu, w.W + g.len, g.ldw, w.perm, nullptr, 1, k, m, ceil_div(m, 32)));
+        if (U && !g.ext) {
+            // rows of W are sigma_j z_j:  U = A Z^H Sigma^-1 = A T,  T[a][j] = conj(W[perm[j]][a]) / S[j]^2  (n x k)
+            QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose<<<(unsigned)((long long)ceil_div(n, 32) * ceil_div(k, 32)), dim3(32, 8), 0, st>>>(
+                w.T, k, w.W, g.ldw, w.perm, S, 3, k, n, ceil_div(n, 32)));
+            QM_CHECK_LAUNCH();
+            int e = qm_zgemm(m, k, n, 1.0, 0.0, A, lda, w.T, k, 0.0, 0.0, U, ldu, 1, 0, 0, 0, 0, stream_);
+            if (e) return e;
+        }
         if (Vh) {
             dim3 grid(ceil_div(n, 256) > 4096 ? 4096 : ceil_div(n, 256), k);
             QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_rowcopy<<<grid, 256, 0, st>>>(Vh, ldvh, w.W, g.ldw, w.perm, S, 0, k, n));
@@ -1110,9 +1420,17 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         } else if (U)
             QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose<<<(unsigned)((long long)ceil_div(m, 32) * ceil_div(k, 32)), dim3(32, 8), 0, st>>>(
                 U, ldu, w.W, g.ldw, w.perm, S, 0, k, m, ceil_div(m, 32)));
-        if (Vh) {
+        if (Vh && g.ext) {
             dim3 grid(ceil_div(n, 256), k);
             QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_rowcopy<<<grid, 256, 0, st>>>(Vh, ldvh, w.W + g.len, g.ldw, w.perm, nullptr, 1, k, n));
+        }
+        if (Vh && !g.ext) {
+            // rows of W are sigma_j u_j^T:  Vh = Sigma^-1 U^H A = T^H A,  T[a][j] = W[perm[j]][a] / S[j]^2  (m x k)
+            QM_LAUNCH(QM_CLS_SVD_LAYOUT, st, k_transpose<<<(unsigned)((long long)ceil_div(m, 32) * ceil_div(k, 32)), dim3(32, 8), 0, st>>>(
+                w.T, k, w.W, g.ldw, w.perm, S, 2, k, m, ceil_div(m, 32)));
+            QM_CHECK_LAUNCH();
+            int e = qm_zgemm(k, n, m, 1.0, 0.0, w.T, k, A, lda, 0.0, 0.0, Vh, ldvh, 1, 0, 0, 0, 1, stream_);
+            if (e) return e;
         }
     }
     QM_CHECK_LAUNCH();
@@ -1121,9 +1439,9 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
 
 extern "C" int qm_svd(int m, int n, const void* A, long long lda, void* U, long long ldu, void* S, void* Vh,
                       long long ldvh, void* work, long long work_bytes, double tol, int max_sweeps,
-                      int* info_host, void* stream) {
+                      int* info_host, int flags, void* stream) {
     return svd_impl(m, n, A, lda, U, ldu, S, Vh, ldvh, work, work_bytes, tol, max_sweeps, info_host, 0, nullptr,
-                    stream);
+                    flags, stream);
 }
 
 // Sync-free variant (CUDA-graph capturable): exactly `fixed_sweeps` sweeps are enqueued, kernels of the
@@ -1131,9 +1449,9 @@ extern "C" int qm_svd(int m, int n, const void* A, long long lda, void* U, long 
 // converged by then (the caller re-runs that problem through qm_svd).
 extern "C" int qm_svd_static(int m, int n, const void* A, long long lda, void* U, long long ldu, void* S, void* Vh,
                              long long ldvh, void* work, long long work_bytes, double tol, int fixed_sweeps,
-                             void* mismatch, void* stream) {
+                             void* mismatch, int flags, void* stream) {
     return svd_impl(m, n, A, lda, U, ldu, S, Vh, ldvh, work, work_bytes, tol, fixed_sweeps, nullptr,
-                    fixed_sweeps, (int*)mismatch, stream);
+                    fixed_sweeps, (int*)mismatch, flags, stream);
 }
 
 // out (cols x rows, ldo) = transpose of in (rows x cols, ldi), optionally conjugated.  The layout

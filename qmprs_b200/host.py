@@ -27,7 +27,7 @@ def from_dense(K, psi, n_sites, spectra=None):
     r = 1
     for i in range(N - 1, 0, -1):
         M = T.reshape(2 ** i, 2 * r)
-        U, S, Vh = K.svd(M)
+        U, S, Vh = K.svd(M, backmult=True)
         k = S.shape[0]
         if spectra is not None:
             spectra.append(S)
@@ -82,7 +82,7 @@ def right_compress(K, A, max_bond=None, spectra=None, cutoff=CUTOFF):
     for i in range(len(A) - 1, 0, -1):
         b, _, r = A[i].shape
         l0 = A[i - 1].shape[0]
-        U, S, Vh = K.svd(A[i].reshape(b, 2 * r))
+        U, S, Vh = K.svd(A[i].reshape(b, 2 * r), backmult=True)
         k = S.shape[0]
         if spectra is not None:
             spectra.append(S)
@@ -240,7 +240,7 @@ def apply_inverse_layer(K, B, gates, kinds, spectra=None, inverse=True, split="s
                         B[i] = X.reshape(l, 2, 2 * r)
                         B[i + 1] = K.eye(2 * r).reshape(2 * r, 2, r)
                     continue
-                U, S, Vh = K.svd(X)
+                U, S, Vh = K.svd(X, backmult=True)
                 k = S.shape[0]
                 if spectra is not None:
                     spectra.append(S)
@@ -279,7 +279,8 @@ def flat_schedule(kinds_per_layer, n_sites):
 STORED_SWEEP_MAX_BYTES = 64 << 30      # intermediates kept in HBM up to 64 GiB (180 GB per B200)
 
 
-def optimize_layers(K, target, gates_all, kinds_per_layer, n_sites, num_sweeps, envs=None, stored=True, small=True):
+def optimize_layers(K, target, gates_all, kinds_per_layer, n_sites, num_sweeps, envs=None, stored=True, small=True,
+                    persistent=True):
     """``_optimize_unitary_layers``: per sweep rebuild the dense circuit state from the
     current gates (sequential.py:533, 443-447; the reference's full-rank re-compression
     of that state into an MPS is an identity and is skipped) and run one environment
@@ -291,6 +292,11 @@ def optimize_layers(K, target, gates_all, kinds_per_layer, n_sites, num_sweeps, 
         return gates_all
     stored_bytes = (len(sites) + 1) * 16 * (1 << n_sites)
     use_stored = stored and stored_bytes <= STORED_SWEEP_MAX_BYTES
+    if (persistent and use_stored and num_sweeps > 0 and not getattr(K, "static", False)
+            and hasattr(K, "sweeps_persist")):
+        # every sweep (forward + backward pass) in one persistent cooperative launch, one grid barrier per gate-step
+        if K.sweeps_persist(target, n_sites, gates_all, sites, kinds, num_sweeps, envs):
+            return gates_all
     c = None
     vwarm = K.zeros((len(sites), 16)) if use_stored else None      # warm start of the 4x4 polar, per gate
     for _ in range(num_sweeps):
@@ -321,7 +327,7 @@ def from_dense_truncated(K, psi, n_sites, chi, spectra=None):
     T = psi.reshape(-1, 1)
     r = 1
     for i in range(N - 1, 0, -1):
-        U, S, Vh = K.svd(T.reshape(2 ** i, 2 * r))
+        U, S, Vh = K.svd(T.reshape(2 ** i, 2 * r), backmult=True)
         k = S.shape[0]
         if spectra is not None:
             spectra.append(S)

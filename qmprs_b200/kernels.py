@@ -161,17 +161,22 @@ class CudaKernels:
         G = self.gemm(A, A, transA=True)                  # n x n Hermitian PSD
         # V from the ACCUMULATED rotations (Vh of the Jacobi run: unitary to rounding whatever the spectrum);
         # the normalised-row factor U loses orthogonality for eigenvalues near eps * |G|.
-        _, _, Vhg = self.svd(G, _plain=True)
+        # (a pre-conditioner: eigenvalues below eps |G| never meet the relative tolerance; bounded, no warning)
+        _, _, Vhg = self.svd(G, _plain=True, _max_sweeps=12)
         A1 = self.gemm(A, self.transpose(Vhg, conj=True))
         U, S, Vh1 = self.svd(A1, _plain=True)
         return U, S, self.gemm(Vh1, Vhg)
 
-    def svd(self, A, want_u=True, want_vh=True, out_s=None, out_vh=None, _plain=False):
+    def svd(self, A, want_u=True, want_vh=True, out_s=None, out_vh=None, _plain=False, backmult=False,
+            _max_sweeps=None):
+        """Thin SVD.  ``backmult`` (the MPS path's splits): QM_SVD_BACKMULT of the C ABI -- the rotations are not
+        accumulated, the second factor comes from one ZGEMM against ``A`` (include/qmprs_b200.h)."""
         m, n = A.shape
         k = min(m, n)
+        flags = 1 if backmult else 0
         if (not _plain and want_u and want_vh and out_s is None and out_vh is None and k >= self.PRECOND_MIN
                 and max(m, n) >= self.PRECOND_ASPECT * k):
-            if m >= n:
+            if m >= n:                         # (accumulating mode inside: its Gram stage needs a unitary V whatever the spectrum)
                 return self._svd_preconditioned(A)
             # wide: A^H = V S U^H
             V, S, Uh = self._svd_preconditioned(self.transpose(A, conj=True))
@@ -188,15 +193,15 @@ class CudaKernels:
             self._check(self.lib.qm_svd_static(m, n, _p(A), self._ld(A), _p(U), k, _p(S), _p(Vh),
                                                (self._ld(Vh) if Vh is not None else n), _p(self._svd_work),
                                                self._svd_work.numel(), self.svd_tol, fixed,
-                                               _p(self.mismatch), self._stream()), "qm_svd_static")
+                                               _p(self.mismatch), flags, self._stream()), "qm_svd_static")
             return U, S, Vh
         info = (ctypes.c_int * 2)()
         self._check(self.lib.qm_svd(m, n, _p(A), self._ld(A), _p(U), k, _p(S), _p(Vh),
                                     (self._ld(Vh) if Vh is not None else n), _p(self._svd_work),
-                                    self._svd_work.numel(), self.svd_tol, self.svd_max_sweeps, info,
-                                    self._stream()), "qm_svd")
+                                    self._svd_work.numel(), self.svd_tol, _max_sweeps or self.svd_max_sweeps, info,
+                                    flags, self._stream()), "qm_svd")
         self.svd_sweeps += info[0]
-        if not info[1]:
+        if not info[1] and _max_sweeps is None:
             # a partially converged decomposition would silently drive rank cut-offs and gates
             import warnings
             self.svd_unconverged += 1
@@ -328,12 +333,7 @@ class CudaKernels:
                                              self._int_array(kinds), len(sites), _p(self._sweep_work), _p(envs),
                                              _p(vwarm), self._stream()), "qm_sweep_stored")
 
-    SMALL_SWEEP_MAX_SITES = 12
-    SMALL_SWEEP_MAX_GATES = 256
-
-    def sweeps_small(self, targets, n_sites, gates, sites, kinds, num_sweeps, batch=1, envs=None):
-        """All sweeps of `batch` small states in one launch (one CTA per state, vectors in shared memory).
-        ``targets``: [batch, 2^N] dense (not conjugated); ``gates``: [batch * M, 16], updated in place."""
+    def _sched_dev(self, sites, kinds):
         key = (tuple(int(x) for x in sites), tuple(int(x) for x in kinds))
         cache = self.__dict__.setdefault("_sched_cache", {})
         dev = cache.get(key)
@@ -341,6 +341,33 @@ class CudaKernels:
             dev = (torch.tensor(key[0], dtype=torch.int32, device=self.device),
                    torch.tensor(key[1], dtype=torch.int32, device=self.device))
             cache[key] = dev
+        return dev
+
+    def sweeps_persist(self, target, n_sites, gates, sites, kinds, num_sweeps, envs=None):
+        """All sweeps of one large register in one persistent cooperative launch (qm_sweeps_persist).
+        Returns False when the device cannot co-schedule the grid (caller falls back to the per-gate kernels)."""
+        M = len(sites)
+        dev = self._sched_dev(sites, kinds)
+        need = int(self.lib.qm_sweeps_persist_work_bytes(M))
+        w = self.__dict__.get("_persist_work")
+        if w is None or w.numel() < need:
+            w = self._persist_work = torch.empty(need, dtype=torch.uint8, device=self.device)
+        cs = self.empty((M + 1, 1 << n_sites))
+        tbar = self.empty((1 << n_sites,))
+        code = self.lib.qm_sweeps_persist(_p(cs), _p(tbar), _p(target), n_sites, _p(gates), _p(dev[0]), _p(dev[1]), M,
+                                          int(num_sweeps), _p(w), _p(envs), self._stream())
+        if code == -3:
+            return False
+        self._check(code, "qm_sweeps_persist")
+        return True
+
+    SMALL_SWEEP_MAX_SITES = 12
+    SMALL_SWEEP_MAX_GATES = 256
+
+    def sweeps_small(self, targets, n_sites, gates, sites, kinds, num_sweeps, batch=1, envs=None):
+        """All sweeps of `batch` small states in one launch (one CTA per state, vectors in shared memory).
+        ``targets``: [batch, 2^N] dense (not conjugated); ``gates``: [batch * M, 16], updated in place."""
+        dev = self._sched_dev(sites, kinds)
         self._check(self.lib.qm_sweeps_small(_p(targets), n_sites, _p(gates), _p(dev[0]), _p(dev[1]), len(sites),
                                              int(num_sweeps), int(batch), _p(envs), self._stream()), "qm_sweeps_small")
 

@@ -15,7 +15,7 @@ for m, n in zip(args[0::2], args[1::2]):
     best = 1e9
     for rep in range(3):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        U, S, Vh = K.svd(A, _plain=True)
+        U, S, Vh = K.svd(A, _plain=True, backmult=bool(int(os.environ.get("QM_PROBE_BACKMULT", "0"))))
         torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
     s = K.to_host(S)
     sref = np.linalg.svd(a, compute_uv=False)

@@ -71,7 +71,7 @@ class FakeKernels:
         out.copy_(r)
         return out
 
-    def svd(self, A, want_u=True, want_vh=True, out_s=None, out_vh=None):
+    def svd(self, A, want_u=True, want_vh=True, out_s=None, out_vh=None, backmult=False):
         u, s, vh = np.linalg.svd(_np(A), full_matrices=False)
         if self._rng is not None:       # arbitrary singular-vector phases, as a Jacobi SVD would return
             ph = np.exp(2j * np.pi * self._rng.random(s.size))

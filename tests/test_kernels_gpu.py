@@ -381,3 +381,80 @@ def test_svd_tall_preconditioned(K, m, n):
     q2, _ = np.linalg.qr(crand(rng, min(m, n), min(m, n)))
     a = (q1 * np.logspace(0, -7, min(m, n))[None, :]) @ q2
     check_svd(K, a if m >= n else a.T.copy())
+
+
+@pytest.mark.parametrize("m,n", [(64, 64), (48, 100), (100, 48), (128, 512), (512, 128), (256, 256), (300, 77), (33, 40)])
+def test_svd_backmult(K, m, n):
+    """QM_SVD_BACKMULT (the mode of the MPS path's splits): W alone is rotated, the second factor comes from one
+    ZGEMM against the input.  Same singular values as the accumulating mode (the rotations are identical), exact
+    reconstruction, factors orthonormal to eps * kappa."""
+    rng = np.random.default_rng(m * 31 + n)
+    a = crand(rng, m, n)
+    A = K.from_host(a)
+    U, S, Vh = K.svd(A, backmult=True)
+    U0, S0, Vh0 = K.svd(A)
+    u, s, vh = K.to_host(U), K.to_host(S), K.to_host(Vh)
+    assert np.abs(s - K.to_host(S0)).max() <= 1e-14 * s[0]
+    sref = np.linalg.svd(a, compute_uv=False)
+    assert np.all(np.abs(s - sref) <= 1e-10 * sref)
+    assert np.abs((u * s[None, :]) @ vh - a).max() <= 1e-12 * s[0]
+    kappa = s[0] / s[-1]
+    k = min(m, n)
+    assert np.abs(np.conj(u).T @ u - np.eye(k)).max() <= 1e-14 * kappa + 1e-12
+    assert np.abs(vh @ np.conj(vh).T - np.eye(k)).max() <= 1e-14 * kappa + 1e-12
+    # same singular vectors as the accumulating mode up to a phase per pair
+    ph = np.sum(np.conj(K.to_host(Vh0)) * vh, axis=1)
+    assert np.abs(np.abs(ph) - 1).max() <= 1e-8 * kappa
+
+
+def test_svd_backmult_rank_deficient(K):
+    """Null directions get arbitrary (finite or not) vectors in the back-multiplied factor; the kept part --
+    what the cutoffs of the MPS path retain -- reconstructs the matrix."""
+    rng = np.random.default_rng(5)
+    a = crand(rng, 64, 3) @ crand(rng, 3, 40)
+    U, S, Vh = K.svd(K.from_host(a), backmult=True)
+    u, s, vh = K.to_host(U), K.to_host(S), K.to_host(Vh)
+    assert np.all(s[3:] <= 1e-12 * s[0])
+    assert np.abs((u[:, :3] * s[None, :3]) @ vh[:3] - a).max() <= 1e-12 * s[0]
+    assert np.all(np.isfinite(u[:, :3])) and np.all(np.isfinite(vh[:3]))
+
+
+@pytest.mark.parametrize("N,L,S,blocks", [(13, 2, 3, False), (9, 3, 2, True), (16, 1, 2, False), (4, 2, 2, True)])
+def test_sweeps_persist_matches_stored(K, N, L, S, blocks):
+    """qm_sweeps_persist (all sweeps in one cooperative launch, one grid barrier per gate-step, every CTA reducing
+    and updating redundantly) against S rounds of qm_circuit_states + qm_sweep_stored: same circuit state after
+    the sweeps, same environments of the last sweep, unitary gates; block boundaries (unfused pending gates) and
+    one-qubit gates included; a second call on the same inputs is bit-identical."""
+    rng = np.random.default_rng(1000 * N + L)
+    kinds_layer = [2] * (N - 1) + [1]
+    if blocks:
+        kinds_layer = ([2, 2, 1, 2, 1, 1, 1, 2, 2] * 2)[:N]
+        kinds_layer[-1] = 1
+    kinds = kinds_layer * L
+    sites = list(range(N)) * L
+    M = len(kinds)
+    gates = np.zeros((M, 16), dtype=np.complex128)
+    for idx, k in enumerate(kinds):
+        d = 4 if k == 2 else 2
+        q, _ = np.linalg.qr(crand(rng, d, d))
+        gates[idx, : d * d] = q.reshape(-1)
+    target = crand(rng, 2 ** N)
+    T = K.from_host(target)
+    Gp, Gp2, Gs = K.from_host(gates), K.from_host(gates), K.from_host(gates)
+    envs_p, envs_s = K.zeros((M, 16)), K.zeros((M, 16))
+    assert K.sweeps_persist(T, N, Gp, sites, kinds, S, envs_p)
+    assert K.sweeps_persist(T, N, Gp2, sites, kinds, S)
+    assert np.array_equal(K.to_host(Gp), K.to_host(Gp2))
+    vwarm = K.zeros((M, 16))
+    for sweep in range(S):
+        cs = K.circuit_states(N, Gs, sites, kinds)
+        K.sweep_stored(cs, K.conj_scale_copy(T, conj=True), N, Gs, sites, kinds, envs_s, vwarm)
+    fp = K.to_host(K.circuit_state(N, Gp, sites, kinds))
+    fs = K.to_host(K.circuit_state(N, Gs, sites, kinds))
+    assert np.abs(fp - fs).max() <= 1e-10
+    assert np.abs(K.to_host(envs_p) - K.to_host(envs_s)).max() <= 1e-10
+    gp = K.to_host(Gp)
+    for idx, k in enumerate(kinds):
+        d = 4 if k == 2 else 2
+        u = gp[idx, : d * d].reshape(d, d)
+        assert np.abs(u @ u.conj().T - np.eye(d)).max() <= 1e-12
