@@ -51,6 +51,17 @@ int qm_svd_static(int m, int n, const void* A, long long lda, void* U, long long
                   long long ldvh, void* work, long long work_bytes, double tol, int fixed_sweeps, void* mismatch,
                   int flags, void* stream);
 
+/* Small problems (min(m,n) <= 64 and the work matrix within one SM's shared memory, e.g. every matrix of a
+ * 12-qubit / chi=64 register): `batch` independent thin SVDs of one shape, ONE CTA each, the whole Jacobi
+ * iteration inside the kernel -- no workspace, no host synchronisation, CUDA-graph capturable.  Same outputs and
+ * flags as qm_svd; strides in elements between consecutive problems (0 for batch = 1); U / Vh may be NULL.
+ * mismatch (optional int[1]) is set to 1 if a problem has not converged after max_sweeps sweeps.
+ * qm_svd_small_fits: 1 if the shape is supported (else qm_svd_small returns -3). */
+int qm_svd_small_fits(int m, int n, int flags);
+int qm_svd_small(int m, int n, const void* A, long long lda, long long strideA, void* U, long long ldu,
+                 long long strideU, void* S, long long strideS, void* Vh, long long ldvh, long long strideVh,
+                 double tol, int max_sweeps, int flags, int batch, void* mismatch, void* stream);
+
 /* out (cols x rows) = in^T (optionally conjugated): the coalesced reshape/transposed-store kernels
  * that stream the statevector in the TT-SVD (quimb from_dense reshapes, mps.py:242), exposed for
  * tests and HBM-bandwidth measurement (32*rows*cols bytes per call). */
@@ -152,9 +163,11 @@ int qm_sweep_stored(const void* cs, void* tbar, int n_sites, void* gates, const 
  * shared memory (same arithmetic as qm_circuit_state + qm_sweep per sweep; sequential.py:443-505,
  * 509-541).  targets: [batch][2^N] (not conjugated); gates: [batch][n_gates][16], updated in place;
  * sites_dev / kinds_dev: DEVICE int[n_gates], one schedule for the batch; envs: optional
- * [batch][n_gates][16], environments of the last sweep.  Returns -3 if the state does not fit. */
+ * [batch][n_gates][16], environments of the last sweep.  psis / overlaps (optional): overlaps[batch][2] (double)
+ * receives <psi_b| circuit_b |0..0> / |psi_b| for the final gates (README.md:66), psi_b = psis[b] ([batch][2^N]) or the
+ * target when psis is NULL; num_sweeps = 0 is then allowed.  Returns -3 if the state does not fit. */
 int qm_sweeps_small(const void* targets, int n_sites, void* gates, const int* sites_dev, const int* kinds_dev,
-                    int n_gates, int num_sweeps, int batch, void* envs, void* stream);
+                    int n_gates, int num_sweeps, int batch, void* envs, const void* psis, void* overlaps, void* stream);
 
 /* Large registers: ALL `num_sweeps` optimisation sweeps (forward circuit states + backward environment
  * sweep, sequential.py:509-541, :443-505) in one persistent cooperative launch, one CTA per SM and one grid

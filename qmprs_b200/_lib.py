@@ -23,6 +23,8 @@ SIGNATURES = {
     "qm_svd_work_bytes": (_ll, [_i, _i]),
     "qm_svd": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _d, _i, _ip, _i, _vp]),
     "qm_svd_static": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _d, _i, _vp, _i, _vp]),
+    "qm_svd_small_fits": (_i, [_i, _i, _i]),
+    "qm_svd_small": (_i, [_i, _i, _vp, _ll, _ll, _vp, _ll, _ll, _vp, _ll, _vp, _ll, _ll, _d, _i, _i, _i, _vp, _vp]),
     "qm_expect_ints": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "qm_expect_not_close": (_i, [_vp, _d, _vp, _vp]),
     "qm_transpose": (_i, [_vp, _ll, _vp, _ll, _ll, _ll, _i, _vp]),
@@ -47,7 +49,7 @@ SIGNATURES = {
     "qm_sweep": (_i, [_vp, _vp, _i, _vp, _ip, _ip, _i, _vp, _vp, _vp]),
     "qm_circuit_states": (_i, [_vp, _i, _vp, _ip, _ip, _i, _vp]),
     "qm_sweep_stored": (_i, [_vp, _vp, _i, _vp, _ip, _ip, _i, _vp, _vp, _vp, _vp]),
-    "qm_sweeps_small": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "qm_sweeps_small": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "qm_sweeps_persist_work_bytes": (_ll, [_i]),
     "qm_sweeps_persist": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "qm_version": (_i, []),

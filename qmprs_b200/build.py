@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "gemm.cu", "svd.cu", "qr.cu", "mps_ops.cu", "dense.cu", "dense_small.cu", "dense_persist.cu")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "gemm.cu", "svd.cu", "qr.cu", "mps_ops.cu", "dense.cu", "dense_small.cu", "dense_persist.cu", "small_svd.cu")]
 OUT = os.path.join(HERE, "libqmprs_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -80,7 +80,8 @@ __device__ __forceinline__ void small_env(cplx* c, const cplx* t, int nst, int q
 
 __global__ void __launch_bounds__(NTS, 1)
 k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ gates_g, const int* __restrict__ sites,
-               const int* __restrict__ kinds, int n_gates, int num_sweeps, cplx* __restrict__ envs_g, int warm) {
+               const int* __restrict__ kinds, int n_gates, int num_sweeps, cplx* __restrict__ envs_g, int warm,
+               const cplx* __restrict__ psis, double* __restrict__ overlaps) {
     extern __shared__ __align__(16) unsigned char sw_smem[];
     const int nst = 1 << nbits;
     cplx* c = (cplx*)sw_smem;
@@ -148,6 +149,41 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
         }
     }
     for (int i = tid; i < n_gates * 16; i += blockDim.x) gg[i] = g[i];
+    if (overlaps) {
+        // <psi | circuit |0..0>> / |psi| with the final gates (psi: the state's own row of `psis`, else the target):
+        // the fidelity users report (README.md:66), so that a batch needs no per-state circuit + dot kernels
+        const cplx* psi = psis ? psis + (long long)blockIdx.x * nst : target;
+        __syncthreads();
+        for (int i = tid; i < nst; i += blockDim.x) c[i] = mk(i == 0 ? 1.0 : 0.0, 0.0);
+        __syncthreads();
+        for (int k = 0; k < n_gates; k++) {
+            if (gd[k] == 4) small_apply<4, 0>(c, nst, gq[k], g + k * 16);
+            else small_apply<2, 0>(c, nst, gq[k], g + k * 16);
+            __syncthreads();
+        }
+        cplx ov = mk(0.0, 0.0);
+        double nr = 0.0;
+        for (int i = tid; i < nst; i += blockDim.x) {
+            const cplx p = psi[i];
+            ccfma(ov, p, c[i]);
+            nr += cabs2(p);
+        }
+        double v3[3] = {ov.x, ov.y, nr};
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            v3[j] = warp_sum(v3[j]);
+            if (lane == 0) wsum[warp][j] = v3[j];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double s3[3] = {0.0, 0.0, 0.0};
+            for (int w = 0; w < nw; w++)                              // fixed order
+                for (int j = 0; j < 3; j++) s3[j] += wsum[w][j];
+            const double inv = s3[2] > 0.0 ? rsqrt(s3[2]) : 0.0;
+            overlaps[2 * blockIdx.x] = s3[0] * inv;
+            overlaps[2 * blockIdx.x + 1] = s3[1] * inv;
+        }
+    }
 }
 
 }  // namespace
@@ -157,11 +193,15 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
 // gates: device [batch][n_gates][16] in application order, updated in place; sites/kinds: DEVICE int[n_gates]
 // (one schedule for the whole batch); envs (optional): [batch][n_gates][16] environments of the last sweep.
 // Returns -3 when the state does not fit (callers then use qm_circuit_states + qm_sweep_stored).
+// psis / overlaps (optional, both may be NULL): overlaps[batch][2] <- <psi_b| circuit_b |0..0> / |psi_b| with the final
+// gates (psi_b = psis[b] or the target when psis is NULL); with overlaps given, num_sweeps = 0 is allowed.
 extern "C" int qm_sweeps_small(const void* targets, int n_sites, void* gates, const int* sites_dev, const int* kinds_dev,
-                               int n_gates, int num_sweeps, int batch, void* envs, void* stream) {
+                               int n_gates, int num_sweeps, int batch, void* envs, const void* psis, void* overlaps,
+                               void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_sites < 2 || n_sites > 12 || n_gates < 1 || n_gates > 256 || batch < 1) return -3;
-    if (num_sweeps <= 0) return 0;
+    if (num_sweeps <= 0 && !overlaps) return 0;
+    if (num_sweeps < 0) num_sweeps = 0;
     const size_t nst = (size_t)1 << n_sites;
     size_t smem = 2 * nst * sizeof(cplx) + (size_t)n_gates * 16 * sizeof(cplx) + (size_t)n_gates * 2 * sizeof(int);
     const int warm = smem + (size_t)n_gates * 16 * sizeof(cplx) <= 220 * 1024;      // room for the polar warm starts
@@ -177,7 +217,8 @@ extern "C" int qm_sweeps_small(const void* targets, int n_sites, void* gates, co
     // same algorithmic bytes as the unfused kernels so that the classes stay comparable)
     qm_prof_work(QM_CLS_ENV, (double)batch * num_sweeps * n_gates * 96.0 * (double)nst);
     QM_LAUNCH(QM_CLS_ENV, st, k_sweeps_small<<<batch, threads, smem, st>>>(
-        (const cplx*)targets, n_sites, (cplx*)gates, sites_dev, kinds_dev, n_gates, num_sweeps, (cplx*)envs, warm));
+        (const cplx*)targets, n_sites, (cplx*)gates, sites_dev, kinds_dev, n_gates, num_sweeps, (cplx*)envs, warm,
+        (const cplx*)psis, (double*)overlaps));
     QM_CHECK_LAUNCH();
     return 0;
 }

@@ -23,8 +23,11 @@ from qmprs_b200.kernels import CudaKernels, get_kernels
 
 
 class _Lane:
-    def __init__(self, device, n, chi, L, S, threshold, sample_state, split="svd"):
+    def __init__(self, device, n, chi, L, S, threshold, sample_state, split="svd", defer_sweeps=False):
+        """``defer_sweeps``: the captured graph stops after the layer extraction and leaves ``gates`` (before any
+        sweep) and the dense ``target``; the sweeps of a whole batch then run in ONE launch (run_into)."""
         self.n, self.chi, self.L, self.S, self.threshold = n, chi, L, S, threshold
+        self.defer = bool(defer_sweeps)
         self.K = CudaKernels(device)                      # private workspaces
         self.stream = torch.cuda.Stream(device)
         self.psi_in = torch.empty(2 ** n, dtype=torch.complex128, device=device)
@@ -34,14 +37,19 @@ class _Lane:
         with torch.cuda.stream(self.stream):
             # eager warm-up on this lane: lazy initialisation, attribute calls, workspace growth
             self.psi_in.copy_(torch.from_numpy(sample_state))
-            host.prepare_device(K, self.psi_in, n, chi, L, S, threshold, split=split)
+            host.prepare_device(K, self.psi_in, n, chi, L, 0 if self.defer else S, threshold, split=split)
         self.stream.synchronize()
         n0 = K.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=self.stream):
             K.begin_static()
             work = K.scale_copy(self.psi_in.reshape(-1, 1)).reshape(-1)
-            gates, kinds, ov, _, _ = host.prepare_device(K, work, n, chi, L, S, threshold, split=split)
+            if self.defer:
+                gates, kinds, _, A = host.prepare_layers_device(K, work, n, chi, L, threshold, split=split)
+                ov = None
+                self.target = host.to_dense(K, A)                     # sequential.py:440 (mps.mps)
+            else:
+                gates, kinds, ov, _, _ = host.prepare_device(K, work, n, chi, L, S, threshold, split=split)
             K.end_static()
         self.nodes = K.launch_count() - n0
         self.gates, self.kinds, self.ov, self.mismatch = gates, kinds, ov, K.mismatch
@@ -92,14 +100,35 @@ class GraphedPreparer:
         sample = rng.random(2 ** n_qubits) + 1j * rng.random(2 ** n_qubits)
         sample /= np.linalg.norm(sample)
         self.split = split
-        self.lanes = [_Lane(device, *self.cfg, sample, split=split) for _ in range(int(lanes))]
+        self._sample = sample
+        self.n_lanes = int(lanes)
+        self._full = None                    # lanes whose graph is the whole pipeline (run: one state at a time)
+        self._layers = None                  # lanes whose graph stops before the sweeps (run_into: batches)
         self.eager = get_kernels(device)
+        # batches of registers whose sweeps fit one SM's shared memory: per-state graphs extract the layers, then
+        # ONE k_sweeps_small launch (grid = batch) sweeps every state and returns its fidelity
+        self.defer = (self.cfg[0] <= CudaKernels.SMALL_SWEEP_MAX_SITES
+                      and self.cfg[0] * self.cfg[2] <= CudaKernels.SMALL_SWEEP_MAX_GATES)
         self.fallbacks = 0
         self.replays = 0
 
     @property
+    def lanes(self):
+        if self._full is None:
+            self._full = [_Lane(self.device, *self.cfg, self._sample, split=self.split) for _ in range(self.n_lanes)]
+        return self._full
+
+    @property
+    def layer_lanes(self):
+        if self._layers is None:
+            self._layers = [_Lane(self.device, *self.cfg, self._sample, split=self.split, defer_sweeps=True)
+                            for _ in range(self.n_lanes)]
+        return self._layers
+
+    @property
     def nodes_per_graph(self):
-        return self.lanes[0].nodes
+        built = self._layers if self._layers is not None else self.lanes
+        return built[0].nodes
 
     def _finish(self, lane, out):
         tag, res, state = lane.collect()
@@ -127,33 +156,49 @@ class GraphedPreparer:
         main = torch.cuda.current_stream(dev)
         host_states = None
         if hasattr(states, "data_ptr") and states.is_cuda:
-            sdev = states
+            sdev = states.contiguous()
         else:
             host_states = np.ascontiguousarray(np.asarray(states, dtype=np.complex128))
             sdev = torch.from_numpy(host_states).pin_memory().to(dev, non_blocking=True)
         ng, nk = L * n * 32, L * n
         # constant part of the records of the static pipeline: one block per layer, all layers used
-        tmpl = np.concatenate([np.tile(np.array([2.0] * (n - 1) + [1.0]), L), [float(L)]])
+        kinds_layer = [2] * (n - 1) + [1]
+        tmpl = np.concatenate([np.tile(np.array(kinds_layer, dtype=np.float64), L), [float(L)]])
         rec_dev[:B, ng:ng + nk + 1] = torch.from_numpy(tmpl).to(dev)
         flags = torch.zeros(B, dtype=torch.int32, device=dev)
         ready = torch.cuda.Event()
         ready.record(main)
-        nl = len(self.lanes)
-        for lane in self.lanes[:min(nl, B)]:
+        lanes = self.layer_lanes if self.defer else self.lanes
+        nl = len(lanes)
+        for lane in lanes[:min(nl, B)]:
             lane.stream.wait_event(ready)
+        if self.defer:
+            gates_b = torch.empty((B, L * n, 16), dtype=torch.complex128, device=dev)
+            targets_b = torch.empty((B, 2 ** n), dtype=torch.complex128, device=dev)
         for s in range(B):
-            lane = self.lanes[s % nl]
+            lane = lanes[s % nl]
             with torch.cuda.stream(lane.stream):
                 lane.psi_in.copy_(sdev[s], non_blocking=True)
                 lane.mismatch.zero_()
                 lane.graph.replay()
-                rec_dev[s, :ng].copy_(lane.gates.view(torch.float64).reshape(-1), non_blocking=True)
-                rec_dev[s, ng + nk + 1:ng + nk + 3].copy_(lane.ov, non_blocking=True)
+                if self.defer:
+                    gates_b[s].copy_(lane.gates, non_blocking=True)
+                    targets_b[s].copy_(lane.target, non_blocking=True)
+                else:
+                    rec_dev[s, :ng].copy_(lane.gates.view(torch.float64).reshape(-1), non_blocking=True)
+                    rec_dev[s, ng + nk + 1:ng + nk + 3].copy_(lane.ov, non_blocking=True)
                 flags[s:s + 1].copy_(lane.mismatch, non_blocking=True)
         self.replays += B
-        for lane in self.lanes[:min(nl, B)]:
+        for lane in lanes[:min(nl, B)]:
             lane.done.record(lane.stream)
             main.wait_event(lane.done)
+        if self.defer:
+            # every state's sweeps + fidelity in one launch, one CTA per state (sequential.py:509-541; README.md:66)
+            ov = torch.empty((B, 2), dtype=torch.float64, device=dev)
+            self.eager.sweeps_small(targets_b, n, gates_b.view(B * L * n, 16), list(range(n)) * L, kinds_layer * L, S,
+                                    batch=B, psis=sdev, overlaps=ov)
+            rec_dev[:B, :ng] = gates_b.view(torch.float64).reshape(B, ng)
+            rec_dev[:B, ng + nk + 1:ng + nk + 3] = ov
         bad = np.nonzero(flags.cpu().numpy())[0]
         for s in bad:                                      # an assumption failed: eager path, exact semantics
             st = host_states[s] if host_states is not None else sdev[s]

@@ -389,15 +389,24 @@ def disentangle(K, A, num_layers, threshold, record=None, split="svd", precondit
     return gates_all, layer_kinds, overlaps
 
 
+def prepare_layers_device(K, psi, n_sites, chi, num_layers, threshold=1 - 1e-6, record=None, fused=True, split="svd"):
+    """First half of :func:`prepare_device`: normalise ``psi`` in place, build the MPS and extract the layers.
+    Returns (gates_all, kinds per layer, overlaps, MPS).  graphs.py captures this much per state and leaves the
+    sweeps of the whole batch to one launch."""
+    K.div_sqrt(psi, K.vdot(psi, psi))                                 # quick Ket normalisation
+    A = build_mps(K, psi, int(n_sites), chi, record, fused)
+    gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record, split)
+    return gates_all, layer_kinds, overlaps, A
+
+
 def prepare_device(K, psi, n_sites, chi, num_layers, num_sweeps, threshold=1 - 1e-6, record=None, fused=True,
                    split="svd"):
     """Device-to-device core of :func:`prepare`: ``psi`` is a device vector (overwritten by its
     normalised copy), returns device tensors (gates_all [L*N,16], kinds per layer, overlap [2] =
     <psi|circuit> as (re, im), overlaps list).  No host transfer; this is what graphs.py captures."""
     N = int(n_sites)
-    K.div_sqrt(psi, K.vdot(psi, psi))                                 # quick Ket normalisation
-    A = build_mps(K, psi, N, chi, record, fused)
-    gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record, split)
+    gates_all, layer_kinds, overlaps, A = prepare_layers_device(K, psi, N, chi, num_layers, threshold, record, fused,
+                                                                split)
     if num_sweeps > 0:
         target = to_dense(K, A)                                       # sequential.py:440 (mps.mps)
         optimize_layers(K, target, gates_all, layer_kinds, N, num_sweeps)
@@ -429,6 +438,8 @@ def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 -
         sites, kinds = flat_schedule(layer_kinds, N)
         ovt = K.vdot(psi, K.circuit_state(N, gates_all, sites, kinds))
     ov = K.to_host(ovt)
+    if hasattr(K, "check_small_svd"):
+        K.check_small_svd()
     L = len(layer_kinds)
     return {
         "gates": K.to_host(gates_all).reshape(L, N, 16),

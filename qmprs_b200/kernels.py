@@ -58,6 +58,10 @@ class CudaKernels:
         self.svd_unconverged = 0
         self.svd_tol = 1e-14
         self.svd_max_sweeps = 30
+        # matrices that fit one SM's shared memory are decomposed by the single-CTA solver (qm_svd_small): one
+        # launch, no host synchronisation per sweep.  Its sticky "did not converge" flag is read by check_small_svd().
+        self.small_svd = True
+        self._small_flag = None
         # speculative static-shape mode (graphs.py): no host read-backs; assumptions are validated on
         # the device and recorded in `mismatch`
         self.static = False
@@ -181,6 +185,20 @@ class CudaKernels:
             # wide: A^H = V S U^H
             V, S, Uh = self._svd_preconditioned(self.transpose(A, conj=True))
             return self.transpose(Uh, conj=True), S, self.transpose(V, conj=True)
+        if self.small_svd and self.lib.qm_svd_small_fits(m, n, flags):
+            U = self.empty((m, k)) if want_u else None
+            S = out_s if out_s is not None else self.empty((k,), F64)
+            Vh = out_vh if out_vh is not None else (self.empty((k, n)) if want_vh else None)
+            if self.static:
+                flag = self.mismatch
+            else:
+                if self._small_flag is None:
+                    self._small_flag = self.zeros((1,), I32)
+                flag = self._small_flag
+            self._check(self.lib.qm_svd_small(m, n, _p(A), self._ld(A), 0, _p(U), k, 0, _p(S), 0, _p(Vh),
+                                              (self._ld(Vh) if Vh is not None else n), 0, self.svd_tol,
+                                              self.svd_max_sweeps, flags, 1, _p(flag), self._stream()), "qm_svd_small")
+            return U, S, Vh
         need = int(self.lib.qm_svd_work_bytes(m, n))
         if self._svd_work is None or self._svd_work.numel() < need:
             self._svd_work = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=self.device)
@@ -208,6 +226,17 @@ class CudaKernels:
             warnings.warn(f"qm_svd({m}x{n}) did not converge to tol={self.svd_tol} in {self.svd_max_sweeps} sweeps",
                           RuntimeWarning, stacklevel=2)
         return U, S, Vh
+
+    def check_small_svd(self):
+        """Read (and clear) the sticky non-convergence flag of the single-CTA SVDs issued since the last check."""
+        if self._small_flag is None:
+            return
+        if int(self._small_flag.item()):
+            import warnings
+            self.svd_unconverged += 1
+            self._small_flag.zero_()
+            warnings.warn(f"a qm_svd_small problem did not converge to tol={self.svd_tol} in {self.svd_max_sweeps} sweeps",
+                          RuntimeWarning, stacklevel=2)
 
     def transpose(self, A, conj=False):
         rows, cols = A.shape
@@ -364,12 +393,16 @@ class CudaKernels:
     SMALL_SWEEP_MAX_SITES = 12
     SMALL_SWEEP_MAX_GATES = 256
 
-    def sweeps_small(self, targets, n_sites, gates, sites, kinds, num_sweeps, batch=1, envs=None):
+    def sweeps_small(self, targets, n_sites, gates, sites, kinds, num_sweeps, batch=1, envs=None, psis=None,
+                     overlaps=None):
         """All sweeps of `batch` small states in one launch (one CTA per state, vectors in shared memory).
-        ``targets``: [batch, 2^N] dense (not conjugated); ``gates``: [batch * M, 16], updated in place."""
+        ``targets``: [batch, 2^N] dense (not conjugated); ``gates``: [batch * M, 16], updated in place;
+        ``overlaps`` (optional [batch, 2] float64) receives <psi|circuit|0..0>/|psi| for the final gates, psi from
+        ``psis`` ([batch, 2^N]) or the target."""
         dev = self._sched_dev(sites, kinds)
         self._check(self.lib.qm_sweeps_small(_p(targets), n_sites, _p(gates), _p(dev[0]), _p(dev[1]), len(sites),
-                                             int(num_sweeps), int(batch), _p(envs), self._stream()), "qm_sweeps_small")
+                                             int(num_sweeps), int(batch), _p(envs), _p(psis), _p(overlaps),
+                                             self._stream()), "qm_sweeps_small")
 
     # ---- instrumentation ------------------------------------------------------------
     def launch_count(self):

@@ -458,3 +458,97 @@ def test_sweeps_persist_matches_stored(K, N, L, S, blocks):
         d = 4 if k == 2 else 2
         u = gp[idx, : d * d].reshape(d, d)
         assert np.abs(u @ u.conj().T - np.eye(d)).max() <= 1e-12
+
+
+@pytest.mark.parametrize("S", [0, 2])
+def test_sweeps_small_overlaps(K, S):
+    """Batched fidelity output of qm_sweeps_small: <psi_b|circuit_b|0..0>/|psi_b| with the final gates, against
+    qm_circuit_state + numpy per state (also with num_sweeps = 0: circuit + overlap only)."""
+    rng = np.random.default_rng(31 + S)
+    N, L, batch = 6, 2, 3
+    kinds = ([2] * (N - 1) + [1]) * L
+    sites = list(range(N)) * L
+    M = len(kinds)
+    gates = np.zeros((batch, M, 16), dtype=np.complex128)
+    for b in range(batch):
+        for idx, k in enumerate(kinds):
+            d = 4 if k == 2 else 2
+            q, _ = np.linalg.qr(crand(rng, d, d))
+            gates[b, idx, : d * d] = q.reshape(-1)
+    targets = np.stack([crand(rng, 2 ** N) for _ in range(batch)])
+    psis = np.stack([2.5 * crand(rng, 2 ** N) for _ in range(batch)])          # not normalised on purpose
+    for use_psis in (True, False):
+        Gs = K.from_host(gates.reshape(batch * M, 16))
+        ov = K.zeros((batch, 2), dtype=__import__("torch").float64)
+        K.sweeps_small(K.from_host(targets), N, Gs, sites, kinds, S, batch, None,
+                       K.from_host(psis) if use_psis else None, ov)
+        gs = K.to_host(Gs).reshape(batch, M, 16)
+        if S == 0:
+            assert np.array_equal(gs, gates)
+        for b in range(batch):
+            c = K.to_host(K.circuit_state(N, K.from_host(gs[b]), sites, kinds))
+            ref_vec = psis[b] if use_psis else targets[b]
+            ref = np.vdot(ref_vec, c) / np.linalg.norm(ref_vec)
+            got = complex(*K.to_host(ov)[b])
+            assert abs(got - ref) <= 1e-12
+
+
+def check_factors(a, u, s, vh, kappa_tol=False):
+    sref = np.linalg.svd(a, compute_uv=False)
+    scale = sref[0] if sref[0] > 0 else 1.0
+    assert np.all(np.diff(s) <= 1e-300 + 1e-14 * scale)
+    assert np.abs(s - sref).max() <= 1e-12 * scale
+    big = sref > 1e-5 * scale
+    assert np.all(np.abs(s[big] - sref[big]) <= 1e-10 * sref[big])
+    assert np.abs((u * s[None, :]) @ vh - a).max() <= 1e-11 * scale
+    r = int(np.count_nonzero(sref > 1e-12 * scale))
+    tol = 1e-11 if not kappa_tol else 1e-11 + 1e-14 * scale / sref[r - 1]
+    assert np.abs(np.conj(u[:, :r]).T @ u[:, :r] - np.eye(r)).max() <= tol
+    assert np.abs(vh[:r] @ np.conj(vh[:r]).T - np.eye(r)).max() <= tol
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (2, 2), (2, 8), (8, 2), (1, 7), (7, 1), (5, 33), (33, 5), (32, 32), (64, 64),
+                                 (32, 128), (128, 32), (2048, 2), (1024, 4), (63, 64), (64, 17), (16, 64)])
+@pytest.mark.parametrize("backmult", [False, True])
+def test_svd_small_single_cta(K, m, n, backmult):
+    """qm_svd_small (one CTA, whole iteration in shared memory) on the shapes of a 12-qubit / chi=64 register,
+    odd sizes included, through the C ABI with batch = 3 and strided outputs."""
+    import ctypes
+    import torch
+    from qmprs_b200.kernels import _p
+    flags = 1 if backmult else 0
+    assert K.lib.qm_svd_small_fits(m, n, flags)
+    rng = np.random.default_rng(m * 131 + n)
+    batch, k = 3, min(m, n)
+    a = np.stack([crand(rng, m, n) for _ in range(batch)])
+    A = K.from_host(a)
+    U = K.zeros((batch, m, k)); S = K.zeros((batch, k), dtype=torch.float64); Vh = K.zeros((batch, k, n))
+    mis = K.zeros((1,), dtype=torch.int32)
+    code = K.lib.qm_svd_small(m, n, _p(A), n, m * n, _p(U), k, m * k, _p(S), k, _p(Vh), n, k * n, 1e-14, 30, flags,
+                              batch, _p(mis), K._stream())
+    assert code == 0 and int(mis.item()) == 0
+    for b in range(batch):
+        check_factors(a[b], K.to_host(U[b]), K.to_host(S[b]), K.to_host(Vh[b]), kappa_tol=backmult)
+    # the dispatcher in K.svd picks the same kernel for these shapes
+    u1, s1, v1 = K.svd(A[0], backmult=backmult)
+    assert np.array_equal(K.to_host(s1), K.to_host(S[0]))
+
+
+def test_svd_small_graded_and_rank_deficient(K):
+    rng = np.random.default_rng(12)
+    q1, _ = np.linalg.qr(crand(rng, 48, 48))
+    q2, _ = np.linalg.qr(crand(rng, 48, 48))
+    s = np.logspace(0, -8, 48)
+    a = (q1 * s[None, :]) @ q2
+    U, S, Vh = K.svd(K.from_host(a))
+    check_factors(a, K.to_host(U), K.to_host(S), K.to_host(Vh))
+    a = crand(rng, 64, 3) @ crand(rng, 3, 40)
+    U, S, Vh = K.svd(K.from_host(a))
+    sv = K.to_host(S)
+    assert np.all(sv[3:] <= 1e-12 * sv[0])
+    check_factors(a, K.to_host(U), sv, K.to_host(Vh))
+    a = crand(rng, 12, 4); a[:, 1] = 0; a[:, 3] = 0
+    U, S, Vh = K.svd(K.from_host(a))
+    check_factors(a, K.to_host(U), K.to_host(S), K.to_host(Vh))
+    assert K.lib.qm_svd_small_fits(65, 65, 0) == 0 and K.lib.qm_svd_small_fits(64, 4096, 0) == 0
+    K.check_small_svd()
