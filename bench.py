@@ -290,7 +290,7 @@ def load_peaks():
         return {}
 
 
-SVD_STAGE = ("svd_gram", "svd_eig", "svd_apply", "svd_layout")
+SVD_STAGE = ("svd_gram", "svd_eig", "svd_apply", "svd_layout", "svd_round")
 
 
 def roofline_from_profile(prof, peak_tf):
@@ -319,7 +319,7 @@ def roofline_from_profile(prof, peak_tf):
         roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "traffic": None,
                 "peak_source": "FP64: cuBLAS ZGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)"}
-    name = {"svd": "svd stage: k_gram_mma + k_eig + k_apply_mma (+ layout)", "zgemm": "k_zgemm_tma",
+    name = {"svd": "svd stage: k_round (fused Gram + eigen-solve + update per Jacobi round) + layout", "zgemm": "k_zgemm_tma",
             "env_polar": "k_env_fused", "gate": "k_gate2"}.get(dom, dom)
     try:      # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, cold cache)
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))

@@ -69,7 +69,7 @@ extern "C" int qm_prof_num_classes(void) { return QM_NCLS; }
 
 extern "C" const char* qm_prof_class_name(int cls) {
     static const char* names[QM_NCLS] = {"zgemm", "svd_gram", "svd_eig", "svd_apply", "svd_layout", "qr_vec",
-                                         "qr_apply", "small", "gate", "env_polar"};
+                                         "qr_apply", "small", "gate", "env_polar", "svd_round"};
     return (cls >= 0 && cls < QM_NCLS) ? names[cls] : "?";
 }
 

@@ -7,7 +7,7 @@ typedef double2 cplx;
 
 // kernel classes for the launch counter / event profiler (api.cu)
 enum { QM_CLS_GEMM = 0, QM_CLS_SVD_GRAM, QM_CLS_SVD_EIG, QM_CLS_SVD_APPLY, QM_CLS_SVD_LAYOUT, QM_CLS_QR_VEC,
-       QM_CLS_QR_APPLY, QM_CLS_SMALL, QM_CLS_GATE, QM_CLS_ENV, QM_NCLS };
+       QM_CLS_QR_APPLY, QM_CLS_SMALL, QM_CLS_GATE, QM_CLS_ENV, QM_CLS_SVD_ROUND, QM_NCLS };
 void qm_prof_pre(int cls, cudaStream_t st);
 void qm_prof_post(int cls, cudaStream_t st);
 // algorithmic work of the launches of a class (flops for compute kernels, bytes for streaming ones)

@@ -18,6 +18,7 @@
 // At the end sigma_j = |row_j|, Z = rows / sigma, J = the accumulated unitary:
 //   m <  n :  A = J^H Sigma Z          U = J^H,  Vh = Z
 //   m >= n :  A = Z^T Sigma conj(J)    U = Z^T,  Vh = conj(J)
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include "common.cuh"
@@ -472,22 +473,18 @@ __device__ __forceinline__ void eig3_block(const cplx* gi, cplx* g, int pk, int 
     }
 }
 
-__global__ void __launch_bounds__(NTE3)
-k_eig3(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, double tol2, int max_inner, float cross_ratio,
-       int cross_only, PairSpec ps, int slot_base, int* __restrict__ notconv, int* __restrict__ rotated,
-       double* __restrict__ sig2, const int* __restrict__ done) {
-    pdl_wait();
-    pdl_trigger();
-    if (done && *done) return;      // static (sync-free) mode: this SVD already converged
-    extern __shared__ __align__(16) unsigned char eig_smem[];
-    Eig3Smem& sm = *reinterpret_cast<Eig3Smem*>(eig_smem);
+// Eigen-solve of ONE pair by the 512 threads of the calling CTA.  Gp: the pair's nchunks partial Gram slabs;
+// Qp: the pair's 32 x 32 output; (bi, bj): its row blocks; pair: its workspace slot.
+__device__ __forceinline__ void eig3_run(Eig3Smem& sm, const double* Gp, int nchunks, cplx* Qp, double tol2, int max_inner,
+                                         float cross_ratio, int cross_only, int bi, int bj, int pair,
+                                         int* __restrict__ notconv, int* __restrict__ rotated,
+                                         double* __restrict__ sig2) {
     cplx* g = sm.g[0];
     cplx* q = sm.q;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = slot_base + blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int n = PMAX, np = PMAX / 2;
-    // ---- load: sum of the per-chunk partial Gram matrices [pair][chunk][PMAX*PMAX*2] in fixed order ----
+    // ---- load: sum of the per-chunk partial Gram matrices [chunk][PMAX*PMAX*2] in fixed order ----
     {
-        const double* Gp = G + (long long)pair * nchunks * PMAX * PMAX * 2;
         constexpr int NE = PMAX * PMAX / NTE3;            // entries per thread
         double re[NE], im[NE];
 #pragma unroll
@@ -663,11 +660,8 @@ k_eig3(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, double tol2
         if (sm.s_stop) { rr++; break; }
     }
     g = sm.g[rr & 1];                                      // buffer written by the last executed round
-    cplx* Qp = Qout + (long long)pair * PMAX * PMAX;
     for (int e = tid; e < n * n; e += NTE3) Qp[e] = q[(e / n) * GS + (e % n)];
     if (tid < n) {
-        int bi, bj;
-        get_pair(ps, blockIdx.x, bi, bj);
         const int row = tid < BSZ ? bi * BSZ + tid : bj * BSZ + (tid - BSZ);
         sig2[row] = g[tid * GS + tid].x;
     }
@@ -680,6 +674,391 @@ k_eig3(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, double tol2
             const int mx = sm.s_mc > sm.s_mi ? sm.s_mc : sm.s_mi;
             atomicMax(notconv + 2, mx);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// (2'') Mixed-precision eigen-solve of a full 32 x 32 Gram matrix (round 2, second step).
+//
+// ncu on k_eig3 (profiles/ncu_r02_summary.md): a rotation round costs ~1800 cycles and its critical path is one
+// warp's chain of ~45 DEPENDENT FP64 instructions (block update -> pivots -> two rsqrt -> rotation) at ~40 cycles
+// each; the FP64 pipe itself is 11 % busy.  The chain cannot be made shorter in FP64, but it does not need FP64:
+//   * any unitary Q applied to the pair's rows leaves the SVD exact -- the quality of Q only decides how fast the
+//     OUTER iteration converges (its Gram matrices are re-formed in FP64 from W every visit);
+//   * so the Jacobi recurrence itself (G update -> pivots -> angle) runs in FP32 on a scaled copy of G, with the
+//     diagonal tracked in FP64 (differences of nearly equal squared norms decide the angles of close pairs);
+//   * each rotation is then made EXACTLY unitary in FP64 from its FP32 tangent t:  c = 1/sqrt(1 + |t|^2),
+//     o = -t c (one FP32-seeded third-order rsqrt step), off the critical path, and applied to Q in FP64.
+// An FP32 angle is accurate to ~1e-7 of itself, so a visit leaves a residual of max(eps^2, 1e-7 eps) from an
+// off-diagonal level eps instead of eps^2: the same number of outer sweeps to reach 1e-14.
+// Round layout (one barrier per round, 512 threads):
+//   warp 0         diagonal blocks + the 16 blocks holding the next round's pivots, then the next round's angles;
+//   warps 1,2,3,5  the 120 off-diagonal blocks (FP32), mirrored;
+//   warp 6         lanes 0-15: exact (c, o) of round r in FP64 from t(r);
+//   warps 4, 7-15  Q <- R(r-1) Q in FP64 (one round behind, 320 threads for 512 items).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ long long gtimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct Eig4Smem {
+    cplx gd[PMAX * GS];              // fresh Gram matrix in FP64 (load, convergence scan)
+    cplx q[PMAX * GS];
+    float2 gf[2][PMAX * GS];         // scaled FP32 working copies (double-buffered)
+    double hd[PMAX];                 // HALF the scaled diagonal, FP64
+    float rcf[2][PMAX / 2];          // FP32 rotation of a round: c, o
+    float2 rof[2][PMAX / 2];
+    float2 rt[2][PMAX / 2];          // FP32 tangent t = sign(dd) g / den, kept for the FP64 side (two rounds alive)
+    int ract[4][PMAX / 2];           // active flags (G side reads [r&1], Q side one and two rounds later)
+    double rc[2][PMAX / 2];          // exact FP64 rotation: row p <- c x + o y ;  row q <- -conj(o) x + c y
+    cplx ro[2][PMAX / 2];
+    unsigned char sched[(PMAX - 1) * (PMAX / 2) * 2];
+    unsigned char slot[(PMAX - 1) * PMAX];
+    unsigned char blk[NOFF * 2];
+    int s_off, s_mc, s_mi, s_stop, s_any;
+    double s_scale;
+};
+
+__device__ __forceinline__ void eig4_pair(const Eig4Smem& sm, bool cross, int r, int k, int& p, int& q) {
+    if (cross) { p = k; q = BSZ + ((k + r) & (BSZ - 1)); }
+    else { p = sm.sched[2 * (r * (PMAX / 2) + k)]; q = sm.sched[2 * (r * (PMAX / 2) + k) + 1]; }
+}
+__device__ __forceinline__ int eig4_slot(const Eig4Smem& sm, bool cross, int r, int i) {
+    if (cross) return i < BSZ ? i : ((i - BSZ - r) & (BSZ - 1));
+    return sm.slot[r * PMAX + i];
+}
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 f2mulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a conj(b)
+__device__ __forceinline__ float2 f2conj(float2 a) { return make_float2(a.x, -a.y); }
+
+// FP32 G' = R G R^H on block (k, l), read from gi, written to go (+ mirror for off-diagonal blocks)
+__device__ __forceinline__ void eig4_block(const float2* gi, float2* go, int pk, int qk, int pl, int ql, float ck, float2 ok,
+                                           float cl, float2 ol, bool diag, bool act) {
+    const float2 g00 = gi[pk * GS + pl], g01 = gi[pk * GS + ql], g10 = gi[qk * GS + pl], g11 = gi[qk * GS + ql];
+    const float2 u0 = f2mul(ok, g10), u1 = f2mul(ok, g11), u2 = f2mul(f2conj(ok), g00), u3 = f2mul(f2conj(ok), g01);
+    const float2 a00 = make_float2(fmaf(g00.x, ck, u0.x), fmaf(g00.y, ck, u0.y));
+    const float2 a01 = make_float2(fmaf(g01.x, ck, u1.x), fmaf(g01.y, ck, u1.y));
+    const float2 a10 = make_float2(fmaf(g10.x, ck, -u2.x), fmaf(g10.y, ck, -u2.y));
+    const float2 a11 = make_float2(fmaf(g11.x, ck, -u3.x), fmaf(g11.y, ck, -u3.y));
+    const float2 v0 = f2mulc(a01, ol), v1 = f2mul(ol, a00), v2 = f2mulc(a11, ol), v3 = f2mul(ol, a10);
+    float2 b00 = make_float2(fmaf(a00.x, cl, v0.x), fmaf(a00.y, cl, v0.y));
+    float2 b01 = make_float2(fmaf(a01.x, cl, -v1.x), fmaf(a01.y, cl, -v1.y));
+    float2 b10 = make_float2(fmaf(a10.x, cl, v2.x), fmaf(a10.y, cl, v2.y));
+    float2 b11 = make_float2(fmaf(a11.x, cl, -v3.x), fmaf(a11.y, cl, -v3.y));
+    if (diag) {
+        b00.y = 0.f; b11.y = 0.f;
+        if (act) { b01 = make_float2(0.f, 0.f); b10 = b01; }
+        go[pk * GS + pl] = b00; go[pk * GS + ql] = b01; go[qk * GS + pl] = b10; go[qk * GS + ql] = b11;
+    } else {
+        go[pk * GS + pl] = b00; go[pk * GS + ql] = b01; go[qk * GS + pl] = b10; go[qk * GS + ql] = b11;
+        go[pl * GS + pk] = f2conj(b00); go[ql * GS + pk] = f2conj(b01); go[pl * GS + qk] = f2conj(b10); go[ql * GS + qk] = f2conj(b11);
+    }
+}
+
+// Eigen-solve of ONE pair by the 512 threads of the calling CTA (same contract as eig3_run).  Returns false --
+// nothing written -- when the squared row norms of the pair span more than 24 decades (numerically null rows of
+// a rank-deficient matrix): their mutual cosines would fall below the FP32 range, the caller then runs eig3_run.
+__device__ __forceinline__ bool eig4_run(Eig4Smem& sm, const double* Gp, int nchunks, cplx* Qp, double tol2, int max_inner,
+                                         float cross_ratio, int cross_only, int bi, int bj, int pair,
+                                         int* __restrict__ notconv, int* __restrict__ rotated,
+                                         double* __restrict__ sig2, long long* tdbg = nullptr) {
+    cplx* g = sm.gd;
+    cplx* q = sm.q;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int n = PMAX, np = PMAX / 2;
+    // ---- load: sum of the per-chunk partial Gram matrices [chunk][PMAX*PMAX*2] in fixed order ----
+    {
+        constexpr int NE = PMAX * PMAX / NTE3;            // entries per thread
+        double re[NE], im[NE];
+#pragma unroll
+        for (int it = 0; it < NE; it++) { re[it] = 0.0; im[it] = 0.0; }
+#pragma unroll 8
+        for (int c = 0; c < nchunks; c++) {                // 2 x 8 independent L2 loads in flight per thread
+#pragma unroll
+            for (int it = 0; it < NE; it++) {
+                const double2 v = __ldcg((const double2*)(Gp + (long long)c * PMAX * PMAX * 2 + 2 * (tid + it * NTE3)));
+                re[it] += v.x; im[it] += v.y;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < NE; it++) {
+            const int e = tid + it * NTE3, i = e / PMAX, j = e % PMAX;
+            g[i * GS + j] = mk(re[it], im[it]);
+            q[i * GS + j] = mk(i == j ? 1.0 : 0.0, 0.0);
+        }
+    }
+    for (int e = tid; e < (n - 1) * np; e += NTE3) {
+        int r = e / np, k = e % np, a, b;
+        circle_pair(r, k, n, a, b);
+        sm.sched[2 * e] = (unsigned char)a;
+        sm.sched[2 * e + 1] = (unsigned char)b;
+        sm.slot[r * PMAX + a] = (unsigned char)k;
+        sm.slot[r * PMAX + b] = (unsigned char)k;
+    }
+    if (tid < NOFF) {
+        int k = 0, rem = tid;
+        while (rem >= np - 1 - k) { rem -= np - 1 - k; k++; }
+        sm.blk[2 * tid] = (unsigned char)k;
+        sm.blk[2 * tid + 1] = (unsigned char)(k + 1 + rem);
+    }
+    if (tid == 0) { sm.s_off = 0; sm.s_mc = 0; sm.s_mi = 0; sm.s_stop = 0; sm.s_any = 0; }
+    __syncthreads();
+    // Fresh Gram matrix (FP64): already diagonal to tolerance?  Largest relative off-diagonal
+    // |g_ij|^2/(g_ii g_jj) among cross-block and intra-block entries decides the schedule.
+    {
+        int offd = 0;
+        float mc = 0.f, mi = 0.f;
+        for (int e = tid; e < n * n; e += NTE3) {
+            const int i = e / n, j = e % n;
+            if (i < j) {
+                const double a = g[i * GS + i].x, b = g[j * GS + j].x;
+                if (a > 0.0 && b > 0.0) {
+                    const double m2 = cabs2(g[i * GS + j]);
+                    if (m2 > tol2 * a * b) {
+                        offd = 1;
+                        const float rel = (float)(m2 / (a * b));
+                        if ((i < BSZ) == (j < BSZ)) mi = fmaxf(mi, rel); else mc = fmaxf(mc, rel);
+                    }
+                }
+            }
+        }
+        if (offd) sm.s_off = 1;
+        if (mc > 0.f) atomicMax(&sm.s_mc, __float_as_int(mc));
+        if (mi > 0.f) atomicMax(&sm.s_mi, __float_as_int(mi));
+    }
+    // scale: largest diagonal entry -> 1 (FP32 range; every entry of a PSD matrix is bounded by it)
+    if (warp == 0) {
+        double d = g[lane * GS + lane].x, dn = d;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+            dn = fmin(dn, __shfl_xor_sync(0xffffffffu, dn, o));
+        }
+        if (lane == 0) sm.s_scale = (d > 0.0 && dn > 1e-24 * d) ? 1.0 / d : -1.0;
+    }
+    __syncthreads();
+    if (sm.s_scale < 0.0 && sm.s_off) return false;        // uniform
+    if (tdbg && threadIdx.x == 0) tdbg[0] = gtimer();      // loaded + scanned
+    const bool cross = cross_only && (__int_as_float(sm.s_mi) <= cross_ratio * __int_as_float(sm.s_mc));
+    const int nrounds = cross ? BSZ : n - 1;
+    const int total = sm.s_off ? max_inner * nrounds : 0;
+    const float tol2f = (float)tol2;
+    if (total > 0) {
+        const double sc = sm.s_scale;
+        for (int e = tid; e < n * n; e += NTE3) {
+            const int i = e / n, j = e % n;
+            const cplx v = g[i * GS + j];
+            sm.gf[0][i * GS + j] = make_float2((float)(v.x * sc), (float)(v.y * sc));
+        }
+        if (tid < n) sm.hd[tid] = 0.5 * sc * g[tid * GS + tid].x;
+    }
+    __syncthreads();
+
+    // FP32 angle of pair slot j for (global) round rr from buffer gb and the FP64 half-diagonal; also advances the
+    // half-diagonal by the rotation (a' = a - T, b' = b + T, T = Re(conj(t) g)).
+    auto make_rotation = [&](const float2* gb, int rr, int j) -> int {
+        int p, qq;
+        eig4_pair(sm, cross, rr % nrounds, j, p, qq);
+        const double ha = sm.hd[p], hb = sm.hd[qq];
+        const float2 gpq = gb[p * GS + qq];
+        float c = 1.f;
+        float2 o = make_float2(0.f, 0.f), t = o;
+        int act = 0;
+        if (ha > 0.0 && hb > 0.0) {
+            // relative test in FP32 on cos = g / sqrt(a b) (a b itself may underflow FP32)
+            const float ra = rsqrtf(2.f * (float)ha), rb = rsqrtf(2.f * (float)hb);
+            const float cx = gpq.x * ra * rb, cy = gpq.y * ra * rb;
+            if (fmaf(cx, cx, cy * cy) > tol2f) {
+                float ddf = (float)(hb - ha);                  // dd = (b - a) / 2 from the FP64 half-diagonal
+                // local power-of-two scale: the squares below must not underflow for numerically null rows
+                const float m = fmaxf(fabsf(ddf), fmaxf(fabsf(gpq.x), fabsf(gpq.y)));
+                const int ex = (__float_as_int(m) >> 23) & 0xff;
+                const float s2 = __int_as_float((254 - (ex > 0 ? (ex < 253 ? ex : 253) : 1)) << 23);
+                ddf *= s2;
+                const float gx = gpq.x * s2, gy = gpq.y * s2;
+                const float mag2 = fmaf(gx, gx, gy * gy);
+                const float hh = fmaf(ddf, ddf, mag2);
+                const float den = fabsf(ddf) + sqrtf(hh);
+                const float inv = copysignf(__frcp_rn(den), ddf);
+                t = make_float2(gx * inv, gy * inv);            // |t| <= 1, scale free
+                c = rsqrtf(fmaf(t.x, t.x, fmaf(t.y, t.y, 1.f)));
+                o = make_float2(-t.x * c, -t.y * c);
+                act = 1;
+                // T = Re(conj(t) g) in unscaled units; half-diagonal moves by T / 2
+                const double T2 = 0.5 * (double)fmaf(t.x, gpq.x, t.y * gpq.y);
+                sm.hd[p] = ha - T2;
+                sm.hd[qq] = hb + T2;
+            }
+        }
+        sm.rcf[rr & 1][j] = c;
+        sm.rof[rr & 1][j] = o;
+        sm.rt[rr & 1][j] = t;
+        sm.ract[rr & 3][j] = act;
+        return act;
+    };
+
+    int sweep_any = 0;
+    if (total > 0 && warp == 0) {
+        int act = 0;
+        if (lane < np) act = make_rotation(sm.gf[0], 0, lane);
+        sweep_any = __any_sync(0xffffffffu, act);
+    }
+    __syncthreads();
+    if (tdbg && threadIdx.x == 0) { tdbg[1] = gtimer(); tdbg[4] = total; }      // converted, first angles
+    // warp roles: 0 = pivots + next angles; 1,2,3,5 = off-diagonal blocks (FP32); 6 = exact rotations (FP64);
+    // 4, 7..15 = Q (FP64), 320 threads
+    const int bw = warp == 5 ? 3 : warp - 1;
+    const bool is_blk = warp == 1 || warp == 2 || warp == 3 || warp == 5;
+    const bool is_q = warp == 4 || warp >= 7;
+    const int qtid = (warp == 4 ? 0 : warp - 6) * 32 + lane;
+    // iteration `it`: G update of round it (FP32) and the angles of round it+1; exact rotation of round it; Q update
+    // of round it-1.  nG = rounds that run (shrinks when an inner sweep ends without a rotation); one drain iteration.
+    int nG = total;
+    long long cyc[6] = {0, 0, 0, 0, 0, 0};               // timing study (tdbg): cycles per phase, lane 0 of warps 0 / 6 / 7
+    for (int it = 0; it < nG + 1; it++) {
+        const bool g_live = it < nG;
+        const int r = it % nrounds, cur = it & 1;
+        const long long ck0 = tdbg ? clock64() : 0;
+        if (g_live && warp == 0) {
+            const float2* gi = sm.gf[cur];
+            float2* go = sm.gf[cur ^ 1];
+            const bool have_next = it + 1 < total;
+            int k, l;
+            const bool diag = lane < np;
+            if (diag) { k = lane; l = lane; }
+            else {
+                int p2 = 0, q2 = 0;
+                eig4_pair(sm, cross, (it + 1) % nrounds, lane - np, p2, q2);
+                const int k1 = eig4_slot(sm, cross, r, p2), k2 = eig4_slot(sm, cross, r, q2);
+                k = k1 < k2 ? k1 : k2;
+                l = k1 < k2 ? k2 : k1;
+            }
+            if (diag || (have_next && k != l)) {
+                int pk, qk, pl, ql;
+                eig4_pair(sm, cross, r, k, pk, qk);
+                eig4_pair(sm, cross, r, l, pl, ql);
+                eig4_block(gi, go, pk, qk, pl, ql, sm.rcf[cur][k], sm.rof[cur][k], sm.rcf[cur][l], sm.rof[cur][l], diag,
+                           sm.ract[it & 3][k] != 0);
+            }
+            __syncwarp();
+            if (tdbg) cyc[0] += clock64() - ck0;
+            if (have_next) {
+                if ((it + 1) % nrounds == 0) {             // an inner sweep just ended
+                    if (!sweep_any) { if (lane == 0) sm.s_stop = 1; }
+                    sweep_any = 0;
+                }
+                int act = 0;
+                if (lane < np) act = make_rotation(go, it + 1, lane);
+                sweep_any |= __any_sync(0xffffffffu, act);
+            }
+            if (tdbg) cyc[1] += clock64() - ck0;
+        } else if (g_live && is_blk) {
+            const int t = bw * 32 + lane;
+            if (t < NOFF) {
+                const int k = sm.blk[2 * t], l = sm.blk[2 * t + 1];
+                int pk, qk, pl, ql;
+                eig4_pair(sm, cross, r, k, pk, qk);
+                eig4_pair(sm, cross, r, l, pl, ql);
+                eig4_block(sm.gf[cur], sm.gf[cur ^ 1], pk, qk, pl, ql, sm.rcf[cur][k], sm.rof[cur][k], sm.rcf[cur][l],
+                           sm.rof[cur][l], false, false);
+            }
+        } else if (g_live && warp == 6) {
+            // exact unitary rotation of round `it` from its FP32 tangent: c = 1/sqrt(1+|t|^2), o = -t c
+            if (lane < np) {
+                const int j = lane;
+                double c = 1.0;
+                cplx o = mk(0.0, 0.0);
+                if (sm.ract[it & 3][j]) {
+                    const float2 t = sm.rt[cur][j];
+                    const double tx = (double)t.x, ty = (double)t.y;
+                    const double x = fma(tx, tx, fma(ty, ty, 1.0));          // in [1, 2]
+                    const double y0 = (double)rsqrtf((float)x);
+                    const double e = fma(-x * y0, y0, 1.0);                  // 1 - x y0^2, |e| ~ 2^-22
+                    c = fma(y0 * e, fma(0.375, e, 0.5), y0);                 // y0 (1 + e/2 + 3 e^2/8): error ~ e^3
+                    o = mk(-tx * c, -ty * c);
+                }
+                sm.rc[cur][j] = c;
+                sm.ro[cur][j] = o;
+            }
+            if (tdbg) cyc[2] += clock64() - ck0;
+        } else if (is_q && it >= 1) {
+            // Q' = R(it-1) Q in FP64
+            const int rq = it - 1, rr_ = rq % nrounds, cq = rq & 1;
+            for (int item = qtid; item < np * PMAX; item += 320) {
+                const int k = item >> 5, col = item & 31;
+                if (sm.ract[rq & 3][k]) {
+                    int pk, qk;
+                    eig4_pair(sm, cross, rr_, k, pk, qk);
+                    const double ck = sm.rc[cq][k];
+                    const cplx ok = sm.ro[cq][k];
+                    const cplx x = q[pk * GS + col], y = q[qk * GS + col];
+                    q[pk * GS + col] = cadd(cscale(x, ck), cmul(ok, y));
+                    q[qk * GS + col] = csub(cscale(y, ck), cmul(cconj(ok), x));
+                }
+            }
+            if (tdbg) cyc[3] += clock64() - ck0;
+        }
+        if (tid == 32 && g_live) {
+            int any = 0;
+#pragma unroll
+            for (int j = 0; j < np; j++) any |= sm.ract[it & 3][j];
+            if (any) sm.s_any = 1;
+        }
+        __syncthreads();
+        if (tdbg) cyc[4] += clock64() - ck0;
+        if (g_live && sm.s_stop) nG = it + 1;              // uniform: read after the barrier
+    }
+    if (tdbg) {
+        // lane 0 of warps 0 (block, block+angles, whole iteration), 6 (exact rotation), 7 (Q) report through shared memory
+        double* scr = (double*)sm.gd;                      // the FP64 Gram copy is dead by now (sig2 reads it only if !s_any)
+        __syncthreads();
+        if (tid == 0) { scr[600] = (double)cyc[0]; scr[601] = (double)cyc[1]; scr[604] = (double)cyc[4]; }
+        if (tid == 6 * 32) scr[602] = (double)cyc[2];
+        if (tid == 7 * 32) scr[603] = (double)cyc[3];
+        __syncthreads();
+        if (tid == 0) { tdbg[6] = (long long)scr[600]; tdbg[7] = (long long)scr[601]; tdbg[8] = (long long)scr[602];
+                        tdbg[9] = (long long)scr[603]; tdbg[10] = (long long)scr[604]; }
+    }
+    if (tdbg && threadIdx.x == 0) { tdbg[2] = gtimer(); tdbg[5] = nG; }         // rotations done
+    for (int e = tid; e < n * n; e += NTE3) Qp[e] = q[(e / n) * GS + (e % n)];
+    if (tid < n) {
+        const int row = tid < BSZ ? bi * BSZ + tid : bj * BSZ + (tid - BSZ);
+        // rotated rows: the FP64-tracked diagonal (approximate, not final); untouched pairs: the fresh Gram diagonal
+        sig2[row] = (sm.s_any && sm.s_scale > 0.0) ? 2.0 * sm.hd[tid] / sm.s_scale : g[tid * GS + tid].x;
+    }
+    if (tid == 0) {
+        rotated[pair] = sm.s_any;
+        if (sm.s_off) {
+            atomicAdd(notconv, 1);
+            const int mx = sm.s_mc > sm.s_mi ? sm.s_mc : sm.s_mi;
+            atomicMax(notconv + 2, mx);
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(NTE3)
+k_eig3(double* __restrict__ G, int nchunks, cplx* __restrict__ Qout, double tol2, int max_inner, float cross_ratio,
+       int cross_only, PairSpec ps, int slot_base, int* __restrict__ notconv, int* __restrict__ rotated,
+       double* __restrict__ sig2, const int* __restrict__ done, int mixed) {
+    pdl_wait();
+    pdl_trigger();
+    if (done && *done) return;      // static (sync-free) mode: this SVD already converged
+    extern __shared__ __align__(16) unsigned char eig_smem[];
+    const int pair = slot_base + blockIdx.x;
+    int bi, bj;
+    get_pair(ps, blockIdx.x, bi, bj);
+    if (mixed && eig4_run(*reinterpret_cast<Eig4Smem*>(eig_smem), G + (long long)pair * nchunks * PMAX * PMAX * 2, nchunks,
+                          Qout + (long long)pair * PMAX * PMAX, tol2, max_inner, cross_ratio, cross_only, bi, bj, pair,
+                          notconv, rotated, sig2))
+        return;
+    __syncthreads();
+    {
+        eig3_run(*reinterpret_cast<Eig3Smem*>(eig_smem), G + (long long)pair * nchunks * PMAX * PMAX * 2, nchunks,
+                 Qout + (long long)pair * PMAX * PMAX, tol2, max_inner, cross_ratio, cross_only, bi, bj, pair, notconv,
+                 rotated, sig2);
     }
 }
 
@@ -697,24 +1076,20 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // tiles (tile row w/2, tile columns 2(w%2), 2(w%2)+1) and runs over the whole chunk, so there is no
 // cross-warp reduction: the warp stores its tiles straight into the chunk's partial slab, which
 // k_eig sums over chunks.  A lane's 16-byte load W[row][k] is both an A and a B operand.
-__global__ void __launch_bounds__(NT)
-k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, PairSpec ps, int slot_base,
-           double* __restrict__ G, const int* __restrict__ done) {
-    pdl_wait();
-    pdl_trigger();
-    if (done && *done) return;      // static (sync-free) mode: this SVD already converged
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = slot_base + blockIdx.y;
+// One 8-warp team: partial Gram of the pair's 32 rows over columns [c0, c1) -> slab Gp [PMAX*PMAX*2] (plain stores).
+template <bool CG>
+__device__ __forceinline__ cplx ldw_(const cplx* p) { return CG ? __ldcg(p) : *p; }
+
+template <bool CG>
+__device__ __forceinline__ void gram_mma_part(const cplx* W, long long ldw, int bi, int bj, long long c0,
+                                              long long c1, double* __restrict__ Gp, int warp, int lane) {
     const int g = lane >> 2, t = lane & 3;
-    int bi, bj;
-    get_pair(ps, blockIdx.y, bi, bj);
     const int mt = warp >> 1, nt0 = (warp & 1) * 2;
     auto rowptr = [&](int r) { return W + (long long)(r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ)) * ldw; };
     const cplx* pa = rowptr(mt * 8 + g);
     const cplx* pb0 = rowptr(nt0 * 8 + g);
     const cplx* pb1 = rowptr(nt0 * 8 + 8 + g);
     double cr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, ci[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-    const long long c0 = (long long)blockIdx.x * chunk;
-    const long long c1 = (c0 + chunk < len) ? c0 + chunk : len;
     // register double-buffering, prefetch distance PF k-steps (operands come from L2)
     constexpr int PF = 4;
     cplx fa[PF], fb0[PF], fb1[PF];
@@ -722,9 +1097,9 @@ k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, PairSp
     for (int s = 0; s < PF; s++) {
         const long long col = c0 + 4 * s + t;
         const bool ok = col < c1;
-        fa[s] = ok ? pa[col] : mk(0.0, 0.0);
-        fb0[s] = ok ? pb0[col] : mk(0.0, 0.0);
-        fb1[s] = ok ? pb1[col] : mk(0.0, 0.0);
+        fa[s] = ok ? ldw_<CG>(pa + col) : mk(0.0, 0.0);
+        fb0[s] = ok ? ldw_<CG>(pb0 + col) : mk(0.0, 0.0);
+        fb1[s] = ok ? ldw_<CG>(pb1 + col) : mk(0.0, 0.0);
     }
     for (long long k0 = c0; k0 < c1; k0 += 4 * PF) {
 #pragma unroll
@@ -736,17 +1111,17 @@ k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, PairSp
             fb0[s] = ok ? pb0[col] : mk(0.0, 0.0);
             fb1[s] = ok ? pb1[col] : mk(0.0, 0.0);
             // W_m conj(W_n): re = ar*br + ai*bi ; im = ai*br - ar*bi   (zero operands past c1 add nothing)
+            // (four independent accumulators back to back, then their second products: same order per accumulator)
             dmma884(cr[0][0], cr[0][1], wa.x, wb0.x);
-            dmma884(cr[0][0], cr[0][1], wa.y, wb0.y);
             dmma884(ci[0][0], ci[0][1], wa.y, wb0.x);
-            dmma884(ci[0][0], ci[0][1], -wa.x, wb0.y);
             dmma884(cr[1][0], cr[1][1], wa.x, wb1.x);
-            dmma884(cr[1][0], cr[1][1], wa.y, wb1.y);
             dmma884(ci[1][0], ci[1][1], wa.y, wb1.x);
+            dmma884(cr[0][0], cr[0][1], wa.y, wb0.y);
+            dmma884(ci[0][0], ci[0][1], -wa.x, wb0.y);
+            dmma884(cr[1][0], cr[1][1], wa.y, wb1.y);
             dmma884(ci[1][0], ci[1][1], -wa.x, wb1.y);
         }
     }
-    double* Gp = G + ((long long)pair * gridDim.x + blockIdx.x) * PMAX * PMAX * 2;
 #pragma unroll
     for (int j = 0; j < 2; j++) {
         const int row = mt * 8 + g, col = (nt0 + j) * 8 + 2 * t;
@@ -755,31 +1130,32 @@ k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, PairSp
     }
 }
 
-// Wext[rows] <- Q Wext[rows]: each warp owns 8-column strips, loads the 32x8 strip as B
-// fragments, multiplies by Q (A fragments from padded shared planes) and stores in place.
-__global__ void __launch_bounds__(NT, 2)
-k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, PairSpec ps, int slot_base,
-            const cplx* __restrict__ Q, const int* __restrict__ rotated, const int* __restrict__ done) {
+// G = W_pair W_pair^H over a column chunk.  Each of the 8 warps owns two of the sixteen 8x8 output
+// tiles (tile row w/2, tile columns 2(w%2), 2(w%2)+1) and runs over the whole chunk, so there is no
+// cross-warp reduction: the warp stores its tiles straight into the chunk's partial slab, which
+// k_eig sums over chunks.  A lane's 16-byte load W[row][k] is both an A and a B operand.
+__global__ void __launch_bounds__(NT)
+k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, PairSpec ps, int slot_base,
+           double* __restrict__ G, const int* __restrict__ done) {
     pdl_wait();
     pdl_trigger();
     if (done && *done) return;      // static (sync-free) mode: this SVD already converged
-    const int pair = slot_base + blockIdx.y;
-    if (!rotated[pair]) return;
-    constexpr int QS = PMAX + 4;
-    __shared__ double qr[PMAX * QS], qi[PMAX * QS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
+    const int tid = threadIdx.x, pair = slot_base + blockIdx.y;
     int bi, bj;
     get_pair(ps, blockIdx.y, bi, bj);
-    const cplx* Qp = Q + (long long)pair * PMAX * PMAX;
-    for (int e = tid; e < PMAX * PMAX; e += NT) {
-        cplx v = Qp[e];
-        qr[(e / PMAX) * QS + (e % PMAX)] = v.x;
-        qi[(e / PMAX) * QS + (e % PMAX)] = v.y;
-    }
-    __syncthreads();
     const long long c0 = (long long)blockIdx.x * chunk;
-    const long long c1 = (c0 + chunk < lenx) ? c0 + chunk : lenx;
+    const long long c1 = (c0 + chunk < len) ? c0 + chunk : len;
+    gram_mma_part<false>(W, ldw, bi, bj, c0, c1, G + ((long long)pair * gridDim.x + blockIdx.x) * PMAX * PMAX * 2,
+                         tid >> 5, tid & 31);
+}
+
+// One 8-warp team: rows <- Q rows over columns [c0, c1): each warp owns 8-column strips (stride 64), loads the 32x8
+// strip as B fragments, multiplies by Q (A fragments from the padded shared planes qr / qi) and stores in place.
+constexpr int QS = PMAX + 4;
+template <bool CG>
+__device__ __forceinline__ void apply_mma_part(cplx* W, long long ldw, int bi, int bj, long long c0,
+                                               long long c1, const double* qr, const double* qi, int warp, int lane) {
+    const int g = lane >> 2, t = lane & 3;
     // software pipeline: the next strip's B fragments are in flight while the current one is multiplied
     long long n0 = c0 + warp * 8;
     cplx b[8];
@@ -790,7 +1166,7 @@ k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, Pair
         for (int kt = 0; kt < 8; kt++) {
             int r = kt * 4 + t;
             long long row = r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ);
-            b[kt] = ok ? W[row * ldw + col] : mk(0.0, 0.0);
+            b[kt] = ok ? ldw_<CG>(W + row * ldw + col) : mk(0.0, 0.0);
         }
     }
     while (n0 < c1) {
@@ -803,23 +1179,32 @@ k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, Pair
             for (int kt = 0; kt < 8; kt++) {
                 int r = kt * 4 + t;
                 long long row = r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ);
-                bn[kt] = ok ? W[row * ldw + col] : mk(0.0, 0.0);
+                bn[kt] = ok ? ldw_<CG>(W + row * ldw + col) : mk(0.0, 0.0);
             }
         }
         double cr[4][2], ci[4][2];
 #pragma unroll
         for (int mt = 0; mt < 4; mt++) { cr[mt][0] = cr[mt][1] = ci[mt][0] = ci[mt][1] = 0.0; }
 #pragma unroll
-        for (int kt = 0; kt < 8; kt++)
+        for (int kt = 0; kt < 8; kt++) {
+            // eight independent accumulators back to back, then their second products (same order per accumulator)
+            double ar[4], ai[4];
 #pragma unroll
             for (int mt = 0; mt < 4; mt++) {
-                double ar = qr[(mt * 8 + g) * QS + kt * 4 + t];
-                double ai = qi[(mt * 8 + g) * QS + kt * 4 + t];
-                dmma884(cr[mt][0], cr[mt][1], ar, b[kt].x);
-                dmma884(cr[mt][0], cr[mt][1], -ai, b[kt].y);
-                dmma884(ci[mt][0], ci[mt][1], ar, b[kt].y);
-                dmma884(ci[mt][0], ci[mt][1], ai, b[kt].x);
+                ar[mt] = qr[(mt * 8 + g) * QS + kt * 4 + t];
+                ai[mt] = qi[(mt * 8 + g) * QS + kt * 4 + t];
             }
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+                dmma884(cr[mt][0], cr[mt][1], ar[mt], b[kt].x);
+                dmma884(ci[mt][0], ci[mt][1], ar[mt], b[kt].y);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+                dmma884(cr[mt][0], cr[mt][1], -ai[mt], b[kt].y);
+                dmma884(ci[mt][0], ci[mt][1], ai[mt], b[kt].x);
+            }
+        }
 #pragma unroll
         for (int mt = 0; mt < 4; mt++) {
             int r = mt * 8 + g;
@@ -833,6 +1218,167 @@ k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, Pair
 #pragma unroll
         for (int kt = 0; kt < 8; kt++) b[kt] = bn[kt];
         n0 = n1;
+    }
+}
+
+// Wext[rows] <- Q Wext[rows]
+__global__ void __launch_bounds__(NT, 2)
+k_apply_mma(cplx* __restrict__ W, long long ldw, long long lenx, int chunk, PairSpec ps, int slot_base,
+            const cplx* __restrict__ Q, const int* __restrict__ rotated, const int* __restrict__ done) {
+    pdl_wait();
+    pdl_trigger();
+    if (done && *done) return;      // static (sync-free) mode: this SVD already converged
+    const int pair = slot_base + blockIdx.y;
+    if (!rotated[pair]) return;
+    __shared__ double qr[PMAX * QS], qi[PMAX * QS];
+    const int tid = threadIdx.x;
+    int bi, bj;
+    get_pair(ps, blockIdx.y, bi, bj);
+    const cplx* Qp = Q + (long long)pair * PMAX * PMAX;
+    for (int e = tid; e < PMAX * PMAX; e += NT) {
+        cplx v = Qp[e];
+        qr[(e / PMAX) * QS + (e % PMAX)] = v.x;
+        qi[(e / PMAX) * QS + (e % PMAX)] = v.y;
+    }
+    __syncthreads();
+    const long long c0 = (long long)blockIdx.x * chunk;
+    const long long c1 = (c0 + chunk < lenx) ? c0 + chunk : lenx;
+    apply_mma_part<false>(W, ldw, bi, bj, c0, c1, qr, qi, tid >> 5, tid & 31);
+}
+
+// ---------------------------------------------------------------------------------
+// Fused Jacobi round (round 2).  The three kernels of a round (Gram, eigen-solve, update) and the two
+// cross-stream hand-overs between them cost more than the work itself on matrices of the MPS path (a 1024 x 1024
+// round: ~7 us of Gram, ~25 us of eigen-solve, ~10 us of update, but ~60 us per round measured; 6 launches and 8
+// event calls per round on the host).  Here a round is ONE cooperative launch over all pairs:
+//   grid = (chunks, pairs), 512 threads = two 8-warp teams.
+//   1. each team forms the pair's partial Gram matrix over its sub-chunk of columns -> slab (plain stores);
+//   2. ticket per pair: the LAST CTA of a pair to arrive solves the 32 x 32 eigen-problem (eig3_run), writes Q,
+//      and releases the pair's flag (epoch = round number); the other CTAs of the pair spin on the flag
+//      (cooperative launch: every CTA is resident, so the wait cannot deadlock);
+//   3. each team applies Q to its sub-chunk of columns.
+// Reproducible: the slabs are summed in fixed order whichever CTA arrives last.
+// ---------------------------------------------------------------------------------
+constexpr int NTR = 512;
+struct RoundSmem {
+    union {
+        Eig3Smem e;
+        Eig4Smem e4;
+        struct { double qr[PMAX * QS], qi[PMAX * QS]; } a;
+    };
+    int s_last;
+};
+constexpr size_t EIG34_SMEM = sizeof(Eig3Smem) > sizeof(Eig4Smem) ? sizeof(Eig3Smem) : sizeof(Eig4Smem);
+
+// grid-wide barrier of a cooperative launch (all CTAs resident): monotonically increasing counter, no reset
+__device__ __forceinline__ void round_grid_barrier(unsigned int* bar, unsigned int& target, unsigned int nblocks) {
+    __syncthreads();
+    target += nblocks;
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // publish this CTA's rows of W
+        atomicAdd(bar, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while ((int)(v - target) < 0);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Rounds [r_begin, r_end) of one sweep in ONE cooperative launch (a grid barrier between rounds: the launch gap of
+// ~10 us per round was a fifth of the round).  W is read with ld.global.cg throughout: other SMs rewrite it between
+// rounds of the same launch.
+template <bool DBG>
+__global__ void __launch_bounds__(NTR, 1)
+k_round(cplx* W, long long ldw, int len, long long lenx, int chunk_g, int chunk_a, int nbp, int r_begin, int r_end,
+        double* G, cplx* Q, double tol2, int max_inner, float cross_ratio, int cross_only, int* notconv, int* rotated,
+        double* sig2, unsigned int* ticket, unsigned int* flag, unsigned int* bar, unsigned int epoch0,
+        unsigned int bar0, int mixed, long long* dbg) {
+    // dbg (QM_ROUND_DEBUG=1): per-CTA sums of phase durations in ns: [0] gram, [1] ticket, [2] wait (waiters), [11] eig
+    // (solvers), [3] update, [4..8] inside the eigen-solve (load+scan, convert, rotations, write-back, rounds),
+    // [9] rounds, [10] eigen-solves, [12..15] cycles of the mixed-precision loop phases
+    extern __shared__ __align__(16) unsigned char eig_smem[];
+    RoundSmem& sm = *reinterpret_cast<RoundSmem*>(eig_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, team = warp >> 3, w8 = warp & 7;
+    const int pair = blockIdx.y, nch = gridDim.x, nslab = 2 * nch;
+    const unsigned int nblocks = gridDim.x * gridDim.y;
+    double* Gp = G + (long long)pair * nslab * PMAX * PMAX * 2;
+    cplx* Qp = Q + (long long)pair * PMAX * PMAX;
+    unsigned int bar_target = bar0;
+    for (int r = r_begin; r < r_end; r++) {
+        long long tt[4] = {0, 0, 0, 0}, te[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (DBG && tid == 0) tt[0] = gtimer();
+        const PairSpec ps = {0, r, nbp, 0, 0};
+        const unsigned int epoch = epoch0 + (unsigned int)(r - r_begin);
+        int bi, bj;
+        get_pair(ps, pair, bi, bj);
+        // ---- 1. partial Gram matrices ----
+        {
+            const int sub = 2 * blockIdx.x + team;
+            long long c0 = (long long)sub * chunk_g;
+            if (c0 > len) c0 = len;                        // an empty range still writes its (zero) slab
+            const long long c1 = (c0 + chunk_g < len) ? c0 + chunk_g : len;
+            gram_mma_part<true>(W, ldw, bi, bj, c0, c1, Gp + (long long)sub * PMAX * PMAX * 2, w8, lane);
+        }
+        __syncthreads();
+        if (DBG && tid == 0) tt[1] = gtimer();
+        if (tid == 0) {
+            __threadfence();                               // the CTA's slabs before its ticket
+            const unsigned int t = atomicAdd(&ticket[pair], 1u);
+            sm.s_last = (t == (unsigned int)nch - 1u);
+            if (sm.s_last) ticket[pair] = 0u;              // every CTA of the pair has drawn its ticket
+        }
+        __syncthreads();
+        if (DBG && tid == 0) tt[2] = gtimer();
+        const bool was_last = sm.s_last != 0;
+        if (was_last) {
+            // ---- 2. eigen-solve by the last CTA of the pair ----
+            __threadfence();
+            if (!(mixed && eig4_run(sm.e4, Gp, nslab, Qp, tol2, max_inner, cross_ratio, cross_only, bi, bj, pair, notconv,
+                                    rotated, sig2, DBG ? te : nullptr))) {
+                __syncthreads();
+                eig3_run(sm.e, Gp, nslab, Qp, tol2, max_inner, cross_ratio, cross_only, bi, bj, pair, notconv, rotated, sig2);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag + pair), "r"(epoch) : "memory");
+        } else {
+            if (tid == 0) {
+                unsigned int v;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag + pair) : "memory");
+                } while (v != epoch);
+            }
+        }
+        __syncthreads();
+        if (DBG && tid == 0) tt[3] = gtimer();
+        // ---- 3. update ----
+        if (__ldcg(rotated + pair)) {
+            for (int e = tid; e < PMAX * PMAX; e += NTR) {
+                const cplx v = __ldcg(Qp + e);
+                sm.a.qr[(e / PMAX) * QS + (e % PMAX)] = v.x;
+                sm.a.qi[(e / PMAX) * QS + (e % PMAX)] = v.y;
+            }
+            __syncthreads();
+            const int sub = 2 * blockIdx.x + team;
+            const long long c0 = (long long)sub * chunk_a;
+            const long long c1 = (c0 + chunk_a < lenx) ? c0 + chunk_a : lenx;
+            apply_mma_part<true>(W, ldw, bi, bj, c0, c1, sm.a.qr, sm.a.qi, w8, lane);
+        }
+        if (DBG) {
+            __syncthreads();
+            if (tid == 0) {
+                const long long t4 = gtimer();
+                long long* d = dbg + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 16;
+                d[0] += tt[1] - tt[0]; d[1] += tt[2] - tt[1]; d[was_last ? 11 : 2] += tt[3] - tt[2]; d[3] += t4 - tt[3]; d[9] += 1;
+                if (was_last && te[0]) {
+                    d[4] += te[0] - tt[2]; d[5] += te[1] - te[0]; d[6] += te[2] - te[1]; d[7] += tt[3] - te[2];
+                    d[8] += te[5]; d[10] += 1; d[12] += te[6]; d[13] += te[7]; d[14] += te[8]; d[15] += te[9];
+                }
+            }
+        }
+        if (r + 1 < r_end) round_grid_barrier(bar, bar_target, nblocks);     // rows of W and the shared-memory union
     }
 }
 
@@ -1090,7 +1636,7 @@ constexpr int MAXCH = 32;     // Gram partial slots per pair (DMMA path)
 constexpr int MAXCH1 = 64;    // Gram slabs of the single-block path
 
 struct Work {
-    cplx* W; double* G; cplx* Q; int* rotated; double* sig2; int* perm; int* notconv; cplx* T;
+    cplx* W; double* G; cplx* Q; int* rotated; double* sig2; int* perm; int* notconv; cplx* T; unsigned int* sync;
     size_t total;
 };
 
@@ -1111,6 +1657,7 @@ Work carve(const Geom& g, void* base) {
     w.sig2 = (double*)(b + off); off += align_up((size_t)g.nvp * sizeof(double));
     w.perm = (int*)(b + off); off += align_up((size_t)g.nvp * sizeof(int));
     w.notconv = (int*)(b + off); off += align_up(4 * sizeof(int));   // [0] not-converged count, [1] done flag, [2] max rel off-diag^2 (float bits)
+    w.sync = (unsigned int*)(b + off); off += align_up((2 * (size_t)g.npairs + 1) * sizeof(unsigned int));   // fused rounds: ticket[], flag[], grid barrier
     w.total = off;
     return w;
 }
@@ -1193,10 +1740,10 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
     };
     const double tol2 = tol * tol;
     static bool eig_attr_set = false;
-    static int eig_version = 3;        // QM_EIG=1 selects the first formulation for the 32-row pairs too (A/B runs)
+    static int eig_version = 3;        // 32-row pairs: 3 = FP64 (eig3_run, default), 4 = mixed precision (eig4_run: measured slower in situ), 1 = round-1 kernel
     if (!eig_attr_set) {
         QM_CUDA(cudaFuncSetAttribute(k_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIG_SMEM));
-        QM_CUDA(cudaFuncSetAttribute(k_eig3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Eig3Smem)));
+        QM_CUDA(cudaFuncSetAttribute(k_eig3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIG34_SMEM));
         if (getenv("QM_EIG")) eig_version = atoi(getenv("QM_EIG"));
         eig_attr_set = true;
     }
@@ -1220,6 +1767,8 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
     const int* donep = is_static ? w.notconv + 1 : nullptr;
     if (is_static) max_sweeps = fixed_sweeps;
     QM_CUDA(cudaMemsetAsync(w.notconv, 0, 4 * sizeof(int), st));
+    QM_CUDA(cudaMemsetAsync(w.sync, 0, (2 * (size_t)g.npairs + 1) * sizeof(unsigned int), st));
+    unsigned int fused_barriers = 0;                       // grid barriers passed so far in this SVD
     // a sweep that STARTS below `early` (largest |cos| between rows) ends near early^2 (quadratic regime): no
     // verification sweep after it.  QM_SVD_EARLY overrides for experiments.
     static const float early = getenv("QM_SVD_EARLY") ? (float)atof(getenv("QM_SVD_EARLY")) : 1e-9f;
@@ -1269,6 +1818,36 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
             phases[nphases++] = {1, q, q, q, {a1, a1 + q, a2, a2 + q}, {b1 + q, b1, b2 + q, b2}};
         }
     }
+    // Fused schedule (eager mode, multi-block): one cooperative launch per round over all pairs (k_round).
+    static int sched_fused = -1, round_capacity = 0;
+    if (sched_fused < 0) {
+        const char* e5 = getenv("QM_SVD_SCHED");
+        sched_fused = !(e5 && strcmp(e5, "grouped") == 0);
+        int dev = 0, n_sm = 0, per_sm = 0;
+        QM_CUDA(cudaGetDevice(&dev));
+        QM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        QM_CUDA(cudaFuncSetAttribute(k_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem)));
+        QM_CUDA(cudaFuncSetAttribute(k_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem)));
+        QM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_round<false>, NTR, sizeof(RoundSmem)));
+        round_capacity = n_sm * per_sm;
+    }
+    int fused_nch = 0;
+    if (sched_fused && !g.single && !is_static && g.npairs <= round_capacity) {
+        fused_nch = round_capacity / g.npairs;
+        if (fused_nch > MAXCH / 2) fused_nch = MAXCH / 2;               // 2 slabs per CTA, MAXCH slabs per pair
+        const int by_len = g.len / 128 > 1 ? g.len / 128 : 1;           // at least 64 Gram columns per 8-warp team
+        if (fused_nch > by_len) fused_nch = by_len;
+    }
+    const bool fused = fused_nch > 0;
+    // QM_ROUND_DEBUG=1: per-CTA phase timings of k_round accumulated over this SVD, printed at its end
+    static const int round_debug = getenv("QM_ROUND_DEBUG") ? atoi(getenv("QM_ROUND_DEBUG")) : 0;
+    static long long* round_dbg_buf = nullptr;
+    long long* round_dbg = nullptr;
+    if (round_debug && fused) {
+        if (!round_dbg_buf) QM_CUDA(cudaMalloc(&round_dbg_buf, 4096 * 16 * sizeof(long long)));
+        round_dbg = round_dbg_buf;
+        QM_CUDA(cudaMemsetAsync(round_dbg, 0, 4096 * 16 * sizeof(long long), st));
+    }
     const int npl = grouped ? g.npairs / NG : g.npairs;         // pairs per DMMA launch
     long long chunk_g = g.single ? pick_chunk(g.len) : gram_chunk(npl);
     if (g.single && (g.len + chunk_g - 1) / chunk_g > MAXCH1) chunk_g = ((g.len + MAXCH1 - 1) / MAXCH1 + TC - 1) / TC * TC;
@@ -1288,13 +1867,14 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
                 w.W, g.ldw, g.len, (int)chunk_g, ps, slot, w.G, donep));
         };
         auto launch_eig = [&](const PairSpec& ps, int np, int slot, cudaStream_t s) {
-            if (eig_version == 3 && !g.single) {
-                if (is_static) QM_LAUNCH(QM_CLS_SVD_EIG, s, k_eig3<<<np, NTE3, sizeof(Eig3Smem), s>>>(
+            if (eig_version >= 3 && !g.single) {
+                const int mixed = eig_version == 4;
+                if (is_static) QM_LAUNCH(QM_CLS_SVD_EIG, s, k_eig3<<<np, NTE3, EIG34_SMEM, s>>>(
                     w.G, eig_chunks, w.Q, tol2, max_inner, tune_ratio, cross_only, ps, slot, w.notconv, w.rotated,
-                    w.sig2, donep));
-                else QM_LAUNCH(QM_CLS_SVD_EIG, s, qm_launch_dep(k_eig3, dim3(np), dim3(NTE3), sizeof(Eig3Smem), s,
+                    w.sig2, donep, mixed));
+                else QM_LAUNCH(QM_CLS_SVD_EIG, s, qm_launch_dep(k_eig3, dim3(np), dim3(NTE3), EIG34_SMEM, s,
                     w.G, eig_chunks, w.Q, tol2, max_inner, tune_ratio, cross_only, ps, slot, w.notconv, w.rotated,
-                    w.sig2, donep));
+                    w.sig2, donep, mixed));
                 return;
             }
             if (is_static) QM_LAUNCH(QM_CLS_SVD_EIG, s, k_eig<<<np, NTE, EIG_SMEM, s>>>(
@@ -1310,7 +1890,37 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
             else QM_LAUNCH(QM_CLS_SVD_APPLY, s, qm_launch_dep(k_apply_mma, dim3(nca, np), dim3(NT), 0, s,
                 w.W, g.ldw, lenx, (int)chunk_a, ps, slot, w.Q, w.rotated, donep));
         };
-        if (grouped) {
+        if (fused) {
+            const int nteams = 2 * fused_nch;
+            int cg = (int)(((g.len + nteams - 1) / nteams + 31) / 32 * 32);
+            int ca = (int)(((lenx + nteams - 1) / nteams + 63) / 64 * 64);
+            unsigned int* ticket = w.sync;
+            unsigned int* flag = w.sync + g.npairs;
+            {
+                // every round of the sweep in one cooperative launch (QM_SVD_ROUNDS_PER_LAUNCH limits it for A/B runs)
+                static const int rpl = getenv("QM_SVD_ROUNDS_PER_LAUNCH") ? atoi(getenv("QM_SVD_ROUNDS_PER_LAUNCH")) : 1 << 20;
+                unsigned int* bar = w.sync + 2 * g.npairs;
+                const unsigned int nblocks = (unsigned int)fused_nch * (unsigned int)g.npairs;
+                for (int r0 = 0; r0 < g.rounds; r0 += rpl) {
+                    int r1 = r0 + rpl < g.rounds ? r0 + rpl : g.rounds;
+                    int rb = r0;
+                    unsigned int epoch0 = (unsigned int)(sweeps * g.rounds + r0 + 1);
+                    unsigned int bar0 = fused_barriers * nblocks;
+                    fused_barriers += (unsigned int)(r1 - r0 - 1);
+                    cplx* Wp = w.W; long long ldw = g.ldw; int len = g.len; long long lx = lenx; int nbp = g.nbp;
+                    double* Gp = w.G; cplx* Qp = w.Q; double t2 = tol2; int mi = max_inner; float cr = tune_ratio;
+                    int co = cross_only; int* nc = w.notconv; int* rot = w.rotated; double* s2 = w.sig2;
+                    int mixed = eig_version == 4;
+                    long long* dbg = round_dbg;
+                    void* args[] = {&Wp, &ldw, &len, &lx, &cg, &ca, &nbp, &rb, &r1, &Gp, &Qp, &t2, &mi, &cr, &co, &nc, &rot,
+                                    &s2, &ticket, &flag, &bar, &epoch0, &bar0, &mixed, &dbg};
+                    QM_LAUNCH(QM_CLS_SVD_ROUND, st, cudaLaunchCooperativeKernel(
+                        dbg ? (void*)k_round<true> : (void*)k_round<false>, dim3(fused_nch, g.npairs), dim3(NTR), args,
+                        sizeof(RoundSmem), st));
+                }
+            }
+            qm_prof_work(QM_CLS_SVD_ROUND, 8.0 * g.nrows * g.nrows * ((double)g.len + (double)lenx) * g.npairs * g.rounds);
+        } else if (grouped) {
             for (int ph = 0; ph < nphases; ph++) {
                 const Phase& P = phases[ph];
                 bool pending[MAXG] = {false, false, false, false};
@@ -1368,8 +1978,10 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
             }
         }
         // complex MAC = 8 flops: Gram nrows^2 x len, update nrows^2 x lenx, per pair and round
-        qm_prof_work(QM_CLS_SVD_GRAM, 8.0 * g.nrows * g.nrows * (double)g.len * g.npairs * g.rounds);
-        qm_prof_work(QM_CLS_SVD_APPLY, 8.0 * g.nrows * g.nrows * (double)lenx * g.npairs * g.rounds);
+        if (!fused) {
+            qm_prof_work(QM_CLS_SVD_GRAM, 8.0 * g.nrows * g.nrows * (double)g.len * g.npairs * g.rounds);
+            qm_prof_work(QM_CLS_SVD_APPLY, 8.0 * g.nrows * g.nrows * (double)lenx * g.npairs * g.rounds);
+        }
         QM_CHECK_LAUNCH();
         sweeps++;
         if (is_static) {
@@ -1384,6 +1996,23 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         float mx;
         memcpy(&mx, &h[2], sizeof(float));
         if (h[0] == 0 || mx <= early2) { converged = 1; break; }
+    }
+    if (round_dbg) {
+        const int ncta = fused_nch * g.npairs;
+        long long* h = (long long*)malloc((size_t)ncta * 16 * sizeof(long long));
+        QM_CUDA(cudaMemcpyAsync(h, round_dbg, (size_t)ncta * 16 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        QM_CUDA(cudaStreamSynchronize(st));
+        double sum[16] = {0};
+        for (int c = 0; c < ncta; c++)
+            for (int k = 0; k < 16; k++) sum[k] += (double)h[c * 16 + k];
+        free(h);
+        const double nl = sum[9] > 0 ? sum[9] : 1, ne = sum[10] > 0 ? sum[10] : 1, nw = nl - ne > 0 ? nl - ne : 1;
+        fprintf(stderr, "[k_round %dx%d nch=%d sweeps=%d] per CTA-launch (us): gram %.2f ticket %.2f wait %.2f (waiters) eig-total %.2f (solvers) update %.2f | "
+                        "eig: load+scan %.2f convert %.2f rotations %.2f write+flag %.2f rounds %.1f | cycles/round: w0 block %.0f w0 block+angles %.0f prep %.0f Q %.0f\n",
+                m, n, fused_nch, sweeps, sum[0] / nl * 1e-3, sum[1] / nl * 1e-3, sum[2] / nw * 1e-3, sum[11] / ne * 1e-3, sum[3] / nl * 1e-3,
+                sum[4] / ne * 1e-3, sum[5] / ne * 1e-3, sum[6] / ne * 1e-3, sum[7] / ne * 1e-3, sum[8] / ne,
+                sum[12] / (sum[8] > 0 ? sum[8] : 1), sum[13] / (sum[8] > 0 ? sum[8] : 1), sum[14] / (sum[8] > 0 ? sum[8] : 1),
+                sum[15] / (sum[8] > 0 ? sum[8] : 1));
     }
     if (is_static && mismatch) QM_LAUNCH(QM_CLS_SMALL, st, k_static_check<<<1, 1, 0, st>>>(w.notconv, mismatch));
     if (info_host) { info_host[0] = sweeps; info_host[1] = converged; }

@@ -23,7 +23,7 @@ def test_library_builds_and_exports_header_symbols():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     assert lib.qm_version() == 100
-    assert lib.qm_prof_num_classes() == 10
+    assert lib.qm_prof_num_classes() == 11
 
 
 def test_binding_table_matches_header():

@@ -96,3 +96,60 @@ def test_circuit_emission_convention():
     from oracle import qmprs_oracle as O
     layers = [[(0, 2, mats)]]
     assert np.abs(circ.get_statevector() - O.circuit_state(layers, n)).max() < 1e-14
+
+
+def test_ket_snake_and_compress_hand_computed():
+    """base.py:99-102 pre-processing (quick Ket.change_indexing / Ket.compress), hand-computed examples.
+    snake: the register read as a 2 x 2^(n-1) image, every second row reversed (boustrophedon);
+    compress: the smallest `p` percent of the amplitudes (by modulus) are zeroed, the rest renormalised."""
+    v = np.arange(1, 9, dtype=float)                      # 3 qubits: rows [1 2 3 4], [5 6 7 8]
+    k = Ket(v)
+    k.change_indexing("snake")
+    want = np.array([1, 2, 3, 4, 8, 7, 6, 5], dtype=float)
+    assert np.allclose(k.data, want / np.linalg.norm(want), atol=1e-15)
+    k.change_indexing("snake")                             # an involution
+    assert np.allclose(k.data, v / np.linalg.norm(v), atol=1e-15)
+    k2 = Ket([1.0, 2.0, 3.0, 4.0])                         # fewer than 3 qubits: unchanged
+    k2.change_indexing("snake")
+    assert np.allclose(k2.data, np.array([1, 2, 3, 4]) / np.sqrt(30.0))
+    k.change_indexing("row")
+    assert np.allclose(k.data, v / np.linalg.norm(v), atol=1e-15)
+    # compress: 8 amplitudes, 37.5 % -> the 3 smallest moduli (1, -2, 3j) go to zero
+    w = np.array([5, 1, -2, 3j, 4, 6, -7, 8j], dtype=complex)
+    k3 = Ket(w)
+    k3.compress(37.5)
+    kept = np.array([5, 0, 0, 0, 4, 6, -7, 8j], dtype=complex)
+    assert np.allclose(k3.data, kept / np.linalg.norm(kept), atol=1e-15)
+    k4 = Ket(w)
+    k4.compress(0.0)
+    assert np.allclose(k4.data, w / np.linalg.norm(w), atol=1e-15)
+
+
+def test_prepare_state_preprocessing_branches_are_applied_in_reference_order():
+    """base.py:96-104: Ket wrap -> change_indexing -> compress -> MPS -> prepare_mps, observed through a stub
+    encoder (no device needed)."""
+    from qmprs_b200.synthesis.mps_encoding.base import MPSEncoder
+    import qmprs_b200.synthesis.mps_encoding.base as base_mod
+    seen = {}
+
+    class FakeMPS:
+        def __init__(self, statevector, bond_dimension):
+            seen["data"] = np.array(statevector.data)
+            seen["chi"] = bond_dimension
+
+    class Stub(MPSEncoder):
+        def prepare_mps(self, mps, **kwargs):
+            seen["kwargs"] = kwargs
+            return "circuit"
+
+    old = base_mod.MPS
+    base_mod.MPS = FakeMPS
+    try:
+        v = np.array([5, 1, -2, 3, 4, 6, -7, 8], dtype=complex)
+        out = Stub(GateListCircuit).prepare_state(v, 16, compression_percentage=25.0, index_type="snake", num_layers=3)
+    finally:
+        base_mod.MPS = old
+    snake = np.array([5, 1, -2, 3, 8, -7, 6, 4], dtype=complex)
+    snake[[1, 2]] = 0                                       # 25 % of 8 = the two smallest moduli
+    assert out == "circuit" and seen["chi"] == 16 and seen["kwargs"] == {"num_layers": 3}
+    assert np.allclose(seen["data"], snake / np.linalg.norm(snake), atol=1e-15)
