@@ -505,7 +505,7 @@ def measure_batch(args, wl, env, steps, warmup, main_line):
     n, chi, L, S = wl["n"], wl["chi"], wl["layers"], wl["sweeps"]
     B = args.batch or wl["batch"]
     states = np.stack([rand_state(n, s) for s in range(B)])          # seed = state index
-    prep = GraphedPreparer(n, chi, L, S, lanes=args.lanes, device=str(dev)) if args.lanes > 0 else None
+    prep = GraphedPreparer(n, chi, L, S, lanes=args.lanes, device=str(dev), width=args.width) if args.lanes > 0 else None
     sdev = torch.from_numpy(states).to(dev)
     small = 2 * world * max(args.lanes, 1)
     for w in range(max(warmup, 1)):
@@ -548,8 +548,11 @@ def measure_batch(args, wl, env, steps, warmup, main_line):
         for s in range(4):
             host.prepare(K, sdev[s], n, chi, L, S)
         roof = roofline_from_profile(K.prof_end(), peak_tf)
+        if roof.get("kernel") == "k_env_fused":
+            roof["kernel"] = "k_sweeps_small (all sweeps of a state in one CTA, vectors in shared memory)"
         roof["note"] = ("eager instrumented pass over 4 states; the timed region replays the same kernels from CUDA "
-                        "graphs, where launch latency (not any pipe) bounds a 12-qubit state")
+                        "graphs, where launch latency (not any pipe) bounds a 12-qubit state; the sweeps kernel works "
+                        "out of shared memory, so its HBM fraction is not a utilisation figure")
     if world == 1 and not args.no_cpu_baseline:
         pool = CpuBatchPool(wl)
         v, cores, nst, wall = pool.sample(per_core=2, first_seed=0)
@@ -575,7 +578,7 @@ def measure_batch(args, wl, env, steps, warmup, main_line):
         "dtype": "c128", "data": "synthetic", "config": cfg,
         "fidelity_mean": fid, "cpu_baseline": cpu, "clocks": clk, "roofline": roof,
         "gpu_launches": launches,
-        "graph": ({"lanes": args.lanes, "kernel_nodes_per_state": prep.nodes_per_graph,
+        "graph": ({"lanes": args.lanes, "states_per_graph": prep.width, "kernel_nodes_per_state": prep.nodes_per_graph,
                    "eager_fallbacks": prep.fallbacks} if prep else None),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 16 * 2 ** n),
                 "d2h_bytes_per_step": int(world * ((B + world - 1) // world) * rl * 8)},
@@ -586,6 +589,7 @@ def measure_batch(args, wl, env, steps, warmup, main_line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lanes", type=int, default=32, help="concurrent CUDA-graph lanes per GPU for --workload c5 (0 = eager)")
+    ap.add_argument("--width", type=int, default=16, help="states per captured graph (advanced in lock step) in the batch workload")
     ap.add_argument("--batch", type=int, default=0, help="states per step for the batch workload (default: config 5's 4096)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

@@ -112,6 +112,34 @@ int qm_chi2_first(const void* T0, void* Csite, void* stream);
 int qm_complete_unitaries(const void* C, const void* bond, int n_sites, void* gates, void* kinds, void* bad,
                           double sign_tol, void* stream);
 
+/* ---- fused bookkeeping for small registers (bonds <= 64; one kernel instead of a group of launches: a batch of
+ * small states replayed from CUDA graphs is bound by the number of kernel nodes) -------------------------------- */
+
+/* qm_trim + qm_expect_ints + 2 x qm_scale_copy: rank by the cutoff (mode 0 'rel' + max_bond, singular values absorbed
+ * to the left: left = U S, right = Vh; mode 1 'rsum2' + Frobenius renormalisation, sqrt absorbed on both sides),
+ * outputs in the shapes of the ASSUMED rank expect_rank (left: m x expect, right: expect x n, contiguous);
+ * mismatch[0] = 1 if the data give another rank.  quimb _trim_and_renorm_svd_result + absorb behind mps.py:242,
+ * :451-453, :968-971. */
+int qm_split_absorb(const void* U, long long ldu, const void* S, const void* Vh, long long ldvh, int m, int n, int k,
+                    double cutoff, int mode, int max_bond, int expect_rank, void* left, void* right, void* mismatch,
+                    void* stream);
+
+/* qm_zgemm + qm_theta_gate: X (2l x 2r) = M (A A2), A: (l,2,b), A2: (b,2,r), M = G or G^H (mps.py:968-971). */
+int qm_theta_small(const void* A, const void* A2, int l, int b, int r, const void* G, int dagger, void* X, void* stream);
+
+/* chi=2 truncation (mps.py:881), fast path through left environments: qm_chi2_env: Lout (r x r) =
+ * sum_p B[:,p,:]^H Lprev B[:,p,:] (Lprev NULL = identity; B: (l,2,r)); qm_chi2_bond: one bond -- M = L T, H = T^H M,
+ * rank <= 2 selection with the canonical phase rule (as qm_chi2_select, squared = 2), Tout (l0 x 4) = Bprev (T Vsel). */
+int qm_chi2_env(const void* Lprev, const void* B, int l, int r, void* Lout, void* stream);
+int qm_chi2_bond(const void* L, int b, const void* T, const void* Bprev, int l0, double cutoff, double tie,
+                 double ambiguous_rel, void* Csite, void* bond, void* ambiguous, void* Tout, void* stream);
+
+/* <0..0|psi> as the product of the p = 0 slices of all sites in one launch (mps.py:1020-1039).  sites: HOST array of
+ * device pointers to the (l,2,r) tensors; dims: HOST int[n_sites+1] bond sizes; out: complex[1]; with tol >= 0 the
+ * early-break test |f - 1| <= tol (sequential.py:390) must NOT fire, else mismatch[0] = 1. */
+int qm_zero_overlap(const void* const* sites, const int* dims, int n_sites, double tol, void* out, void* mismatch,
+                    void* stream);
+
 /* out (r,2,l) = in (l,2,r) with the bond axes swapped: mirror image of a site tensor, used
  * for the left-handed canonicalize/compress variants (mps.py:396, :451-453 with mode="left"). */
 int qm_reverse3(void* out, const void* in, int l, int r, void* stream);

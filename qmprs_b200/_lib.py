@@ -38,6 +38,11 @@ SIGNATURES = {
     "qm_chi2_select": (_i, [_vp, _vp, _ll, _d, _d, _vp, _vp, _vp, _i, _d, _vp, _vp]),
     "qm_chi2_first": (_i, [_vp, _vp, _vp]),
     "qm_complete_unitaries": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _vp]),
+    "qm_split_absorb": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _d, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "qm_theta_small": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "qm_chi2_env": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "qm_chi2_bond": (_i, [_vp, _i, _vp, _vp, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
+    "qm_zero_overlap": (_i, [ctypes.POINTER(_vp), _ip, _i, _d, _vp, _vp, _vp]),
     "qm_reverse3": (_i, [_vp, _vp, _i, _i, _vp]),
     "qm_conj_scale_copy": (_i, [_vp, _vp, _ll, _i, _d, _vp]),
     "qm_vdot_out_doubles": (_i, []),

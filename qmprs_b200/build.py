@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "gemm.cu", "svd.cu", "qr.cu", "mps_ops.cu", "dense.cu", "dense_small.cu", "dense_persist.cu", "small_svd.cu")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "gemm.cu", "svd.cu", "qr.cu", "mps_ops.cu", "dense.cu", "dense_small.cu", "dense_persist.cu", "small_svd.cu", "small_mps.cu")]
 OUT = os.path.join(HERE, "libqmprs_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -23,7 +23,8 @@ def needs_build() -> bool:
         return True
     t = os.path.getmtime(OUT)
     deps = SRC + [os.path.join(ROOT, "include", "qmprs_b200.h"), os.path.join(HERE, "csrc", "common.cuh"),
-            os.path.join(HERE, "csrc", "polar.cuh"), os.path.join(HERE, "csrc", "small_linalg.cuh")]
+            os.path.join(HERE, "csrc", "polar.cuh"), os.path.join(HERE, "csrc", "small_linalg.cuh"),
+            os.path.join(HERE, "csrc", "chi2_select.cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -10,6 +10,7 @@
 //   qm_complete_unitaries _generate_{first,two,last}_site_unitary, generate_unitary_layer  :565-847
 #include "common.cuh"
 #include "small_linalg.cuh"
+#include "chi2_select.cuh"
 #include "qmprs_b200.h"
 
 namespace {
@@ -131,59 +132,7 @@ __global__ void k_chi2_select(const double* __restrict__ S, const cplx* __restri
                               double cutoff, double tie, cplx* __restrict__ Csite, cplx* __restrict__ Vsel,
                               int* __restrict__ bond, int squared, double amb_rel, int* __restrict__ ambiguous) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int n = 0;
-    double sv[4];
-    cplx vh_local[4][4];
-    if (squared == 2) {
-        // Vh points at the 4x4 Hermitian PSD matrix H = T^H L T itself: one-sided Jacobi on its columns
-        // gives H V = U Sigma with Sigma = eigenvalues and V = eigenvectors; sort descending.
-        cplx A[4][4], V[4][4];
-        for (int i = 0; i < 4; i++)
-            for (int j = 0; j < 4; j++) { A[i][j] = Vh[(long long)i * ldvh + j]; V[i][j] = mk(i == j ? 1.0 : 0.0, 0.0); }
-        jacobi_cols(A, V, 4);
-        double lam[4];
-        int ord[4] = {0, 1, 2, 3};
-        for (int j = 0; j < 4; j++) {
-            double s2 = 0.0;
-            for (int i = 0; i < 4; i++) s2 += cabs2(A[i][j]);
-            lam[j] = sqrt(s2);
-        }
-        for (int a = 0; a < 3; a++)
-            for (int b = a + 1; b < 4; b++)
-                if (lam[ord[b]] > lam[ord[a]]) { int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
-        for (int j = 0; j < 4; j++) {
-            sv[j] = sqrt(lam[ord[j]]);
-            for (int c = 0; c < 4; c++) vh_local[j][c] = cconj(V[c][ord[j]]);
-        }
-    } else {
-        for (int j = 0; j < 4; j++) {
-            sv[j] = squared ? sqrt(S[j] > 0.0 ? S[j] : 0.0) : S[j];
-            for (int c = 0; c < 4; c++) vh_local[j][c] = Vh[(long long)j * ldvh + c];
-        }
-    }
-    if (squared && ambiguous && sv[1] <= amb_rel * sv[0]) ambiguous[0] = 1;
-    double thr = cutoff * sv[0];
-    for (int j = 0; j < 4; j++) n += (sv[j] > thr) ? 1 : 0;
-    if (n < 1) n = 1;
-    if (n > 2) n = 2;
-    for (int j = 0; j < 2; j++) {
-        cplx row[4];
-        for (int c = 0; c < 4; c++) row[c] = (j < n) ? vh_local[j][c] : mk(0.0, 0.0);
-        if (j < n) {
-            double mx = 0.0;
-            for (int c = 0; c < 4; c++) { double a = cabs2(row[c]); mx = a > mx ? a : mx; }
-            int pick = 0;
-            for (int c = 0; c < 4; c++) if (cabs2(row[c]) >= (1.0 - tie) * mx) { pick = c; break; }
-            double a = sqrt(cabs2(row[pick]));
-            cplx ph = (a > 0.0) ? mk(row[pick].x / a, row[pick].y / a) : mk(1.0, 0.0);
-            for (int c = 0; c < 4; c++) row[c] = cmulc(row[c], ph);      // row / ph
-        }
-        for (int c = 0; c < 4; c++) {
-            Csite[j * 4 + c] = row[c];
-            Vsel[c * 2 + j] = cconj(row[c]);
-        }
-    }
-    bond[0] = n;
+    chi2_select_dev(S, Vh, ldvh, cutoff, tie, Csite, Vsel, bond, squared, amb_rel, ambiguous);
 }
 
 // site 0 of the chi=2 MPS: C0 = T0 / ||T0||  (T0 is 1 x 2 x 2 padded -> 4 entries)

@@ -85,11 +85,58 @@ class _Lane:
         return tag, res, state
 
 
+class _BatchLane:
+    """One captured graph that extracts the layers of ``width`` states in LOCK STEP on one stream
+    (:func:`qmprs_b200.host.prepare_layers_lockstep`).  A lane executes its kernels one after the other and the
+    kernels of a small register are single CTAs, so a lane with one state per graph keeps ONE SM busy -- and the
+    hardware runs at most 32 lanes side by side (work queues).  Measured on config 5 (profiles/bench_r02_c5_*.json):
+    cutting the kernel nodes per state from 1814 to 691 moved the throughput by 10 %, and forking a graph into
+    parallel per-state branches by nothing: the bound was the per-lane chain of single-CTA SVDs (23 of the ~28 ms of
+    kernel time of a state).  In lock step the SVD of every split is ONE launch with grid = width."""
+
+    def __init__(self, device, n, chi, L, threshold, sample_state, width=8):
+        self.n, self.L, self.width = n, L, int(width)
+        dim, M, W = 2 ** n, L * n, int(width)
+        self.K = K = CudaKernels(device)
+        self.stream = torch.cuda.Stream(device)
+        self.psi_in = torch.empty((W, dim), dtype=torch.complex128, device=device)
+        self.gates_out = torch.empty((W, M, 16), dtype=torch.complex128, device=device)
+        self.target_out = torch.empty((W, dim), dtype=torch.complex128, device=device)
+        self.flags = torch.zeros(W + 1, dtype=torch.int32, device=device)
+        sample = torch.from_numpy(sample_state)
+
+        def pipeline():
+            K.begin_static()
+            work = [K.scale_copy(self.psi_in[w].reshape(-1, 1)).reshape(-1) for w in range(W)]
+            res = host.prepare_layers_lockstep(K, work, n, chi, L, threshold, self.flags)
+            for w, (gates, kinds, A) in enumerate(res):
+                if len(kinds) != L:
+                    raise RuntimeError("static capture produced an unexpected layer count")
+                self.gates_out[w].copy_(gates)
+                self.target_out[w].copy_(host.to_dense(K, A))         # sequential.py:440 (mps.mps)
+            K.end_static()
+            return res[0][1]
+
+        with torch.cuda.stream(self.stream):
+            for w in range(W):
+                self.psi_in[w].copy_(sample)
+            pipeline()                                     # uncaptured warm-up: lazy initialisation, attribute calls
+        self.stream.synchronize()
+        if int(self.flags.max().item()) != 0:
+            raise RuntimeError("static assumptions do not hold for the sample state")
+        n0 = K.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self.kinds = pipeline()
+        self.nodes = (K.launch_count() - n0) / W           # kernel nodes per state
+        self.done = torch.cuda.Event()
+
+
 class GraphedPreparer:
     """``prepare_state`` for a stream of equally sized states through captured CUDA graphs."""
 
     def __init__(self, n_qubits, bond_dimension, num_layers=1, num_sweeps=0, threshold=1 - 1e-6, lanes=4,
-                 device=None, split="svd"):
+                 device=None, split="svd", width=8):
         if not isinstance(num_layers, int) or num_layers < 1:
             raise ValueError("The number of layers must be a positive integer.")
         if device is None:
@@ -102,13 +149,17 @@ class GraphedPreparer:
         self.split = split
         self._sample = sample
         self.n_lanes = int(lanes)
+        self.width = max(1, int(width))      # states per graph of the batch path (advanced in lock step)
         self._full = None                    # lanes whose graph is the whole pipeline (run: one state at a time)
         self._layers = None                  # lanes whose graph stops before the sweeps (run_into: batches)
         self.eager = get_kernels(device)
-        # batches of registers whose sweeps fit one SM's shared memory: per-state graphs extract the layers, then
-        # ONE k_sweeps_small launch (grid = batch) sweeps every state and returns its fidelity
-        self.defer = (self.cfg[0] <= CudaKernels.SMALL_SWEEP_MAX_SITES
-                      and self.cfg[0] * self.cfg[2] <= CudaKernels.SMALL_SWEEP_MAX_GATES)
+        # batches of registers whose sweeps fit one SM's shared memory and whose bonds fit the small-register kernels:
+        # graphs of `width` states in lock step extract the layers, then ONE k_sweeps_small launch (grid = batch)
+        # sweeps every state and returns its fidelity
+        nq = self.cfg[0]
+        self.defer = (split == "svd" and nq <= CudaKernels.SMALL_SWEEP_MAX_SITES and self.cfg[1] >= 1
+                      and nq * self.cfg[2] <= CudaKernels.SMALL_SWEEP_MAX_GATES
+                      and min(2 ** (nq // 2), self.cfg[1]) <= CudaKernels.FUSED_MAX_BOND)
         self.fallbacks = 0
         self.replays = 0
 
@@ -121,7 +172,8 @@ class GraphedPreparer:
     @property
     def layer_lanes(self):
         if self._layers is None:
-            self._layers = [_Lane(self.device, *self.cfg, self._sample, split=self.split, defer_sweeps=True)
+            n, chi, L, S, thr = self.cfg
+            self._layers = [_BatchLane(self.device, n, chi, L, thr, self._sample, width=self.width)
                             for _ in range(self.n_lanes)]
         return self._layers
 
@@ -168,28 +220,45 @@ class GraphedPreparer:
         flags = torch.zeros(B, dtype=torch.int32, device=dev)
         ready = torch.cuda.Event()
         ready.record(main)
-        lanes = self.layer_lanes if self.defer else self.lanes
-        nl = len(lanes)
-        for lane in lanes[:min(nl, B)]:
-            lane.stream.wait_event(ready)
         if self.defer:
+            lanes = self.layer_lanes
+            nl, wd = len(lanes), self.width
             gates_b = torch.empty((B, L * n, 16), dtype=torch.complex128, device=dev)
             targets_b = torch.empty((B, 2 ** n), dtype=torch.complex128, device=dev)
-        for s in range(B):
-            lane = lanes[s % nl]
-            with torch.cuda.stream(lane.stream):
-                lane.psi_in.copy_(sdev[s], non_blocking=True)
-                lane.mismatch.zero_()
-                lane.graph.replay()
-                if self.defer:
-                    gates_b[s].copy_(lane.gates, non_blocking=True)
-                    targets_b[s].copy_(lane.target, non_blocking=True)
-                else:
+            ngroups = (B + wd - 1) // wd
+            gflags = torch.zeros((ngroups, wd + 1), dtype=torch.int32, device=dev)
+            used = lanes[:min(nl, ngroups)]
+            for lane in used:
+                lane.stream.wait_event(ready)
+            for gi, g0 in enumerate(range(0, B, wd)):
+                lane = lanes[gi % nl]
+                w = min(wd, B - g0)
+                with torch.cuda.stream(lane.stream):
+                    lane.psi_in[:w].copy_(sdev[g0:g0 + w], non_blocking=True)
+                    if w < wd:                             # ragged tail: idle slots redo the last state
+                        lane.psi_in[w:].copy_(sdev[g0 + w - 1].expand(wd - w, -1), non_blocking=True)
+                    lane.flags.zero_()
+                    lane.graph.replay()
+                    gates_b[g0:g0 + w].copy_(lane.gates_out[:w], non_blocking=True)
+                    targets_b[g0:g0 + w].copy_(lane.target_out[:w], non_blocking=True)
+                    gflags[gi].copy_(lane.flags, non_blocking=True)
+        else:
+            lanes = self.lanes
+            nl = len(lanes)
+            used = lanes[:min(nl, B)]
+            for lane in used:
+                lane.stream.wait_event(ready)
+            for s in range(B):
+                lane = lanes[s % nl]
+                with torch.cuda.stream(lane.stream):
+                    lane.psi_in.copy_(sdev[s], non_blocking=True)
+                    lane.mismatch.zero_()
+                    lane.graph.replay()
                     rec_dev[s, :ng].copy_(lane.gates.view(torch.float64).reshape(-1), non_blocking=True)
                     rec_dev[s, ng + nk + 1:ng + nk + 3].copy_(lane.ov, non_blocking=True)
-                flags[s:s + 1].copy_(lane.mismatch, non_blocking=True)
+                    flags[s:s + 1].copy_(lane.mismatch, non_blocking=True)
         self.replays += B
-        for lane in lanes[:min(nl, B)]:
+        for lane in used:
             lane.done.record(lane.stream)
             main.wait_event(lane.done)
         if self.defer:
@@ -199,7 +268,12 @@ class GraphedPreparer:
                                     batch=B, psis=sdev, overlaps=ov)
             rec_dev[:B, :ng] = gates_b.view(torch.float64).reshape(B, ng)
             rec_dev[:B, ng + nk + 1:ng + nk + 3] = ov
-        bad = np.nonzero(flags.cpu().numpy())[0]
+        if self.defer:
+            gf = gflags.cpu().numpy()
+            per_state = (gf[:, :wd] | gf[:, wd:wd + 1]).reshape(-1)[:B]      # own flag or the group's
+            bad = np.nonzero(per_state)[0]
+        else:
+            bad = np.nonzero(flags.cpu().numpy())[0]
         for s in bad:                                      # an assumption failed: eager path, exact semantics
             st = host_states[s] if host_states is not None else sdev[s]
             res = host.prepare(self.eager, st, n, chi, L, S, thr, split=self.split)

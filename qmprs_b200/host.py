@@ -53,6 +53,13 @@ def bond_dims(A):
     return [int(a.shape[2]) for a in A[:-1]]
 
 
+def _fused_small(K, A):
+    """Static (CUDA-graph) mode on a register whose bonds all fit the fused small-register kernels
+    (csrc/small_mps.cu): a batch of such states is bound by the number of kernel nodes, not by arithmetic."""
+    return (getattr(K, "static", False) and getattr(K, "fused_small", True) and hasattr(K, "split_absorb")
+            and max(int(a.shape[0]) for a in A) <= K.FUSED_MAX_BOND and max(int(a.shape[2]) for a in A) <= K.FUSED_MAX_BOND)
+
+
 def copy_mps(K, A):
     return [K.scale_copy(a.reshape(a.shape[0] * 2, a.shape[2])).reshape(a.shape) for a in A]
 
@@ -134,9 +141,13 @@ def chi2_layer(K, B, debug=None, accurate=False):
     SVD of R_{i-1} T_i itself.
     """
     N = len(B)
+    fused = not accurate and _fused_small(K, B)
     facs = [None] * (N - 1)        # R_i (accurate) or L_i (fast)
     prev = None
     for i in range(N - 1):
+        if fused:
+            prev = facs[i] = K.chi2_env(prev, B[i])        # L_i in one launch
+            continue
         l, _, r = B[i].shape
         if accurate:
             M = B[i].reshape(l * 2, r) if prev is None else K.gemm(prev, B[i].reshape(l, 2 * r)).reshape(-1, r)
@@ -157,6 +168,9 @@ def chi2_layer(K, B, debug=None, accurate=False):
     Vh4 = K.zeros((4, 4))
     Vsel = K.zeros((4, 2))
     for i in range(N - 1, 0, -1):
+        if fused:
+            T = K.chi2_bond(facs[i - 1], T, B[i - 1], C[i], bond[i - 1:i], ambiguous)
+            continue
         M = K.gemm(facs[i - 1], T)                         # R T (k x 4)  or  L T (b x 4)
         if accurate:
             if M.shape[0] < 4:
@@ -230,8 +244,12 @@ def apply_inverse_layer(K, B, gates, kinds, spectra=None, inverse=True, split="s
             else:
                 l, _, b = B[i].shape
                 _, _, r = B[i + 1].shape
-                X = K.gemm(B[i].reshape(l * 2, b), B[i + 1].reshape(b, 2 * r))
-                K.theta_gate(X, l, r, G, dagger=inverse)
+                fused = split == "svd" and _fused_small(K, [B[i], B[i + 1]])
+                if fused:
+                    X = K.theta_small(B[i], B[i + 1], G, dagger=inverse)
+                else:
+                    X = K.gemm(B[i].reshape(l * 2, b), B[i + 1].reshape(b, 2 * r))
+                    K.theta_gate(X, l, r, G, dagger=inverse)
                 if split == "exact":
                     if 2 * l <= 2 * r:
                         B[i] = K.eye(2 * l).reshape(l, 2, 2 * l)
@@ -244,6 +262,11 @@ def apply_inverse_layer(K, B, gates, kinds, spectra=None, inverse=True, split="s
                 k = S.shape[0]
                 if spectra is not None:
                     spectra.append(S)
+                if fused:
+                    left, right = K.split_absorb(U, S, Vh, CUTOFF, MODE_RSUM2, 0, k)
+                    B[i] = left.reshape(l, 2, k)
+                    B[i + 1] = right.reshape(k, 2, r)
+                    continue
                 rank, f = K.trim(S, k, CUTOFF, MODE_RSUM2)
                 n = K.read_int(rank, expect=k)
                 B[i] = K.scale_copy(U[:, :n], S, f, mode=2, half_power=True).reshape(l, 2, n)
@@ -258,6 +281,9 @@ def zero_overlap(K, B, break_tol=None):
     """conj(psi[0]) as a product of the p=0 slices (only element 0 of the dense vector is used).
     With ``break_tol`` the value only feeds the early-break test (sequential.py:390); in the
     kernels' static mode that test is validated on the device and None is returned."""
+    if _fused_small(K, B):
+        K.zero_overlap_fused(B, break_tol if break_tol is not None else -1.0)
+        return None
     v = B[0][:, 0, :]
     for i in range(1, len(B)):
         v = K.gemm(v, B[i][:, 0, :])
@@ -331,6 +357,12 @@ def from_dense_truncated(K, psi, n_sites, chi, spectra=None):
         k = S.shape[0]
         if spectra is not None:
             spectra.append(S)
+        if getattr(K, "static", False) and getattr(K, "fused_small", True) and hasattr(K, "split_absorb"):
+            n = min(k, chi) if chi else k
+            T, right = K.split_absorb(U, S, Vh, CUTOFF, MODE_REL, chi or 0, n)
+            A[i] = right.reshape(n, 2, r)
+            r = n
+            continue
         rank, _ = K.trim(S, k, CUTOFF, MODE_REL, chi or 0)
         n = K.read_int(rank, expect=min(k, chi) if chi else k)
         A[i] = K.scale_copy(Vh[:n]).reshape(n, 2, r)
@@ -397,6 +429,93 @@ def prepare_layers_device(K, psi, n_sites, chi, num_layers, threshold=1 - 1e-6, 
     A = build_mps(K, psi, int(n_sites), chi, record, fused)
     gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record, split)
     return gates_all, layer_kinds, overlaps, A
+
+
+def prepare_layers_lockstep(K, psis, n_sites, chi, num_layers, threshold, flags):
+    """:func:`prepare_layers_device` for W small states AT ONCE in the static (CUDA-graph) mode of one stream.
+    A graph lane executes its kernels one after the other, and the kernels of a small register are single CTAs:
+    one state per lane keeps one SM busy.  Here the W states advance in lock step -- same shapes by the static
+    assumptions -- so that the dominant kernel, the single-CTA Jacobi SVD, is launched ONCE per split for all W
+    (grid = W); the cheap bookkeeping kernels stay per state.  ``flags``: int32[W + 1] device vector, flags[w] is
+    state w's "an assumption failed" flag, flags[W] the group's (a batched SVD did not converge).
+    Returns [(gates_all, kinds per layer, MPS)] per state; ``psis`` are normalised in place."""
+    assert K.static and chi
+    W, N = len(psis), int(n_sites)
+    grp = flags[W:W + 1]
+
+    def per_state(w):
+        K.mismatch = flags[w:w + 1]
+
+    for w in range(W):
+        per_state(w)
+        K.div_sqrt(psis[w], K.vdot(psis[w], psis[w]))                 # quick Ket normalisation
+    # ---- A1 + A2: TT-SVD in Schmidt form with max_bond (from_dense_truncated) ----
+    A = [[None] * N for _ in range(W)]
+    r = 1
+    X = K.empty((W, 2 ** (N - 1), 2))
+    for w in range(W):
+        K.scale_copy(psis[w].reshape(-1, 2), out=X[w])
+    for i in range(N - 1, 0, -1):
+        m, nn = 2 ** i, 2 * r
+        k = min(m, nn)
+        K.mismatch = grp
+        U, S, Vh = K.svd_small_batch(X, backmult=True)
+        n = min(k, chi)
+        Xn = K.empty((W, m // 2, 2 * n)) if i > 1 else None
+        Tl = []
+        for w in range(W):
+            per_state(w)
+            left, right = K.split_absorb(U[w], S[w], Vh[w], CUTOFF, MODE_REL, chi, n, out_left=None if Xn is None else Xn[w])
+            A[w][i] = right.reshape(n, 2, r)
+            Tl.append(left)
+        X, r = Xn, n
+    for w in range(W):
+        A[w][0] = Tl[w].reshape(1, 2, r)
+    # ---- layers (disentangle) ----
+    B = []
+    for w in range(W):
+        per_state(w)
+        Bw = copy_mps(K, A[w])
+        normalize_site0(K, Bw)
+        B.append(Bw)
+    layer_gates = [[] for _ in range(W)]
+    kinds = None
+    for _ in range(num_layers):
+        G = []
+        for w in range(W):
+            per_state(w)
+            g, kinds = chi2_layer(K, B[w])                            # mps.py:849-891
+            G.append(g)
+            layer_gates[w].append(g)
+        # inverse layer (mps.py:944-971), one block spanning all sites by the static assumption
+        for w in range(W):
+            per_state(w)
+            l, _, rr = B[w][N - 1].shape
+            K.site_gate(B[w][N - 1], l, rr, G[w][N - 1], dagger=True)
+        for i in range(N - 2, -1, -1):
+            l, _, b = B[0][i].shape
+            rr = B[0][i + 1].shape[2]
+            Xt = K.empty((W, 2 * l, 2 * rr))
+            for w in range(W):
+                per_state(w)
+                K.theta_small(B[w][i], B[w][i + 1], G[w][i], True, out=Xt[w])
+            K.mismatch = grp
+            U, S, Vh = K.svd_small_batch(Xt, backmult=True)
+            k = S.shape[1]
+            for w in range(W):
+                per_state(w)
+                left, right = K.split_absorb(U[w], S[w], Vh[w], CUTOFF, MODE_RSUM2, 0, k)
+                B[w][i] = left.reshape(l, 2, k)
+                B[w][i + 1] = right.reshape(k, 2, rr)
+        for w in range(W):
+            per_state(w)
+            zero_overlap(K, B[w], break_tol=(1 - threshold) + 1e-5)   # sequential.py:390 validated on the device
+    import torch
+    out = []
+    for w in range(W):
+        lg = list(reversed(layer_gates[w]))                           # sequential.py:396
+        out.append((torch.cat(lg, dim=0).contiguous(), [kinds] * num_layers, A[w]))
+    return out
 
 
 def prepare_device(K, psi, n_sites, chi, num_layers, num_sweeps, threshold=1 - 1e-6, record=None, fused=True,

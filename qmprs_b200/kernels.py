@@ -227,6 +227,26 @@ class CudaKernels:
                           RuntimeWarning, stacklevel=2)
         return U, S, Vh
 
+    def svd_small_batch(self, X, backmult=False):
+        """Thin SVDs of the W same-shape matrices X[w] (W, m, n) in ONE launch, one CTA each (qm_svd_small).
+        Returns U (W, m, k), S (W, k), Vh (W, k, n); non-convergence of any of them sets ``self.mismatch``."""
+        W, m, n = X.shape
+        k = min(m, n)
+        flags = 1 if backmult else 0
+        assert X.is_contiguous() and self.lib.qm_svd_small_fits(m, n, flags)
+        U = self.empty((W, m, k))
+        S = self.empty((W, k), F64)
+        Vh = self.empty((W, k, n))
+        flag = self.mismatch if self.static else self._small_flag_tensor()
+        self._check(self.lib.qm_svd_small(m, n, _p(X), n, m * n, _p(U), k, m * k, _p(S), k, _p(Vh), n, k * n, self.svd_tol,
+                                          self.svd_max_sweeps, flags, W, _p(flag), self._stream()), "qm_svd_small")
+        return U, S, Vh
+
+    def _small_flag_tensor(self):
+        if self._small_flag is None:
+            self._small_flag = self.zeros((1,), I32)
+        return self._small_flag
+
     def check_small_svd(self):
         """Read (and clear) the sticky non-convergence flag of the single-CTA SVDs issued since the last check."""
         if self._small_flag is None:
@@ -299,6 +319,53 @@ class CudaKernels:
         self._check(self.lib.qm_complete_unitaries(_p(C), _p(bond), n_sites, _p(gates), _p(kinds), _p(bad), SIGN_TOL,
                                                    self._stream()), "qm_complete_unitaries")
         return gates, kinds, bad
+
+    # ---- fused bookkeeping for small registers (csrc/small_mps.cu) ---------------------
+    FUSED_MAX_BOND = 64
+
+    def split_absorb(self, U, S, Vh, cutoff, mode, max_bond, expect, out_left=None):
+        """trim + rank check + absorb in one launch (static mode): returns (left m x expect, right expect x n).
+        ``out_left``: contiguous buffer of m * expect elements that receives ``left`` (e.g. the next split's input)."""
+        m, k = U.shape
+        n = Vh.shape[1]
+        left = self.empty((m, expect)) if out_left is None else out_left.reshape(m, expect)
+        right = self.empty((expect, n))
+        self._check(self.lib.qm_split_absorb(_p(U), self._ld(U), _p(S), _p(Vh), self._ld(Vh), m, n, k, float(cutoff),
+                                             int(mode), int(max_bond or 0), int(expect), _p(left), _p(right),
+                                             _p(self.mismatch), self._stream()), "qm_split_absorb")
+        return left, right
+
+    def theta_small(self, A, A2, G, dagger, out=None):
+        l, _, b = A.shape
+        r = A2.shape[2]
+        X = self.empty((2 * l, 2 * r)) if out is None else out
+        self._check(self.lib.qm_theta_small(_p(A), _p(A2), l, b, r, _p(G), 1 if dagger else 0, _p(X), self._stream()),
+                    "qm_theta_small")
+        return X
+
+    def chi2_env(self, Lprev, B):
+        l, _, r = B.shape
+        out = self.empty((r, r))
+        self._check(self.lib.qm_chi2_env(_p(Lprev), _p(B), l, r, _p(out), self._stream()), "qm_chi2_env")
+        return out
+
+    def chi2_bond(self, L, T, Bprev, Csite, bond_slot, ambiguous):
+        b = T.shape[0]
+        l0 = Bprev.shape[0]
+        Tout = self.empty((l0, 4))
+        self._check(self.lib.qm_chi2_bond(_p(L), b, _p(T), _p(Bprev), l0, CUTOFF, TIE_REL, CHI2_AMBIGUOUS_REL, _p(Csite),
+                                          _p(bond_slot), _p(ambiguous), _p(Tout), self._stream()), "qm_chi2_bond")
+        return Tout
+
+    def zero_overlap_fused(self, B, tol):
+        """<0..0|psi> in one launch; with tol >= 0 (static mode) the early break is validated on the device."""
+        n = len(B)
+        ptrs = (ctypes.c_void_p * n)(*[b.data_ptr() for b in B])
+        dims = (ctypes.c_int * (n + 1))(*([int(B[0].shape[0])] + [int(b.shape[2]) for b in B]))
+        out = self.empty((1,))
+        self._check(self.lib.qm_zero_overlap(ptrs, dims, n, float(tol), _p(out), _p(self.mismatch), self._stream()),
+                    "qm_zero_overlap")
+        return out
 
     def reverse3(self, a):
         l, _, r = a.shape

@@ -552,3 +552,72 @@ def test_svd_small_graded_and_rank_deficient(K):
     check_factors(a, K.to_host(U), K.to_host(S), K.to_host(Vh))
     assert K.lib.qm_svd_small_fits(65, 65, 0) == 0 and K.lib.qm_svd_small_fits(64, 4096, 0) == 0
     K.check_small_svd()
+
+
+def test_fused_small_register_kernels(K):
+    """csrc/small_mps.cu against the kernel groups they replace (numpy here): split+absorb, theta with the gate,
+    chi=2 environment and bond step, zero overlap."""
+    import torch
+    rng = np.random.default_rng(77)
+    K.begin_static()
+    try:
+        # split + absorb, both modes, rank equal / not equal to the assumed one
+        m, n, k = 24, 40, 24
+        u, _ = np.linalg.qr(crand(rng, m, k)); vh = np.linalg.qr(crand(rng, n, k))[0].conj().T
+        s = np.sort(rng.random(k))[::-1] + 0.1
+        U, S, Vh = K.from_host(u), K.from_host(s, torch.float64), K.from_host(vh)
+        left, right = K.split_absorb(U, S, Vh, 1e-10, 1, 0, k)
+        assert np.abs(K.to_host(left) - u * np.sqrt(s)[None, :]).max() < 1e-14
+        assert np.abs(K.to_host(right) - np.sqrt(s)[:, None] * vh).max() < 1e-14
+        left, right = K.split_absorb(U, S, Vh, 1e-10, 0, 8, 8)
+        assert np.abs(K.to_host(left) - (u * s[None, :])[:, :8]).max() < 1e-14 and np.abs(K.to_host(right) - vh[:8]).max() == 0
+        assert int(K.mismatch.item()) == 0
+        s2 = s.copy(); s2[-3:] = 1e-9 * s2[0]                 # rsum2 drops the three tiny values: rank 21 != 24
+        K.split_absorb(U, K.from_host(s2, torch.float64), Vh, 1e-10, 1, 0, k)
+        assert int(K.mismatch.item()) == 1
+        K.mismatch.zero_()
+        # theta with gate
+        l, b, r = 5, 7, 6
+        A, A2 = crand(rng, l, 2, b), crand(rng, b, 2, r)
+        G, _ = np.linalg.qr(crand(rng, 4, 4))
+        for dag in (False, True):
+            X = K.to_host(K.theta_small(K.from_host(A), K.from_host(A2), K.from_host(G.reshape(-1)), dag))
+            Mx = G.conj().T if dag else G
+            th = np.einsum("abcd,lcx,xdr->labr", Mx.reshape(2, 2, 2, 2), A, A2).reshape(2 * l, 2 * r)
+            assert np.abs(X - th).max() < 1e-13
+        # chi=2 environment
+        Bt = crand(rng, l, 2, r)
+        Lp = crand(rng, l, l); Lp = Lp @ Lp.conj().T
+        L1 = K.to_host(K.chi2_env(K.from_host(Lp), K.from_host(Bt)))
+        ref = sum(Bt[:, p, :].conj().T @ Lp @ Bt[:, p, :] for p in range(2))
+        assert np.abs(L1 - ref).max() < 1e-12
+        L0 = K.to_host(K.chi2_env(None, K.from_host(Bt)))
+        assert np.abs(L0 - sum(Bt[:, p, :].conj().T @ Bt[:, p, :] for p in range(2))).max() < 1e-13
+        # chi=2 bond step against the unfused kernels
+        bb, l0 = 9, 4
+        Lm = crand(rng, bb, bb); Lm = Lm @ Lm.conj().T
+        T, Bprev = crand(rng, bb, 4), crand(rng, l0, 2, bb)
+        C1, C2 = K.zeros((8,)), K.zeros((8,))
+        bond1, bond2 = K.zeros((1,), dtype=torch.int32), K.zeros((1,), dtype=torch.int32)
+        amb1, amb2 = K.zeros((1,), dtype=torch.int32), K.zeros((1,), dtype=torch.int32)
+        Tout = K.to_host(K.chi2_bond(K.from_host(Lm), K.from_host(T), K.from_host(Bprev), C1, bond1, amb1))
+        Td, Ld = K.from_host(T), K.from_host(Lm)
+        M = K.gemm(Ld, Td)
+        H = K.gemm(Td, M, transA=True)
+        Vsel = K.zeros((4, 2))
+        K.chi2_select(K.zeros((4,), dtype=torch.float64), H, C2, Vsel, bond2, squared=2, ambiguous=amb2)
+        W = K.gemm(Td, Vsel)
+        Tref = K.to_host(K.gemm(K.from_host(Bprev).reshape(l0 * 2, bb), W).reshape(l0, 4))
+        assert np.abs(Tout - Tref).max() < 1e-12 and np.abs(K.to_host(C1) - K.to_host(C2)).max() < 1e-12
+        assert int(bond1.item()) == int(bond2.item()) and int(amb1.item()) == int(amb2.item())
+        # zero overlap
+        dims = [1, 2, 4, 3, 1]
+        Bs = [crand(rng, dims[i], 2, dims[i + 1]) for i in range(4)]
+        v = np.ones((1, 1), dtype=complex)
+        for t in Bs:
+            v = v @ t[:, 0, :]
+        out = K.to_host(K.zero_overlap_fused([K.from_host(t) for t in Bs], -1.0))
+        assert abs(out[0] - v[0, 0]) < 1e-13
+        assert int(K.mismatch.item()) == 0
+    finally:
+        K.end_static()
