@@ -72,6 +72,13 @@ int qm_transpose(void* out, long long ldo, const void* in, long long ldi, long l
  * diagonal.  Replaces quimb qr_stabilized behind left_canonize / right_canonize /
  * tensor_compress_bond: mps.py:396-398, :451-453. */
 int qm_qr(int m, int n, void* A, long long lda, void* tau, void* stream);
+/* Blocked forms (compact WY, panels of 32 columns, LAPACK zgeqrf / zlarft / zlarfb): the panel by the column kernels,
+ * everything to its right by three ZGEMMs on the FP64 tensor cores.  Same output layout as qm_qr / qm_qr_formq.
+ * work: qm_qr_work_bytes(m, n) bytes of device scratch. */
+long long qm_qr_work_bytes(int m, int n);
+int qm_qr_blocked(int m, int n, void* A, long long lda, void* tau, void* work, long long work_bytes, void* stream);
+int qm_qr_formq_blocked(int m, int k, const void* A, long long lda, const void* tau, void* Q, long long ldq, void* work,
+                        long long work_bytes, void* stream);
 int qm_qr_formq(int m, int k, const void* A, long long lda, const void* tau, void* Q, long long ldq, void* stream);
 int qm_qr_finish(int m, int n, const void* A, long long lda, void* R, long long ldr, void* Q, long long ldq,
                  void* stream);

@@ -29,6 +29,9 @@ SIGNATURES = {
     "qm_expect_not_close": (_i, [_vp, _d, _vp, _vp]),
     "qm_transpose": (_i, [_vp, _ll, _vp, _ll, _ll, _ll, _i, _vp]),
     "qm_qr": (_i, [_i, _i, _vp, _ll, _vp, _vp]),
+    "qm_qr_work_bytes": (_ll, [_i, _i]),
+    "qm_qr_blocked": (_i, [_i, _i, _vp, _ll, _vp, _vp, _ll, _vp]),
+    "qm_qr_formq_blocked": (_i, [_i, _i, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp]),
     "qm_qr_formq": (_i, [_i, _i, _vp, _ll, _vp, _vp, _ll, _vp]),
     "qm_qr_finish": (_i, [_i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp]),
     "qm_trim": (_i, [_vp, _i, _d, _i, _i, _vp, _vp, _vp]),

@@ -104,7 +104,7 @@ def prepare_state_batch(states, bond_dimension: int, num_layers: int = 1, num_sw
         recv = local
     if return_device:
         return recv
-    allrec = recv.cpu().numpy()
+    allrec = recv.cpu().numpy()            # the one device->host copy of the path
     if not (distributed and gather) or world == 1:
         return [unpack_record(allrec[slot], n, num_layers) for slot in range(len(mine))] if world == 1 else \
                {s: unpack_record(allrec[slot], n, num_layers) for slot, s in enumerate(mine)}

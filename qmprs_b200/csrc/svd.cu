@@ -1291,10 +1291,10 @@ __device__ __forceinline__ void round_grid_barrier(unsigned int* bar, unsigned i
 // rounds of the same launch.
 template <bool DBG>
 __global__ void __launch_bounds__(NTR, 1)
-k_round(cplx* W, long long ldw, int len, long long lenx, int chunk_g, int chunk_a, int nbp, int r_begin, int r_end,
+k_round(cplx* W, long long ldw, int len, long long lenx, int chunk, int nbp, int r_begin, int r_end,
         double* G, cplx* Q, double tol2, int max_inner, float cross_ratio, int cross_only, int* notconv, int* rotated,
-        double* sig2, unsigned int* ticket, unsigned int* flag, unsigned int* bar, unsigned int epoch0,
-        unsigned int bar0, int mixed, long long* dbg) {
+        double* sig2, unsigned int* ticket, unsigned int* flag, unsigned int* bar, unsigned int* ver,
+        unsigned int epoch0, unsigned int bar0, int mixed, long long* dbg) {
     // dbg (QM_ROUND_DEBUG=1): per-CTA sums of phase durations in ns: [0] gram, [1] ticket, [2] wait (waiters), [11] eig
     // (solvers), [3] update, [4..8] inside the eigen-solve (load+scan, convert, rotations, write-back, rounds),
     // [9] rounds, [10] eigen-solves, [12..15] cycles of the mixed-precision loop phases
@@ -1313,13 +1313,28 @@ k_round(cplx* W, long long ldw, int len, long long lenx, int chunk_g, int chunk_
         const unsigned int epoch = epoch0 + (unsigned int)(r - r_begin);
         int bi, bj;
         get_pair(ps, pair, bi, bj);
-        // ---- 1. partial Gram matrices ----
+        // Dataflow between rounds (ver != NULL): this CTA owns the columns [2 x chunk x blockIdx.x, + 2 chunk) of its
+        // pair's rows in both phases, so round e may start as soon as the two CTAs that updated the same columns of
+        // row blocks bi and bj in round e-1 are done -- ver[chunk index][block] = last completed epoch -- instead of
+        // waiting for the slowest pair of the whole grid (ncu: 23 % of the warp samples at the grid barrier).
+        if (ver && epoch > 1u) {
+            if (tid < 2) {
+                const unsigned int* vp = ver + (long long)blockIdx.x * nbp + (tid == 0 ? bi : bj);
+                unsigned int v;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(vp) : "memory");
+                } while ((int)(v - (epoch - 1u)) < 0);
+            }
+            __syncthreads();
+        }
+        // ---- 1. partial Gram matrices (teams whose columns lie in the identity extension write a zero slab) ----
+        const int sub = 2 * blockIdx.x + team;
+        const long long cc0 = (long long)sub * chunk;
+        const long long cc1 = (cc0 + chunk < lenx) ? cc0 + chunk : lenx;
         {
-            const int sub = 2 * blockIdx.x + team;
-            long long c0 = (long long)sub * chunk_g;
-            if (c0 > len) c0 = len;                        // an empty range still writes its (zero) slab
-            const long long c1 = (c0 + chunk_g < len) ? c0 + chunk_g : len;
-            gram_mma_part<true>(W, ldw, bi, bj, c0, c1, Gp + (long long)sub * PMAX * PMAX * 2, w8, lane);
+            const long long c0 = cc0 < len ? cc0 : len;
+            const long long c1 = cc1 < len ? cc1 : len;
+            gram_mma_part<true>(W, ldw, bi, bj, c0, c1 > c0 ? c1 : c0, Gp + (long long)sub * PMAX * PMAX * 2, w8, lane);
         }
         __syncthreads();
         if (DBG && tid == 0) tt[1] = gtimer();
@@ -1361,10 +1376,7 @@ k_round(cplx* W, long long ldw, int len, long long lenx, int chunk_g, int chunk_
                 sm.a.qi[(e / PMAX) * QS + (e % PMAX)] = v.y;
             }
             __syncthreads();
-            const int sub = 2 * blockIdx.x + team;
-            const long long c0 = (long long)sub * chunk_a;
-            const long long c1 = (c0 + chunk_a < lenx) ? c0 + chunk_a : lenx;
-            apply_mma_part<true>(W, ldw, bi, bj, c0, c1, sm.a.qr, sm.a.qi, w8, lane);
+            apply_mma_part<true>(W, ldw, bi, bj, cc0, cc1 > cc0 ? cc1 : cc0, sm.a.qr, sm.a.qi, w8, lane);
         }
         if (DBG) {
             __syncthreads();
@@ -1378,7 +1390,16 @@ k_round(cplx* W, long long ldw, int len, long long lenx, int chunk_g, int chunk_
                 }
             }
         }
-        if (r + 1 < r_end) round_grid_barrier(bar, bar_target, nblocks);     // rows of W and the shared-memory union
+        if (ver) {
+            __syncthreads();                               // both teams done with their columns (and the shared-memory union)
+            if (tid == 0) {
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ver + (long long)blockIdx.x * nbp + bi), "r"(epoch) : "memory");
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ver + (long long)blockIdx.x * nbp + bj), "r"(epoch) : "memory");
+            }
+        } else if (r + 1 < r_end) {
+            round_grid_barrier(bar, bar_target, nblocks);  // rows of W and the shared-memory union
+        }
     }
 }
 
@@ -1657,7 +1678,9 @@ Work carve(const Geom& g, void* base) {
     w.sig2 = (double*)(b + off); off += align_up((size_t)g.nvp * sizeof(double));
     w.perm = (int*)(b + off); off += align_up((size_t)g.nvp * sizeof(int));
     w.notconv = (int*)(b + off); off += align_up(4 * sizeof(int));   // [0] not-converged count, [1] done flag, [2] max rel off-diag^2 (float bits)
-    w.sync = (unsigned int*)(b + off); off += align_up((2 * (size_t)g.npairs + 1) * sizeof(unsigned int));   // fused rounds: ticket[], flag[], grid barrier
+    // fused rounds: ticket[npairs], flag[npairs], grid barrier, ver[MAXCH/2][nbp] (dataflow between rounds)
+    w.sync = (unsigned int*)(b + off);
+    off += align_up((2 * (size_t)g.npairs + 1 + (size_t)(MAXCH / 2) * (g.nbp > 0 ? g.nbp : 1)) * sizeof(unsigned int));
     w.total = off;
     return w;
 }
@@ -1767,7 +1790,7 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
     const int* donep = is_static ? w.notconv + 1 : nullptr;
     if (is_static) max_sweeps = fixed_sweeps;
     QM_CUDA(cudaMemsetAsync(w.notconv, 0, 4 * sizeof(int), st));
-    QM_CUDA(cudaMemsetAsync(w.sync, 0, (2 * (size_t)g.npairs + 1) * sizeof(unsigned int), st));
+    QM_CUDA(cudaMemsetAsync(w.sync, 0, (2 * (size_t)g.npairs + 1 + (size_t)(MAXCH / 2) * (g.nbp > 0 ? g.nbp : 1)) * sizeof(unsigned int), st));
     unsigned int fused_barriers = 0;                       // grid barriers passed so far in this SVD
     // a sweep that STARTS below `early` (largest |cos| between rows) ends near early^2 (quadratic regime): no
     // verification sweep after it.  QM_SVD_EARLY overrides for experiments.
@@ -1892,14 +1915,15 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         };
         if (fused) {
             const int nteams = 2 * fused_nch;
-            int cg = (int)(((g.len + nteams - 1) / nteams + 31) / 32 * 32);
-            int ca = (int)(((lenx + nteams - 1) / nteams + 63) / 64 * 64);
+            int chunk = (int)(((lenx + nteams - 1) / nteams + 63) / 64 * 64);       // same columns in Gram and update
+            static const int dataflow = !(getenv("QM_SVD_DATAFLOW") && atoi(getenv("QM_SVD_DATAFLOW")) == 0);
             unsigned int* ticket = w.sync;
             unsigned int* flag = w.sync + g.npairs;
             {
                 // every round of the sweep in one cooperative launch (QM_SVD_ROUNDS_PER_LAUNCH limits it for A/B runs)
                 static const int rpl = getenv("QM_SVD_ROUNDS_PER_LAUNCH") ? atoi(getenv("QM_SVD_ROUNDS_PER_LAUNCH")) : 1 << 20;
                 unsigned int* bar = w.sync + 2 * g.npairs;
+                unsigned int* ver = dataflow ? w.sync + 2 * g.npairs + 1 : nullptr;
                 const unsigned int nblocks = (unsigned int)fused_nch * (unsigned int)g.npairs;
                 for (int r0 = 0; r0 < g.rounds; r0 += rpl) {
                     int r1 = r0 + rpl < g.rounds ? r0 + rpl : g.rounds;
@@ -1912,8 +1936,8 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
                     int co = cross_only; int* nc = w.notconv; int* rot = w.rotated; double* s2 = w.sig2;
                     int mixed = eig_version == 4;
                     long long* dbg = round_dbg;
-                    void* args[] = {&Wp, &ldw, &len, &lx, &cg, &ca, &nbp, &rb, &r1, &Gp, &Qp, &t2, &mi, &cr, &co, &nc, &rot,
-                                    &s2, &ticket, &flag, &bar, &epoch0, &bar0, &mixed, &dbg};
+                    void* args[] = {&Wp, &ldw, &len, &lx, &chunk, &nbp, &rb, &r1, &Gp, &Qp, &t2, &mi, &cr, &co, &nc, &rot,
+                                    &s2, &ticket, &flag, &bar, &ver, &epoch0, &bar0, &mixed, &dbg};
                     QM_LAUNCH(QM_CLS_SVD_ROUND, st, cudaLaunchCooperativeKernel(
                         dbg ? (void*)k_round<true> : (void*)k_round<false>, dim3(fused_nch, g.npairs), dim3(NTR), args,
                         sizeof(RoundSmem), st));

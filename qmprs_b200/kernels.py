@@ -265,19 +265,37 @@ class CudaKernels:
                                           self._stream()), "qm_transpose")
         return out
 
-    def qr(self, A, want_q=True):
-        """Reduced QR with non-negative diag(R).  Returns (Q or None, R)."""
+    QR_BLOCKED_MIN = 64       # below: the column-by-column kernels (a panel is 32 columns)
+
+    def qr(self, A, want_q=True, blocked=None):
+        """Reduced QR with non-negative diag(R).  Returns (Q or None, R).  Matrices with more than 64 columns
+        are factored in panels of 32 with the trailing updates as ZGEMMs on the tensor cores (qm_qr_blocked)."""
         m, n = A.shape
         k = min(m, n)
+        if blocked is None:
+            blocked = k >= self.QR_BLOCKED_MIN
         F = self.empty((m, n))
         self._check(self.lib.qm_scale_copy(_p(F), n, _p(A), self._ld(A), m, n, None, None, 0, 0, self._stream()),
                     "qm_scale_copy")
         tau = self.empty((k,))
-        self._check(self.lib.qm_qr(m, n, _p(F), n, _p(tau), self._stream()), "qm_qr")
+        work = None
+        if blocked:
+            need = int(self.lib.qm_qr_work_bytes(m, n))
+            work = self.__dict__.get("_qr_work")
+            if work is None or work.numel() < need:
+                work = self._qr_work = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._check(self.lib.qm_qr_blocked(m, n, _p(F), n, _p(tau), _p(work), work.numel(), self._stream()),
+                        "qm_qr_blocked")
+        else:
+            self._check(self.lib.qm_qr(m, n, _p(F), n, _p(tau), self._stream()), "qm_qr")
         Q = None
         if want_q:
             Q = self.empty((m, k))
-            self._check(self.lib.qm_qr_formq(m, k, _p(F), n, _p(tau), _p(Q), k, self._stream()), "qm_qr_formq")
+            if blocked:
+                self._check(self.lib.qm_qr_formq_blocked(m, k, _p(F), n, _p(tau), _p(Q), k, _p(work), work.numel(),
+                                                         self._stream()), "qm_qr_formq_blocked")
+            else:
+                self._check(self.lib.qm_qr_formq(m, k, _p(F), n, _p(tau), _p(Q), k, self._stream()), "qm_qr_formq")
         R = self.empty((k, n))
         self._check(self.lib.qm_qr_finish(m, n, _p(F), n, _p(R), n, _p(Q), k, self._stream()), "qm_qr_finish")
         return Q, R
