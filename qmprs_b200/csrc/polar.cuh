@@ -156,8 +156,11 @@ __device__ void polar_conj_warp(const cplx* Es, int d, cplx* gate_out, cplx* scr
     }
     __syncwarp();
     const double tol2 = 4e-30;
-    int quiet = 0;                                   // consecutive rounds without a rotation
-    for (int it = 0; it < 90 && quiet < 3; it++) {
+    // A sweep is the three perfect matchings.  The loop ends after a sweep in which every rotation was tiny
+    // (|cos|^2 <= 1e-16 between the two columns): one-sided Jacobi converges quadratically, so such a sweep leaves
+    // cosines of ~1e-16 -- a verification sweep (three more rounds of the serial chain, ~1.2 us) would find nothing.
+    unsigned big = 0;                                // a rotation above that level happened in the current sweep
+    for (int it = 0; it < 90; it++) {
         const int m = (it % 3) + 1;
         cplx y = shfl_xor_c(x, m);                   // partner column, same row, same matrix
         const bool isp = j < (j ^ m);
@@ -187,8 +190,11 @@ __device__ void polar_conj_warp(const cplx* Es, int d, cplx* gate_out, cplx* scr
             if (isp) x = csub(cscale(x, c), cmul(cconj(se), y));
             else x = cadd(cmul(se, y), cscale(x, c));
         }
-        const unsigned any = __ballot_sync(0xffffffffu, rot);
-        quiet = any ? 0 : quiet + 1;
+        big |= __ballot_sync(0xffffffffu, rot && mag2 > 1e-16 * a * b);
+        if (m == 3) {                                // end of a sweep
+            if (!big) break;
+            big = 0;
+        }
     }
     // column norms of A, null detection
     double n2 = cabs2(x);

@@ -1780,7 +1780,7 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         const char* e1 = getenv("QM_SVD_INNER");
         const char* e2 = getenv("QM_SVD_CROSS");
         const char* e4 = getenv("QM_SVD_GROUPS");
-        tune_inner0 = e0 ? atoi(e0) : 2;
+        tune_inner0 = e0 ? atoi(e0) : 1;      // (2 in round 1: with the fused rounds one inner sweep is 4 % faster, same outer sweeps)
         tune_inner = e1 ? atoi(e1) : 1;
         tune_cross = e2 ? atoi(e2) : 1;
         tune_groups = e4 ? atoi(e4) : 1;
