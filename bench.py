@@ -295,10 +295,10 @@ SVD_STAGE = ("svd_gram", "svd_eig", "svd_apply", "svd_layout", "svd_round")
 
 def roofline_from_profile(prof, peak_tf):
     """`prof`: {class: (ms, launches, algorithmic work)} of one instrumented step (CUDA events around every
-    launch).  Reports the TIME-DOMINANT part of the step.  The Jacobi SVD is three kernels per round
-    (k_gram_mma -> k_eig -> k_apply_mma) of which the 32x32 eigen-solve is latency bound and carries no flops
-    of its own, so the SVD is reported as a stage: algorithmic flops of its Gram + update GEMMs over the time
-    of all its kernels.  Streaming classes are reported against the measured HBM bandwidth."""
+    launch).  Reports the TIME-DOMINANT part of the step.  A Jacobi round is Gram -> 32x32 eigen-solve -> update
+    (one cooperative k_round launch per outer sweep; three kernels per round on the QM_SVD_SCHED=grouped path), of
+    which the eigen-solve is latency bound and carries no flops of its own, so the SVD is reported as a stage:
+    algorithmic flops of its Gram + update GEMMs over the time of all its kernels.  Streaming classes are reported against the measured HBM bandwidth."""
     peaks = load_peaks()
     tot_ms = sum(v[0] for v in prof.values())
     svd_ms = sum(prof[k][0] for k in SVD_STAGE if k in prof)
@@ -323,7 +323,7 @@ def roofline_from_profile(prof, peak_tf):
             "env_polar": "k_env_fused", "gate": "k_gate2"}.get(dom, dom)
     try:      # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, cold cache)
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        t = tj.get("svd_apply" if dom == "svd" else dom)
+        t = tj.get("svd_round" if dom == "svd" else dom)
         roof["traffic"] = t["bytes"] if t else None
         roof["traffic_note"] = t.get("note") if t else None
     except Exception:

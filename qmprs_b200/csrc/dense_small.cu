@@ -4,6 +4,9 @@
 #include "common.cuh"
 #include "polar.cuh"
 #include "qmprs_b200.h"
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 namespace {
 
@@ -78,10 +81,94 @@ __device__ __forceinline__ void small_env(cplx* c, const cplx* t, int nst, int q
     }
 }
 
+// ---- FP64 tensor-pipe variants of the two passes for two-qubit gates (8 groups per warp-step) ------------------
+// A 4x4 complex gate acting on a group is the real 8x8 matrix [[Re M, -Im M], [Im M, Re M]] acting on the group's
+// (re_0..re_3, im_0..im_3): one mma.sync.m8n8k4.f64 pair applies it to 8 groups.  Lane (gr = lane>>2, tc = lane&3)
+// loads amplitude tc of group G0+gr as ONE 16-byte word (its re feeds k-step 0, its im k-step 1) and receives
+// component gr of the results of groups G0+2tc, G0+2tc+1.  The vector FP64 pipe issues ~1 warp-instruction per cycle
+// per SM, which bounded the scalar passes (64 + 128 FP64 instructions per group); here a group costs 1/4 DMMA.
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ int group_base4(int G, int q) { return ((G >> q) << (q + 2)) | (G & ((1 << q) - 1)); }
+
+template <int OP>
+__device__ __forceinline__ void gate_frag(const cplx* G, int lane, double& a0, double& a1) {
+    const int gr = lane >> 2, tc = lane & 3;
+    const cplx m = gate_elem<4, OP>(G, gr & 3, tc);
+    a0 = gr < 4 ? m.x : m.y;
+    a1 = gr < 4 ? -m.y : m.x;
+}
+
+// y = M x for U x 8 groups starting at G0, written back in place.  U independent DMMA chains per warp: the FP64
+// mma has a long latency (~200 cycles measured through this loop), a single chain per warp ran SLOWER than the scalar
+// passes.
+template <int U>
+__device__ __forceinline__ void mma_apply(cplx* x, int G0, int q, double a0, double a1, int lane) {
+    const int gr = lane >> 2, tc = lane & 3, stride = 1 << q;
+    cplx v[U];
+    double d0[U], d1[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        v[u] = x[group_base4(G0 + 8 * u + gr, q) + tc * stride];
+        d0[u] = 0.0;
+        d1[u] = 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) dmma884(d0[u], d1[u], a0, v[u].x);
+#pragma unroll
+    for (int u = 0; u < U; u++) dmma884(d0[u], d1[u], a1, v[u].y);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        double* p0 = (double*)&x[group_base4(G0 + 8 * u + 2 * tc, q) + (gr & 3) * stride] + (gr >> 2);
+        double* p1 = (double*)&x[group_base4(G0 + 8 * u + 2 * tc + 1, q) + (gr & 3) * stride] + (gr >> 2);
+        *p0 = d0[u];
+        *p1 = d1[u];
+    }
+}
+
+template <int U>
+__device__ __forceinline__ void small_apply_mma(cplx* x, int ngroups, int q, double a0, double a1, int warp, int nw,
+                                                int lane) {
+    for (int G0 = warp * 8 * U; G0 < ngroups; G0 += nw * 8 * U) mma_apply<U>(x, G0, q, a0, a1, lane);
+}
+
+// c <- G^H c, then S[m][n] += sum_groups (component m of tbar) (component n of c_new); lane holds S[gr][2tc], S[gr][2tc+1]
+template <int U>
+__device__ __forceinline__ void small_env_mma(cplx* c, const cplx* t, int ngroups, int q, double a0, double a1, int warp,
+                                              int nw, int lane, double& e0, double& e1) {
+    const int gr = lane >> 2, tc = lane & 3, stride = 1 << q;
+    double f0[2 * U], f1[2 * U];
+#pragma unroll
+    for (int u = 0; u < 2 * U; u++) { f0[u] = 0.0; f1[u] = 0.0; }
+    for (int G0 = warp * 8 * U; G0 < ngroups; G0 += nw * 8 * U) {
+        mma_apply<U>(c, G0, q, a0, a1, lane);
+        __syncwarp();
+        double ta[2 * U], yb[2 * U];
+#pragma unroll
+        for (int u = 0; u < 2 * U; u++) {
+            const int b = group_base4(G0 + 4 * u + tc, q) + (gr & 3) * stride;
+            ta[u] = ((const double*)&t[b])[gr >> 2];
+            yb[u] = ((const double*)&c[b])[gr >> 2];
+        }
+#pragma unroll
+        for (int u = 0; u < 2 * U; u++) dmma884(f0[u], f1[u], ta[u], yb[u]);
+    }
+#pragma unroll
+    for (int h = U; h >= 1; h >>= 1)                     // fixed tree over the independent accumulators
+#pragma unroll
+        for (int u = 0; u < h; u++) { f0[u] += f0[u + h]; f1[u] += f1[u + h]; }
+    e0 = f0[0];
+    e1 = f1[0];
+}
+
 __global__ void __launch_bounds__(NTS, 1)
 k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ gates_g, const int* __restrict__ sites,
                const int* __restrict__ kinds, int n_gates, int num_sweeps, cplx* __restrict__ envs_g, int warm,
-               const cplx* __restrict__ psis, double* __restrict__ overlaps) {
+               const cplx* __restrict__ psis, double* __restrict__ overlaps, int allow_mma,
+               long long* __restrict__ dbg) {
     extern __shared__ __align__(16) unsigned char sw_smem[];
     const int nst = 1 << nbits;
     cplx* c = (cplx*)sw_smem;
@@ -91,10 +178,13 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
     cplx* vw = warm ? g + (long long)n_gates * 16 : nullptr;
     int* gq = (int*)(g + (long long)n_gates * 16 * (warm ? 2 : 1));     // lowest bit of each gate
     int* gd = gq + n_gates;                              // dimension (2 or 4)
-    __shared__ double wsum[NTS / 32][32];
+    __shared__ double wsum[NTS / 32][64];
+    __shared__ double ssum64[64];
     __shared__ cplx Es[16];
     __shared__ cplx pol_scratch[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const bool use_mma = allow_mma && (nst >> 2) >= 8 * nw;              // every warp has whole 8-group steps
+    const bool mma4 = (nst >> 2) >= 32 * nw;                             // ... and whole steps of 4 x 8 groups
     const cplx* target = targets + (long long)blockIdx.x * nst;
     cplx* gg = gates_g + (long long)blockIdx.x * n_gates * 16;
     cplx* envs = envs_g ? envs_g + (long long)blockIdx.x * n_gates * 16 : nullptr;
@@ -112,7 +202,12 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
         for (int i = tid; i < nst; i += blockDim.x) c[i] = mk(i == 0 ? 1.0 : 0.0, 0.0);
         __syncthreads();
         for (int k = 0; k < n_gates; k++) {
-            if (gd[k] == 4) small_apply<4, 0>(c, nst, gq[k], g + k * 16);
+            if (gd[k] == 4 && use_mma) {
+                double a0, a1;
+                gate_frag<0>(g + k * 16, lane, a0, a1);
+                if (mma4) small_apply_mma<4>(c, nst >> 2, gq[k], a0, a1, warp, nw, lane);
+                else small_apply_mma<1>(c, nst >> 2, gq[k], a0, a1, warp, nw, lane);
+            } else if (gd[k] == 4) small_apply<4, 0>(c, nst, gq[k], g + k * 16);
             else small_apply<2, 0>(c, nst, gq[k], g + k * 16);
             __syncthreads();
         }
@@ -121,31 +216,84 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
         for (int k = n_gates - 1; k >= 0; k--) {
             const int d = gd[k], q = gq[k];
             cplx* G = g + k * 16;
-            double acc[32];
+            const long long c0 = dbg ? clock64() : 0;
+            const bool mma = d == 4 && use_mma;
+            if (mma) {
+                double a0, a1, e0 = 0.0, e1 = 0.0;
+                gate_frag<1>(G, lane, a0, a1);
+                if (mma4) small_env_mma<4>(c, t, nst >> 2, q, a0, a1, warp, nw, lane, e0, e1);
+                else small_env_mma<1>(c, t, nst >> 2, q, a0, a1, warp, nw, lane, e0, e1);
+                wsum[warp][2 * lane] = e0;
+                wsum[warp][2 * lane + 1] = e1;
+            } else {
+                double acc[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) acc[i] = 0.0;
-            if (d == 4) small_env<4>(c, t, nst, q, G, acc);
-            else small_env<2>(c, t, nst, q, G, acc);
-            const double mine = warp_reduce32(acc, lane);
-            wsum[warp][lane] = mine;
+                for (int i = 0; i < 32; i++) acc[i] = 0.0;
+                if (d == 4) small_env<4>(c, t, nst, q, G, acc);
+                else small_env<2>(c, t, nst, q, G, acc);
+                wsum[warp][lane] = warp_reduce32(acc, lane);
+            }
             __syncthreads();
+            const long long c1 = dbg ? clock64() : 0;
             if (warp == 0) {
-                double ssum = 0.0;
-                for (int w = 0; w < nw; w++) ssum += wsum[w][lane];     // fixed order
-                // lane holds one double of E: (re, im) of entry lane/2
-                const double other = __shfl_xor_sync(0xffffffffu, ssum, 1);
-                if ((lane & 1) == 0 && (lane >> 1) < d * d) Es[lane >> 1] = mk(ssum, other);
+                if (mma) {
+                    double v0[NTS / 32], v1[NTS / 32];                      // fixed pairwise tree over the warps
+#pragma unroll
+                    for (int w = 0; w < NTS / 32; w++) {
+                        v0[w] = w < nw ? wsum[w][2 * lane] : 0.0;
+                        v1[w] = w < nw ? wsum[w][2 * lane + 1] : 0.0;
+                    }
+#pragma unroll
+                    for (int h = NTS / 64; h >= 1; h >>= 1)
+#pragma unroll
+                        for (int w = 0; w < h; w++) {
+                            v0[w] += v0[w + h];
+                            v1[w] += v1[w + h];
+                        }
+                    ssum64[2 * lane] = v0[0];
+                    ssum64[2 * lane + 1] = v1[0];
+                    __syncwarp();
+                    // S is the real 8x8 product of (re, im) components: E[o][b] = sum tbar_o c_b
+                    if (lane < 16) {
+                        const int o = lane >> 2, b = lane & 3;
+                        Es[lane] = mk(ssum64[o * 8 + b] - ssum64[(4 + o) * 8 + 4 + b],
+                                      ssum64[o * 8 + 4 + b] + ssum64[(4 + o) * 8 + b]);
+                    }
+                } else {
+                    double ssum = 0.0;
+                    for (int w = 0; w < nw; w++) ssum += wsum[w][lane];     // fixed order
+                    // lane holds one double of E: (re, im) of entry lane/2
+                    const double other = __shfl_xor_sync(0xffffffffu, ssum, 1);
+                    if ((lane & 1) == 0 && (lane >> 1) < d * d) Es[lane >> 1] = mk(ssum, other);
+                }
                 __syncwarp();
-                polar_conj_warp(Es, d, G, pol_scratch, warm ? vw + k * 16 : nullptr, warm ? vw + k * 16 : nullptr);
+                const int pr = polar_conj_warp(Es, d, G, pol_scratch, warm ? vw + k * 16 : nullptr,
+                                               warm ? vw + k * 16 : nullptr);
+                if (dbg && tid == 0) {
+                    dbg[blockIdx.x * 5 + 3] += pr < 0 ? -pr : pr;
+                    dbg[blockIdx.x * 5 + 4] += pr < 0;
+                }
                 // the rank-deficient branch of the polar returns early in 31 lanes while lane 0 finishes the
                 // single-thread completion: reconverge before the block barrier
                 __syncwarp();
                 if (envs && sweep == num_sweeps - 1 && lane < d * d) envs[k * 16 + lane] = Es[lane];
             }
+            const long long c2 = dbg ? clock64() : 0;
             __syncthreads();
-            if (d == 4) small_apply<4, 2>(t, nst, q, G);
+            if (mma) {
+                double a0, a1;
+                gate_frag<2>(G, lane, a0, a1);
+                if (mma4) small_apply_mma<4>(t, nst >> 2, q, a0, a1, warp, nw, lane);
+                else small_apply_mma<1>(t, nst >> 2, q, a0, a1, warp, nw, lane);
+            } else if (d == 4) small_apply<4, 2>(t, nst, q, G);
             else small_apply<2, 2>(t, nst, q, G);
             __syncthreads();
+            if (dbg && tid == 0) {                 // QM_SMALL_DEBUG: cycles of env pass / reduce + polar / tbar update
+                const long long c3 = clock64();
+                dbg[blockIdx.x * 5] += c1 - c0;
+                dbg[blockIdx.x * 5 + 1] += c2 - c1;
+                dbg[blockIdx.x * 5 + 2] += c3 - c2;
+            }
         }
     }
     for (int i = tid; i < n_gates * 16; i += blockDim.x) gg[i] = g[i];
@@ -157,7 +305,12 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
         for (int i = tid; i < nst; i += blockDim.x) c[i] = mk(i == 0 ? 1.0 : 0.0, 0.0);
         __syncthreads();
         for (int k = 0; k < n_gates; k++) {
-            if (gd[k] == 4) small_apply<4, 0>(c, nst, gq[k], g + k * 16);
+            if (gd[k] == 4 && use_mma) {
+                double a0, a1;
+                gate_frag<0>(g + k * 16, lane, a0, a1);
+                if (mma4) small_apply_mma<4>(c, nst >> 2, gq[k], a0, a1, warp, nw, lane);
+                else small_apply_mma<1>(c, nst >> 2, gq[k], a0, a1, warp, nw, lane);
+            } else if (gd[k] == 4) small_apply<4, 0>(c, nst, gq[k], g + k * 16);
             else small_apply<2, 0>(c, nst, gq[k], g + k * 16);
             __syncthreads();
         }
@@ -204,12 +357,19 @@ extern "C" int qm_sweeps_small(const void* targets, int n_sites, void* gates, co
     if (num_sweeps < 0) num_sweeps = 0;
     const size_t nst = (size_t)1 << n_sites;
     size_t smem = 2 * nst * sizeof(cplx) + (size_t)n_gates * 16 * sizeof(cplx) + (size_t)n_gates * 2 * sizeof(int);
-    const int warm = smem + (size_t)n_gates * 16 * sizeof(cplx) <= 220 * 1024;      // room for the polar warm starts
+    const int warm = smem + (size_t)n_gates * 16 * sizeof(cplx) <= 212 * 1024;      // room for the polar warm starts
     if (warm) smem += (size_t)n_gates * 16 * sizeof(cplx);
     static size_t attr_set = 0;
     if (smem > attr_set) {
         QM_CUDA(cudaFuncSetAttribute(k_sweeps_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
+    }
+    static const int allow_mma = getenv("QM_SMALL_MMA") ? atoi(getenv("QM_SMALL_MMA")) : 1;
+    static const int debug = getenv("QM_SMALL_DEBUG") ? atoi(getenv("QM_SMALL_DEBUG")) : 0;
+    long long* dbg = nullptr;
+    if (debug) {
+        QM_CUDA(cudaMalloc(&dbg, (size_t)batch * 5 * sizeof(long long)));
+        QM_CUDA(cudaMemsetAsync(dbg, 0, (size_t)batch * 5 * sizeof(long long), st));
     }
     long long groups = (long long)(nst >> 2);
     int threads = groups >= NTS ? NTS : (groups < 64 ? 64 : (int)groups);
@@ -218,8 +378,20 @@ extern "C" int qm_sweeps_small(const void* targets, int n_sites, void* gates, co
     qm_prof_work(QM_CLS_ENV, (double)batch * num_sweeps * n_gates * 96.0 * (double)nst);
     QM_LAUNCH(QM_CLS_ENV, st, k_sweeps_small<<<batch, threads, smem, st>>>(
         (const cplx*)targets, n_sites, (cplx*)gates, sites_dev, kinds_dev, n_gates, num_sweeps, (cplx*)envs, warm,
-        (const cplx*)psis, (double*)overlaps));
+        (const cplx*)psis, (double*)overlaps, allow_mma, dbg));
     QM_CHECK_LAUNCH();
+    if (dbg) {
+        std::vector<long long> h((size_t)batch * 5);
+        QM_CUDA(cudaStreamSynchronize(st));
+        QM_CUDA(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        QM_CUDA(cudaFree(dbg));
+        double ph[5] = {0, 0, 0, 0, 0};
+        for (int b = 0; b < batch; b++)
+            for (int j = 0; j < 5; j++) ph[j] += (double)h[(size_t)b * 5 + j];
+        const double steps = (double)batch * num_sweeps * n_gates;
+        fprintf(stderr, "[qm_sweeps_small] cycles per gate-step: env pass %.0f, reduce + polar %.0f, tbar update %.0f; polar rounds %.2f, "
+                "rank-deficient %.4f\n", ph[0] / steps, ph[1] / steps, ph[2] / steps, ph[3] / steps, ph[4] / steps);
+    }
     return 0;
 }
 

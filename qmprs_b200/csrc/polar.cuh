@@ -130,37 +130,16 @@ __device__ __forceinline__ cplx shfl_xor_c(cplx v, int m) {
     return mk(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
 
-// vwarm (optional, global, 16 cplx): right singular vectors found for this gate in the previous sweep.
-// The environments change little from sweep to sweep, so E V_prev already has nearly orthogonal
-// columns and the Jacobi iteration starts in its quadratic regime (2 sweeps instead of 5-6).
-// vwarm_out: where the vectors found now are stored (the same array in the per-gate kernels; a second buffer in the
-// persistent kernel, where every CTA reads the warm start while CTA 0 writes the new one; NULL = do not store).
-__device__ void polar_conj_warp(const cplx* Es, int d, cplx* gate_out, cplx* scratch /* smem, 32 cplx */,
-                                const cplx* vwarm, cplx* vwarm_out) {
-    const int lane = threadIdx.x & 31;
-    const int half = lane >> 4, i = (lane >> 2) & 3, j = lane & 3;
-    cplx x;
-    cplx vin = mk(i == j ? 1.0 : 0.0, 0.0);
-    if (vwarm) {
-        cplx v = vwarm[i * 4 + j];
-        if (__ballot_sync(0xffffffffu, cabs2(v) > 0.0)) vin = v;     // all-zero = no warm start yet
-    }
-    scratch[lane] = (half == 0) ? ((i < d && j < d) ? Es[i * d + j] : mk(i == j ? 1.0 : 0.0, 0.0)) : vin;
-    __syncwarp();
-    if (half == 0) {
-        x = mk(0.0, 0.0);
-#pragma unroll
-        for (int k = 0; k < 4; k++) cfma(x, scratch[i * 4 + k], scratch[16 + k * 4 + j]);   // E V_prev
-    } else {
-        x = vin;
-    }
-    __syncwarp();
+// The Jacobi rounds on the 32 lanes' elements (x: A[i][j] in lanes 0-15, V[i][j] in lanes 16-31).  A sweep is the
+// three perfect matchings.  The loop ends after a sweep in which every rotation was tiny (|cos|^2 <= 1e-16 between
+// the two columns): one-sided Jacobi converges quadratically, so such a sweep leaves cosines of ~1e-16 -- a
+// verification sweep (three more rounds of the serial chain, ~1.2 us) would find nothing.  Returns the rounds done.
+__device__ __forceinline__ int polar_jacobi_rounds(cplx& x, int half, int j) {
     const double tol2 = 4e-30;
-    // A sweep is the three perfect matchings.  The loop ends after a sweep in which every rotation was tiny
-    // (|cos|^2 <= 1e-16 between the two columns): one-sided Jacobi converges quadratically, so such a sweep leaves
-    // cosines of ~1e-16 -- a verification sweep (three more rounds of the serial chain, ~1.2 us) would find nothing.
     unsigned big = 0;                                // a rotation above that level happened in the current sweep
+    int rounds = 0;
     for (int it = 0; it < 90; it++) {
+        rounds++;
         const int m = (it % 3) + 1;
         cplx y = shfl_xor_c(x, m);                   // partner column, same row, same matrix
         const bool isp = j < (j ^ m);
@@ -196,15 +175,81 @@ __device__ void polar_conj_warp(const cplx* Es, int d, cplx* gate_out, cplx* scr
             big = 0;
         }
     }
-    // column norms of A, null detection
+    return rounds;
+}
+
+// vwarm (optional, global, 16 cplx): right singular vectors found for this gate in the previous sweep.
+// The environments change little from sweep to sweep, so E V_prev already has nearly orthogonal
+// columns and the Jacobi iteration starts in its quadratic regime (2 sweeps instead of 5-6).
+// vwarm_out: where the vectors found now are stored (the same array in the per-gate kernels; a second buffer in the
+// persistent kernel, where every CTA reads the warm start while CTA 0 writes the new one; NULL = do not store).
+//
+// Rank-deficient E (every gate of the first layer, whose inputs include a fresh |0>: 1 gate-step in 10 of a
+// 12-qubit / 10-layer circuit) stays in the warp: with U_r, V_r the singular vectors of the non-null part,
+// P_l = I - U_r U_r^H and N_r the null columns of V, the canonical completion  N_l polar(N_l^H N_r) N_r^H  is the
+// partial isometry of P_l N_r N_r^H, whose row and column spaces are orthogonal to those of E.  So the null columns of
+// A = E V are REPLACED by sigma_max P_l V_j and the same Jacobi iteration continues: it orthogonalises those columns
+// among themselves (the others are already orthogonal to them), and U V^H is the canonical polar factor.  Only when
+// the replacement is itself rank-deficient (N_l^H N_r singular; E = 0) the single-thread routine takes over.
+// Round 1 sent every rank-deficient gate there: ~120 k cycles each, half of the polar time of a small state.
+// Returns the number of Jacobi rounds done, negative when the single-thread routine ran (instrumentation only).
+__device__ int polar_conj_warp(const cplx* Es, int d, cplx* gate_out, cplx* scratch /* smem, 32 cplx */,
+                               const cplx* vwarm, cplx* vwarm_out) {
+    const int lane = threadIdx.x & 31;
+    const int half = lane >> 4, i = (lane >> 2) & 3, j = lane & 3;
+    cplx x;
+    cplx vin = mk(i == j ? 1.0 : 0.0, 0.0);
+    if (vwarm) {
+        cplx v = vwarm[i * 4 + j];
+        if (__ballot_sync(0xffffffffu, cabs2(v) > 0.0)) vin = v;     // all-zero = no warm start yet
+    }
+    scratch[lane] = (half == 0) ? ((i < d && j < d) ? Es[i * d + j] : mk(i == j ? 1.0 : 0.0, 0.0)) : vin;
+    __syncwarp();
+    if (half == 0) {                                  // E V_prev, the four products summed as a tree
+        const cplx p0 = cmul(scratch[i * 4 + 0], scratch[16 + 0 * 4 + j]), p1 = cmul(scratch[i * 4 + 1], scratch[16 + 1 * 4 + j]);
+        const cplx p2 = cmul(scratch[i * 4 + 2], scratch[16 + 2 * 4 + j]), p3 = cmul(scratch[i * 4 + 3], scratch[16 + 3 * 4 + j]);
+        x = cadd(cadd(p0, p1), cadd(p2, p3));
+    } else {
+        x = vin;
+    }
+    __syncwarp();
+    int rounds = polar_jacobi_rounds(x, half, j);
+    // column norms of A, null detection (sigma_j <= 1e-13 sigma_max)
     double n2 = cabs2(x);
     n2 += __shfl_xor_sync(0xffffffffu, n2, 4); n2 += __shfl_xor_sync(0xffffffffu, n2, 8);
-    double sig = sqrt(n2);
-    double smax = sig;
-    smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, 1));
-    smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, 2));
-    const bool isnull = (half == 0) && (!(sig > 1e-13 * smax) || smax == 0.0);
-    if (__ballot_sync(0xffffffffu, isnull)) {
+    double nmax = n2;
+    nmax = fmax(nmax, __shfl_xor_sync(0xffffffffu, nmax, 1));
+    nmax = fmax(nmax, __shfl_xor_sync(0xffffffffu, nmax, 2));
+    bool isnull = (half == 0) && (!(n2 > 1e-26 * nmax) || nmax == 0.0);
+    unsigned nullcols = __ballot_sync(0xffffffffu, isnull) & 0xFu;          // bit j: column j of A is null
+    if (nullcols != 0u && nullcols != 0xFu) {
+        const double amax = __shfl_sync(0xffffffffu, nmax, 0);               // sigma_max^2 (of the A half)
+        const bool nj = (nullcols >> j) & 1u;
+        scratch[lane] = (half == 0) ? (nj ? mk(0.0, 0.0) : cscale(x, rsqrt(n2))) : x;   // [0..15] = U_r (0 in null columns), [16..31] = V
+        __syncwarp();
+        // C[k][j] = sum_r conj(U[r][k]) V[r][j], held by lane (k = i, j) of both halves
+        cplx cc = mk(0.0, 0.0);
+#pragma unroll
+        for (int r = 0; r < 4; r++) ccfma(cc, scratch[r * 4 + i], scratch[16 + r * 4 + j]);
+        // W[i][j] = V[i][j] - sum_k U[i][k] C[k][j]  =  (P_l V)[i][j]
+        cplx w = scratch[16 + i * 4 + j];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const cplx ckj = mk(__shfl_sync(0xffffffffu, cc.x, k * 4 + j), __shfl_sync(0xffffffffu, cc.y, k * 4 + j));
+            w = csub(w, cmul(scratch[i * 4 + k], ckj));
+        }
+        if (half == 0 && nj) x = cscale(w, amax * rsqrt(amax));
+        __syncwarp();
+        rounds += polar_jacobi_rounds(x, half, j);
+        n2 = cabs2(x);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, 4); n2 += __shfl_xor_sync(0xffffffffu, n2, 8);
+        nmax = n2;
+        nmax = fmax(nmax, __shfl_xor_sync(0xffffffffu, nmax, 1));
+        nmax = fmax(nmax, __shfl_xor_sync(0xffffffffu, nmax, 2));
+        isnull = (half == 0) && (!(n2 > 1e-26 * nmax) || nmax == 0.0);
+        nullcols = __ballot_sync(0xffffffffu, isnull) & 0xFu;
+    }
+    if (nullcols) {
         if (lane == 0) {
             cplx E[16], P[16];
             for (int k = 0; k < d * d; k++) E[k] = Es[k];
@@ -212,18 +257,18 @@ __device__ void polar_conj_warp(const cplx* Es, int d, cplx* gate_out, cplx* scr
             for (int k = 0; k < d * d; k++) gate_out[k] = P[k];
         }
         if (vwarm_out && half) vwarm_out[i * 4 + j] = mk(0.0, 0.0);
-        return;
+        return -rounds;
     }
     if (vwarm_out && half) vwarm_out[i * 4 + j] = x;
-    if (half == 0) x = cscale(x, 1.0 / sig);
+    if (half == 0) x = cscale(x, rsqrt(n2));
     scratch[lane] = x;                                // [0..15] = U, [16..31] = V
     __syncwarp();
-    if (lane < 16 && i < d && j < d) {
-        cplx sacc = mk(0.0, 0.0);
-#pragma unroll
-        for (int k = 0; k < 4; k++) cfmac(sacc, scratch[i * 4 + k], scratch[16 + j * 4 + k]);   // U V^H
-        gate_out[i * d + j] = cconj(sacc);
+    if (lane < 16 && i < d && j < d) {                // U V^H, the four products summed as a tree
+        const cplx p0 = cmulc(scratch[i * 4 + 0], scratch[16 + j * 4 + 0]), p1 = cmulc(scratch[i * 4 + 1], scratch[16 + j * 4 + 1]);
+        const cplx p2 = cmulc(scratch[i * 4 + 2], scratch[16 + j * 4 + 2]), p3 = cmulc(scratch[i * 4 + 3], scratch[16 + j * 4 + 3]);
+        gate_out[i * d + j] = cconj(cadd(cadd(p0, p1), cadd(p2, p3)));
     }
+    return rounds;
 }
 
 

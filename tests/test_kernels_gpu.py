@@ -287,6 +287,44 @@ def test_polar_via_sweep_full_rank(K):
         assert np.abs(m @ np.conj(m).T - np.eye(d)).max() <= 1e-12
 
 
+def test_polar_rank_deficient_gates_match_canonical_oracle(K):
+    """First-layer gates see a fresh |0> on one or both inputs: their environments have rank 2 / rank 1 and the
+    polar factor is fixed on null(E) by the canonical rule (polar.cuh: null(E) -> null(E^H) by the partial isometry
+    closest to the identity).  The in-warp completion must give the oracle's gates themselves, not only the same
+    circuit state; second layer = full-rank environments for comparison."""
+    rng = np.random.default_rng(5)
+    N, L = 5, 2
+    kinds = ([2] * (N - 1) + [1]) * L
+    sites = list(range(N)) * L
+    gates = np.zeros((L * N, 16), dtype=np.complex128)
+    ref_layers = []
+    for li in range(L):
+        gl = []
+        for i in range(N):
+            d = 4 if i < N - 1 else 2
+            q, _ = np.linalg.qr(crand(rng, d, d))
+            gl.append(q)
+            gates[li * N + i, : d * d] = q.reshape(-1)
+        ref_layers.append([(0, N - 1, gl)])
+    target = crand(rng, 2 ** N)
+    target /= np.linalg.norm(target)
+    G = K.from_host(gates)
+    for sweep in range(2):
+        c = K.circuit_state(N, G, sites, kinds)
+        K.sweep(c, K.conj_scale_copy(K.from_host(target), conj=True), N, G, sites, kinds)
+        O.sweep(target, ref_layers, N, "canonical")
+        g = K.to_host(G)
+        for li in range(L):
+            for i in range(N):
+                ref = ref_layers[li][0][2][i]
+                got = g[li * N + i][: ref.size].reshape(ref.shape)
+                assert np.abs(got - ref).max() <= 1e-9, (sweep, li, i)
+    # the same through the one-CTA kernel
+    G2 = K.from_host(gates)
+    K.sweeps_small(K.from_host(target.reshape(1, -1)), N, G2, sites, kinds, 2)
+    assert np.abs(K.to_host(G2) - K.to_host(G)).max() <= 1e-9
+
+
 def test_sweep_stored_matches_recompute(K):
     """The stored-intermediates sweep (fused kernel) and the recompute sweep are the same
     algorithm: identical circuit states after each sweep, including block boundaries
