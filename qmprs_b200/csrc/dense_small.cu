@@ -82,11 +82,19 @@ __device__ __forceinline__ void small_env(cplx* c, const cplx* t, int nst, int q
 }
 
 // ---- FP64 tensor-pipe variants of the two passes for two-qubit gates (8 groups per warp-step) ------------------
-// A 4x4 complex gate acting on a group is the real 8x8 matrix [[Re M, -Im M], [Im M, Re M]] acting on the group's
-// (re_0..re_3, im_0..im_3): one mma.sync.m8n8k4.f64 pair applies it to 8 groups.  Lane (gr = lane>>2, tc = lane&3)
-// loads amplitude tc of group G0+gr as ONE 16-byte word (its re feeds k-step 0, its im k-step 1) and receives
-// component gr of the results of groups G0+2tc, G0+2tc+1.  The vector FP64 pipe issues ~1 warp-instruction per cycle
-// per SM, which bounded the scalar passes (64 + 128 FP64 instructions per group); here a group costs 1/4 DMMA.
+// The vector FP64 pipe bounds the scalar passes (64 + 128 FP64 instructions per group, ~6 cycles per group and SM);
+// mma.sync.m8n8k4.f64 does a group's gate in 1/4 instruction.  Fragment maps are chosen so that every shared-memory
+// access is a 16-byte word per lane in a conflict-free pattern (8-byte accesses by component ran 4-way conflicted
+// for gates on bits >= 3 and were SLOWER than the scalar code):
+//  * apply, Y^T = X^T M^T: rows = the 8 groups, k = (re | im) of the 4 input amplitudes (two k-steps), columns =
+//    (re, im) of the 4 outputs interleaved.  Lane (gr = lane>>2, tc = lane&3) loads amplitude tc of group G0+gr
+//    (its re is the A operand of k-step 0, its im of k-step 1) and receives (re, im) of output tc of the same
+//    group: one LDS.128, two DMMA, one STS.128 to the address it loaded from.
+//  * environment, S[m][n] += sum_g (component m of tbar_g)(component n of c_g), components = (re_0..3, im_0..3), k =
+//    4 groups per DMMA: lane loads amplitude gr&3 of group G0 + tc + 4(gr>>2) of both vectors (512 contiguous-per-
+//    amplitude bytes per LDS.128) and swaps one double with lane^16, which gives it its operand for the DMMA of groups
+//    G0..G0+3 and the one of groups G0+4..G0+7.
+// The FP64 mma has a long latency (~200 cycles through a dependent chain): U independent chains per warp.
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -94,67 +102,76 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 
 __device__ __forceinline__ int group_base4(int G, int q) { return ((G >> q) << (q + 2)) | (G & ((1 << q) - 1)); }
 
+// B operands of the apply for the 4x4 matrix OP(G): b0 multiplies the re parts of the inputs, b1 the im parts
 template <int OP>
-__device__ __forceinline__ void gate_frag(const cplx* G, int lane, double& a0, double& a1) {
+__device__ __forceinline__ void gate_frag(const cplx* G, int lane, double& b0, double& b1) {
     const int gr = lane >> 2, tc = lane & 3;
-    const cplx m = gate_elem<4, OP>(G, gr & 3, tc);
-    a0 = gr < 4 ? m.x : m.y;
-    a1 = gr < 4 ? -m.y : m.x;
+    const cplx m = gate_elem<4, OP>(G, gr >> 1, tc);          // output gr>>1, input tc
+    b0 = (gr & 1) ? m.y : m.x;
+    b1 = (gr & 1) ? m.x : -m.y;
 }
 
-// y = M x for U x 8 groups starting at G0, written back in place.  U independent DMMA chains per warp: the FP64
-// mma has a long latency (~200 cycles measured through this loop), a single chain per warp ran SLOWER than the scalar
-// passes.
 template <int U>
-__device__ __forceinline__ void mma_apply(cplx* x, int G0, int q, double a0, double a1, int lane) {
+__device__ __forceinline__ void mma_apply(cplx* x, int G0, int q, double b0, double b1, int lane) {
     const int gr = lane >> 2, tc = lane & 3, stride = 1 << q;
+    cplx* p[U];
     cplx v[U];
     double d0[U], d1[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        v[u] = x[group_base4(G0 + 8 * u + gr, q) + tc * stride];
+        p[u] = x + group_base4(G0 + 8 * u + gr, q) + tc * stride;
+        v[u] = *p[u];
         d0[u] = 0.0;
         d1[u] = 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < U; u++) dmma884(d0[u], d1[u], a0, v[u].x);
+    for (int u = 0; u < U; u++) dmma884(d0[u], d1[u], v[u].x, b0);
 #pragma unroll
-    for (int u = 0; u < U; u++) dmma884(d0[u], d1[u], a1, v[u].y);
+    for (int u = 0; u < U; u++) dmma884(d0[u], d1[u], v[u].y, b1);
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        double* p0 = (double*)&x[group_base4(G0 + 8 * u + 2 * tc, q) + (gr & 3) * stride] + (gr >> 2);
-        double* p1 = (double*)&x[group_base4(G0 + 8 * u + 2 * tc + 1, q) + (gr & 3) * stride] + (gr >> 2);
-        *p0 = d0[u];
-        *p1 = d1[u];
-    }
+    for (int u = 0; u < U; u++) *p[u] = mk(d0[u], d1[u]);
 }
 
+// warps w0 .. w0+nwork-1 of the CTA share the groups
 template <int U>
-__device__ __forceinline__ void small_apply_mma(cplx* x, int ngroups, int q, double a0, double a1, int warp, int nw,
+__device__ __forceinline__ void small_apply_mma(cplx* x, int ngroups, int q, double b0, double b1, int wrel, int nwork,
                                                 int lane) {
-    for (int G0 = warp * 8 * U; G0 < ngroups; G0 += nw * 8 * U) mma_apply<U>(x, G0, q, a0, a1, lane);
+    for (int G0 = wrel * 8 * U; G0 < ngroups; G0 += nwork * 8 * U) mma_apply<U>(x, G0, q, b0, b1, lane);
 }
 
-// c <- G^H c, then S[m][n] += sum_groups (component m of tbar) (component n of c_new); lane holds S[gr][2tc], S[gr][2tc+1]
+__device__ __forceinline__ void small_apply_mma_any(cplx* x, int ngroups, int q, double b0, double b1, int wrel,
+                                                    int nwork, int lane) {
+    if (ngroups % (nwork * 64) == 0) small_apply_mma<8>(x, ngroups, q, b0, b1, wrel, nwork, lane);
+    else if (ngroups % (nwork * 32) == 0) small_apply_mma<4>(x, ngroups, q, b0, b1, wrel, nwork, lane);
+    else small_apply_mma<1>(x, ngroups, q, b0, b1, wrel, nwork, lane);
+}
+
+// Environment sums of the CURRENT vectors, S[m][n] += sum_g (component m of tbar_g)(component n of c_g); lane ends with
+// S[gr][2tc], S[gr][2tc+1].  (The gate is taken out afterwards, E = S conj(G_old) in the polar warp, so that the update
+// c <- G_old^H c is off the critical path: the other warps do it while warp 0 runs the polar.)
 template <int U>
-__device__ __forceinline__ void small_env_mma(cplx* c, const cplx* t, int ngroups, int q, double a0, double a1, int warp,
-                                              int nw, int lane, double& e0, double& e1) {
+__device__ __forceinline__ void small_envS_mma(const cplx* c, const cplx* t, int ngroups, int q, int warp, int nw,
+                                               int lane, double& e0, double& e1) {
     const int gr = lane >> 2, tc = lane & 3, stride = 1 << q;
+    const bool lo = gr < 4;
     double f0[2 * U], f1[2 * U];
 #pragma unroll
     for (int u = 0; u < 2 * U; u++) { f0[u] = 0.0; f1[u] = 0.0; }
     for (int G0 = warp * 8 * U; G0 < ngroups; G0 += nw * 8 * U) {
-        mma_apply<U>(c, G0, q, a0, a1, lane);
-        __syncwarp();
-        double ta[2 * U], yb[2 * U];
+        cplx zt[U], zy[U];
 #pragma unroll
-        for (int u = 0; u < 2 * U; u++) {
-            const int b = group_base4(G0 + 4 * u + tc, q) + (gr & 3) * stride;
-            ta[u] = ((const double*)&t[b])[gr >> 2];
-            yb[u] = ((const double*)&c[b])[gr >> 2];
+        for (int u = 0; u < U; u++) {
+            const int b = group_base4(G0 + 8 * u + tc + 4 * (gr >> 2), q) + (gr & 3) * stride;
+            zt[u] = t[b];
+            zy[u] = c[b];
         }
 #pragma unroll
-        for (int u = 0; u < 2 * U; u++) dmma884(f0[u], f1[u], ta[u], yb[u]);
+        for (int u = 0; u < U; u++) {
+            const double rt = __shfl_xor_sync(0xffffffffu, lo ? zt[u].y : zt[u].x, 16);
+            const double ry = __shfl_xor_sync(0xffffffffu, lo ? zy[u].y : zy[u].x, 16);
+            dmma884(f0[2 * u], f1[2 * u], lo ? zt[u].x : rt, lo ? zy[u].x : ry);               // groups G0+8u .. +3
+            dmma884(f0[2 * u + 1], f1[2 * u + 1], lo ? rt : zt[u].y, lo ? ry : zy[u].y);       // groups G0+8u+4 .. +7
+        }
     }
 #pragma unroll
     for (int h = U; h >= 1; h >>= 1)                     // fixed tree over the independent accumulators
@@ -168,7 +185,7 @@ __global__ void __launch_bounds__(NTS, 1)
 k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ gates_g, const int* __restrict__ sites,
                const int* __restrict__ kinds, int n_gates, int num_sweeps, cplx* __restrict__ envs_g, int warm,
                const cplx* __restrict__ psis, double* __restrict__ overlaps, int allow_mma,
-               long long* __restrict__ dbg) {
+               int defer_mode, long long* __restrict__ dbg) {
     extern __shared__ __align__(16) unsigned char sw_smem[];
     const int nst = 1 << nbits;
     cplx* c = (cplx*)sw_smem;
@@ -205,8 +222,7 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
             if (gd[k] == 4 && use_mma) {
                 double a0, a1;
                 gate_frag<0>(g + k * 16, lane, a0, a1);
-                if (mma4) small_apply_mma<4>(c, nst >> 2, gq[k], a0, a1, warp, nw, lane);
-                else small_apply_mma<1>(c, nst >> 2, gq[k], a0, a1, warp, nw, lane);
+                small_apply_mma_any(c, nst >> 2, gq[k], a0, a1, warp, nw, lane);
             } else if (gd[k] == 4) small_apply<4, 0>(c, nst, gq[k], g + k * 16);
             else small_apply<2, 0>(c, nst, gq[k], g + k * 16);
             __syncthreads();
@@ -218,13 +234,19 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
             cplx* G = g + k * 16;
             const long long c0 = dbg ? clock64() : 0;
             const bool mma = d == 4 && use_mma;
+            double gh0 = 0.0, gh1 = 0.0;                      // fragments of G_old^H for the deferred c update
             if (mma) {
-                double a0, a1, e0 = 0.0, e1 = 0.0;
-                gate_frag<1>(G, lane, a0, a1);
-                if (mma4) small_env_mma<4>(c, t, nst >> 2, q, a0, a1, warp, nw, lane, e0, e1);
-                else small_env_mma<1>(c, t, nst >> 2, q, a0, a1, warp, nw, lane, e0, e1);
+                double e0 = 0.0, e1 = 0.0;
+                if (mma4) small_envS_mma<4>(c, t, nst >> 2, q, warp, nw, lane, e0, e1);
+                else small_envS_mma<1>(c, t, nst >> 2, q, warp, nw, lane, e0, e1);
                 wsum[warp][2 * lane] = e0;
                 wsum[warp][2 * lane + 1] = e1;
+                gate_frag<1>(G, lane, gh0, gh1);
+                if (defer_mode == 0) {                       // same warp -> same groups as its part of the S pass
+                    __syncwarp();
+                    if (mma4) small_apply_mma<4>(c, nst >> 2, q, gh0, gh1, warp, nw, lane);
+                    else small_apply_mma<1>(c, nst >> 2, q, gh0, gh1, warp, nw, lane);
+                }
             } else {
                 double acc[32];
 #pragma unroll
@@ -253,11 +275,19 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
                     ssum64[2 * lane] = v0[0];
                     ssum64[2 * lane + 1] = v1[0];
                     __syncwarp();
-                    // S is the real 8x8 product of (re, im) components: E[o][b] = sum tbar_o c_b
+                    // S is the real 8x8 product of (re, im) components: E'[o][b'] = sum tbar_o c_b' with the OLD gate
+                    // still inside c; the environment of the gate is E[o][b] = sum_b' E'[o][b'] conj(G_old[b'][b])
                     if (lane < 16) {
                         const int o = lane >> 2, b = lane & 3;
-                        Es[lane] = mk(ssum64[o * 8 + b] - ssum64[(4 + o) * 8 + 4 + b],
-                                      ssum64[o * 8 + 4 + b] + ssum64[(4 + o) * 8 + b]);
+                        pol_scratch[lane] = mk(ssum64[o * 8 + b] - ssum64[(4 + o) * 8 + 4 + b],
+                                               ssum64[o * 8 + 4 + b] + ssum64[(4 + o) * 8 + b]);
+                    }
+                    __syncwarp();
+                    if (lane < 16) {
+                        const int o = lane >> 2, b = lane & 3;
+                        const cplx p0 = cmulc(pol_scratch[o * 4 + 0], G[0 * 4 + b]), p1 = cmulc(pol_scratch[o * 4 + 1], G[1 * 4 + b]);
+                        const cplx p2 = cmulc(pol_scratch[o * 4 + 2], G[2 * 4 + b]), p3 = cmulc(pol_scratch[o * 4 + 3], G[3 * 4 + b]);
+                        Es[lane] = cadd(cadd(p0, p1), cadd(p2, p3));
                     }
                 } else {
                     double ssum = 0.0;
@@ -277,14 +307,20 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
                 // single-thread completion: reconverge before the block barrier
                 __syncwarp();
                 if (envs && sweep == num_sweeps - 1 && lane < d * d) envs[k * 16 + lane] = Es[lane];
+            } else if (mma && defer_mode == 1) {
+                small_apply_mma_any(c, nst >> 2, q, gh0, gh1, warp - 1, nw - 1, lane);    // c <- G_old^H c, under the polar
+            } else if (mma && defer_mode == 2) {
+                // ... by the warps that do not share warp 0's scheduler (warp % 4 != 0), so that the polar's chain of
+                // dependent FP64 instructions does not queue behind their DMMAs
+                if (nw < 4) small_apply_mma_any(c, nst >> 2, q, gh0, gh1, warp - 1, nw - 1, lane);
+                else if (warp & 3) small_apply_mma_any(c, nst >> 2, q, gh0, gh1, (warp >> 2) * 3 + (warp & 3) - 1, (nw >> 2) * 3, lane);
             }
             const long long c2 = dbg ? clock64() : 0;
             __syncthreads();
             if (mma) {
                 double a0, a1;
                 gate_frag<2>(G, lane, a0, a1);
-                if (mma4) small_apply_mma<4>(t, nst >> 2, q, a0, a1, warp, nw, lane);
-                else small_apply_mma<1>(t, nst >> 2, q, a0, a1, warp, nw, lane);
+                small_apply_mma_any(t, nst >> 2, q, a0, a1, warp, nw, lane);
             } else if (d == 4) small_apply<4, 2>(t, nst, q, G);
             else small_apply<2, 2>(t, nst, q, G);
             __syncthreads();
@@ -308,8 +344,7 @@ k_sweeps_small(const cplx* __restrict__ targets, int nbits, cplx* __restrict__ g
             if (gd[k] == 4 && use_mma) {
                 double a0, a1;
                 gate_frag<0>(g + k * 16, lane, a0, a1);
-                if (mma4) small_apply_mma<4>(c, nst >> 2, gq[k], a0, a1, warp, nw, lane);
-                else small_apply_mma<1>(c, nst >> 2, gq[k], a0, a1, warp, nw, lane);
+                small_apply_mma_any(c, nst >> 2, gq[k], a0, a1, warp, nw, lane);
             } else if (gd[k] == 4) small_apply<4, 0>(c, nst, gq[k], g + k * 16);
             else small_apply<2, 0>(c, nst, gq[k], g + k * 16);
             __syncthreads();
@@ -364,7 +399,11 @@ extern "C" int qm_sweeps_small(const void* targets, int n_sites, void* gates, co
         QM_CUDA(cudaFuncSetAttribute(k_sweeps_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
-    static const int allow_mma = getenv("QM_SMALL_MMA") ? atoi(getenv("QM_SMALL_MMA")) : 1;
+    // DMMA passes: measured faster than the scalar ones up to 10 qubits, slower at 12 (the FP64 tensor pipe of this
+    // chip has the vector pipe's peak and a long latency; profiles/sweeps_small_phases_r02*.log); QM_SMALL_MMA=0/1 forces
+    static const int mma_env = getenv("QM_SMALL_MMA") ? atoi(getenv("QM_SMALL_MMA")) : -1;
+    const int allow_mma = mma_env >= 0 ? mma_env : (n_sites <= 10);
+    static const int defer_mode = getenv("QM_SMALL_DEFER") ? atoi(getenv("QM_SMALL_DEFER")) : 2;
     static const int debug = getenv("QM_SMALL_DEBUG") ? atoi(getenv("QM_SMALL_DEBUG")) : 0;
     long long* dbg = nullptr;
     if (debug) {
@@ -378,7 +417,7 @@ extern "C" int qm_sweeps_small(const void* targets, int n_sites, void* gates, co
     qm_prof_work(QM_CLS_ENV, (double)batch * num_sweeps * n_gates * 96.0 * (double)nst);
     QM_LAUNCH(QM_CLS_ENV, st, k_sweeps_small<<<batch, threads, smem, st>>>(
         (const cplx*)targets, n_sites, (cplx*)gates, sites_dev, kinds_dev, n_gates, num_sweeps, (cplx*)envs, warm,
-        (const cplx*)psis, (double*)overlaps, allow_mma, dbg));
+        (const cplx*)psis, (double*)overlaps, allow_mma, defer_mode, dbg));
     QM_CHECK_LAUNCH();
     if (dbg) {
         std::vector<long long> h((size_t)batch * 5);

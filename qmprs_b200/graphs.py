@@ -15,6 +15,8 @@ they only overlap when each has its own hardware work queue (CUDA_DEVICE_MAX_CON
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -223,7 +225,7 @@ class GraphedPreparer:
         tmpl = np.concatenate([np.tile(np.array(kinds_layer, dtype=np.float64), L), [float(L)]])
         rec_dev[:B, ng:ng + nk + 1] = torch.from_numpy(tmpl).to(dev)
         flags = torch.zeros(B, dtype=torch.int32, device=dev)
-        ready = torch.cuda.Event()
+        ready = torch.cuda.Event(enable_timing=bool(os.environ.get("QM_BATCH_DEBUG")))
         ready.record(main)
         if self.defer:
             lanes = self.layer_lanes
@@ -266,6 +268,10 @@ class GraphedPreparer:
         for lane in used:
             lane.done.record(lane.stream)
             main.wait_event(lane.done)
+        debug = bool(os.environ.get("QM_BATCH_DEBUG"))        # phase times of this call on stderr
+        if debug:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record(main)
         if self.defer:
             # every state's sweeps + fidelity in one launch, one CTA per state (sequential.py:509-541; README.md:66)
             ov = torch.empty((B, 2), dtype=torch.float64, device=dev)
@@ -273,6 +279,12 @@ class GraphedPreparer:
                                     batch=B, psis=sdev, overlaps=ov)
             rec_dev[:B, :ng] = gates_b.view(torch.float64).reshape(B, ng)
             rec_dev[:B, ng + nk + 1:ng + nk + 3] = ov
+        if debug:
+            ev[1].record(main)
+            torch.cuda.synchronize(dev)
+            import sys
+            sys.stderr.write(f"[run_into] B={B}: layers phase ends at +{ready.elapsed_time(ev[0]):.1f} ms, "
+                             f"sweeps phase {ev[0].elapsed_time(ev[1]):.1f} ms\n")
         if self.defer:
             gf = gflags.cpu().numpy()
             per_state = (gf[:, :wd] | gf[:, wd:wd + 1]).reshape(-1)[:B]      # own flag or the group's

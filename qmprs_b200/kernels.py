@@ -55,6 +55,7 @@ class CudaKernels:
         self._sweep_work = None
         self.launches = 0          # C-ABI calls issued (each launches >= 1 kernel)
         self.svd_sweeps = 0
+        self.svd_log = None        # set to a list to record (m, n, sweeps, backmult) of every multi-CTA SVD (scripts/svd_census.py)
         self.svd_unconverged = 0
         self.svd_tol = 1e-14
         self.svd_max_sweeps = 30
@@ -219,6 +220,8 @@ class CudaKernels:
                                     self._svd_work.numel(), self.svd_tol, _max_sweeps or self.svd_max_sweeps, info,
                                     flags, self._stream()), "qm_svd")
         self.svd_sweeps += info[0]
+        if self.svd_log is not None:
+            self.svd_log.append((m, n, int(info[0]), bool(backmult)))
         if not info[1] and _max_sweeps is None:
             # a partially converged decomposition would silently drive rank cut-offs and gates
             import warnings
