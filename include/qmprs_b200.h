@@ -156,6 +156,32 @@ int qm_reverse3(void* out, const void* in, int l, int r, void* stream);
  * qm_expect_ints: vals[i] must equal expect[i] (device array) or `scalar` when expect is NULL.
  * qm_expect_not_close: the early-break test |f - 1| <= tol (sequential.py:390) must not fire. */
 int qm_expect_ints(const void* vals, const void* expect, int n, int scalar, void* mismatch, void* stream);
+
+/* Batch forms of the small-register kernels: `batch` same-shape problems in ONE launch (the lock-step lanes of the
+ * CUDA-graph batch path advance W states together: one graph node per step instead of W; no counterpart in the
+ * reference, which prepares one state per call -- sequential.py:509-541 is run once per state).  `strides`: HOST array
+ * with the element stride between consecutive problems of every pointer argument, in argument order; scalar stride
+ * arguments likewise.  mismatch / bad / ambiguous: int vectors indexed by the problem. */
+int qm_split_absorb_batch(const void* U, long long ldu, const void* S, const void* Vh, long long ldvh, int m, int n,
+                          int k, double cutoff, int mode, int max_bond, int expect_rank, void* left, void* right,
+                          void* mismatch, int batch, const long long* strides /* U S Vh left right */, void* stream);
+int qm_theta_small_batch(const void* A, const void* A2, int l, int b, int r, const void* G, int dagger, void* X,
+                         int batch, const long long* strides /* A A2 G X */, void* stream);
+int qm_chi2_env_batch(const void* Lprev, const void* B, int l, int r, void* Lout, int batch,
+                      const long long* strides /* Lprev B Lout */, void* stream);
+int qm_chi2_bond_batch(const void* L, int b, const void* T, const void* Bprev, int l0, double cutoff, double tie,
+                       double ambiguous_rel, void* Csite, void* bond, void* ambiguous, void* Tout, int batch,
+                       const long long* strides /* L T Bprev Csite bond ambiguous Tout */, void* stream);
+int qm_zero_overlap_batch(const void* const* sites, const int* dims, int n_sites, double tol, void* out, void* mismatch,
+                          int batch, const long long* strides /* one per site tensor */, void* stream);
+int qm_site_gate_batch(void* B, int l, int r, const void* G, int dagger, int batch, long long strideB, long long strideG,
+                       void* stream);
+int qm_chi2_first_batch(const void* T0, void* Csite, int batch, long long strideT, long long strideC, void* stream);
+/* C [batch][n_sites][8], gates [batch][n_sites][16], kinds [batch][n_sites], bad [batch]: dense per problem */
+int qm_complete_unitaries_batch(const void* C, const void* bond, int n_sites, void* gates, void* kinds, void* bad,
+                                double sign_tol, int batch, long long stride_bond, void* stream);
+int qm_expect_ints_batch(const void* vals, const void* expect, int n, int scalar, void* mismatch, int batch,
+                         long long stride_vals, void* stream);
 int qm_expect_not_close(const void* f, double tol, void* mismatch, void* stream);
 
 /* ---- vectors ------------------------------------------------------------------- */

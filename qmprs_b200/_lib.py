@@ -16,6 +16,7 @@ _i = ctypes.c_int
 _ll = ctypes.c_longlong
 _d = ctypes.c_double
 _ip = ctypes.POINTER(ctypes.c_int)
+_llp = ctypes.POINTER(ctypes.c_longlong)
 
 # name -> (restype, argtypes); mirrors include/qmprs_b200.h one to one
 SIGNATURES = {
@@ -46,6 +47,15 @@ SIGNATURES = {
     "qm_chi2_env": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "qm_chi2_bond": (_i, [_vp, _i, _vp, _vp, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     "qm_zero_overlap": (_i, [ctypes.POINTER(_vp), _ip, _i, _d, _vp, _vp, _vp]),
+    "qm_split_absorb_batch": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _d, _i, _i, _i, _vp, _vp, _vp, _i, _llp, _vp]),
+    "qm_theta_small_batch": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _llp, _vp]),
+    "qm_chi2_env_batch": (_i, [_vp, _vp, _i, _i, _vp, _i, _llp, _vp]),
+    "qm_chi2_bond_batch": (_i, [_vp, _i, _vp, _vp, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _i, _llp, _vp]),
+    "qm_zero_overlap_batch": (_i, [ctypes.POINTER(_vp), _ip, _i, _d, _vp, _vp, _i, _llp, _vp]),
+    "qm_site_gate_batch": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _ll, _vp]),
+    "qm_chi2_first_batch": (_i, [_vp, _vp, _i, _ll, _ll, _vp]),
+    "qm_complete_unitaries_batch": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _i, _ll, _vp]),
+    "qm_expect_ints_batch": (_i, [_vp, _vp, _i, _i, _vp, _i, _ll, _vp]),
     "qm_reverse3": (_i, [_vp, _vp, _i, _i, _vp]),
     "qm_conj_scale_copy": (_i, [_vp, _vp, _ll, _i, _d, _vp]),
     "qm_vdot_out_doubles": (_i, []),

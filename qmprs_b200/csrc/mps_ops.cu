@@ -104,7 +104,10 @@ __global__ void k_theta_gate(cplx* __restrict__ X, int l, int r, const cplx* __r
 }
 
 // B viewed as (l, 2, r): B[l,o,r] = sum_p M[o,p] B[l,p,r].  In place.
-__global__ void k_site_gate(cplx* __restrict__ B, int l, int r, const cplx* __restrict__ G, int dagger) {
+__global__ void k_site_gate(cplx* __restrict__ B, int l, int r, const cplx* __restrict__ G, int dagger,
+                            long long sB, long long sG) {
+    B += blockIdx.y * sB;                          // state blockIdx.y of a batch
+    G += blockIdx.y * sG;
     cplx M[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -136,8 +139,10 @@ __global__ void k_chi2_select(const double* __restrict__ S, const cplx* __restri
 }
 
 // site 0 of the chi=2 MPS: C0 = T0 / ||T0||  (T0 is 1 x 2 x 2 padded -> 4 entries)
-__global__ void k_chi2_first(const cplx* __restrict__ T0, cplx* __restrict__ Csite) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void k_chi2_first(const cplx* __restrict__ T0, cplx* __restrict__ Csite, long long sT, long long sC) {
+    if (threadIdx.x != 0) return;
+    T0 += blockIdx.x * sT;                         // one CTA per state of a batch
+    Csite += blockIdx.x * sC;
     double s = 0.0;
     for (int c = 0; c < 4; c++) s += cabs2(T0[c]);
     double inv = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
@@ -191,9 +196,14 @@ __device__ void null_space_hh(cplx M[2][4], int m, int n, cplx Q[4][4], double s
 // if any generated matrix fails the unitarity check (mps.py:837-839).
 __global__ void k_complete_unitaries(const cplx* __restrict__ C, const int* __restrict__ bond, int N,
                                      cplx* __restrict__ gates, int* __restrict__ kinds, int* __restrict__ bad,
-                                     double sign_tol) {
+                                     double sign_tol, long long sbond) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    C += (long long)blockIdx.y * N * 8;            // state blockIdx.y of a batch: C, gates, kinds are dense per state
+    bond += blockIdx.y * sbond;
+    gates += (long long)blockIdx.y * N * 16;
+    kinds += (long long)blockIdx.y * N;
+    bad += blockIdx.y;
     const cplx* A = C + (long long)i * 8;
     int dl = (i == 0) ? 1 : bond[i - 1];
     int dr = (i == N - 1) ? 1 : bond[i];
@@ -321,9 +331,11 @@ __global__ void k_reverse3(cplx* __restrict__ out, const cplx* __restrict__ in, 
 
 // speculative static-shape execution: device-side validation of the assumptions
 __global__ void k_expect_ints(const int* __restrict__ vals, const int* __restrict__ expect, int n, int scalar,
-                              int* __restrict__ mismatch) {
+                              int* __restrict__ mismatch, long long svals) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    vals += blockIdx.y * svals;                    // state blockIdx.y of a batch, its own flag
+    mismatch += blockIdx.y;
     int e = expect ? expect[i] : scalar;
     if (vals[i] != e) mismatch[0] = 1;
 }
@@ -366,11 +378,20 @@ extern "C" int qm_theta_gate(void* X, int l, int r, const void* G, int dagger, v
     return 0;
 }
 
-extern "C" int qm_site_gate(void* B, int l, int r, const void* G, int dagger, void* stream) {
-    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_site_gate<<<ceil_div((long long)l * r, 256), 256, 0, (cudaStream_t)stream>>>((cplx*)B, l, r, (const cplx*)G,
-                                                                                  dagger));
+// Batch forms (one launch for `batch` same-shape states; strides in elements between consecutive states; the flag
+// arguments are int vectors indexed by the state): see the note in small_mps.cu.
+extern "C" int qm_site_gate_batch(void* B, int l, int r, const void* G, int dagger, int batch, long long strideB,
+                                  long long strideG, void* stream) {
+    if (batch < 1 || batch > 65535) return -2;
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream,
+              k_site_gate<<<dim3((unsigned)ceil_div((long long)l * r, 256), (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(
+                  (cplx*)B, l, r, (const cplx*)G, dagger, strideB, strideG));
     QM_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int qm_site_gate(void* B, int l, int r, const void* G, int dagger, void* stream) {
+    return qm_site_gate_batch(B, l, r, G, dagger, 1, 0, 0, stream);
 }
 
 extern "C" int qm_chi2_select(const void* S, const void* Vh, long long ldvh, double cutoff, double tie, void* Csite,
@@ -383,18 +404,34 @@ extern "C" int qm_chi2_select(const void* S, const void* Vh, long long ldvh, dou
     return 0;
 }
 
+extern "C" int qm_chi2_first_batch(const void* T0, void* Csite, int batch, long long strideT, long long strideC,
+                                   void* stream) {
+    if (batch < 1) return -2;
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_chi2_first<<<batch, 32, 0, (cudaStream_t)stream>>>(
+        (const cplx*)T0, (cplx*)Csite, strideT, strideC));
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int qm_chi2_first(const void* T0, void* Csite, void* stream) {
-    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_chi2_first<<<1, 32, 0, (cudaStream_t)stream>>>((const cplx*)T0, (cplx*)Csite));
+    return qm_chi2_first_batch(T0, Csite, 1, 0, 0, stream);
+}
+
+// batch: C [batch][n_sites][8], gates [batch][n_sites][16], kinds [batch][n_sites], bad [batch] dense per state;
+// bond: stride_bond ints between states
+extern "C" int qm_complete_unitaries_batch(const void* C, const void* bond, int n_sites, void* gates, void* kinds,
+                                           void* bad, double sign_tol, int batch, long long stride_bond, void* stream) {
+    if (batch < 1 || batch > 65535) return -2;
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream,
+              k_complete_unitaries<<<dim3((unsigned)ceil_div(n_sites, 64), (unsigned)batch), 64, 0, (cudaStream_t)stream>>>(
+                  (const cplx*)C, (const int*)bond, n_sites, (cplx*)gates, (int*)kinds, (int*)bad, sign_tol, stride_bond));
     QM_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int qm_complete_unitaries(const void* C, const void* bond, int n_sites, void* gates, void* kinds,
                                      void* bad, double sign_tol, void* stream) {
-    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_complete_unitaries<<<ceil_div(n_sites, 64), 64, 0, (cudaStream_t)stream>>>(
-        (const cplx*)C, (const int*)bond, n_sites, (cplx*)gates, (int*)kinds, (int*)bad, sign_tol));
-    QM_CHECK_LAUNCH();
-    return 0;
+    return qm_complete_unitaries_batch(C, bond, n_sites, gates, kinds, bad, sign_tol, 1, 0, stream);
 }
 
 extern "C" int qm_reverse3(void* out, const void* in, int l, int r, void* stream) {
@@ -403,11 +440,19 @@ extern "C" int qm_reverse3(void* out, const void* in, int l, int r, void* stream
     return 0;
 }
 
-extern "C" int qm_expect_ints(const void* vals, const void* expect, int n, int scalar, void* mismatch, void* stream) {
-    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream, k_expect_ints<<<ceil_div(n, 64), 64, 0, (cudaStream_t)stream>>>(
-        (const int*)vals, (const int*)expect, n, scalar, (int*)mismatch));
+// batch: vals + b * stride_vals checked against the same expectation, mismatch[b] set on disagreement
+extern "C" int qm_expect_ints_batch(const void* vals, const void* expect, int n, int scalar, void* mismatch, int batch,
+                                    long long stride_vals, void* stream) {
+    if (batch < 1 || batch > 65535) return -2;
+    QM_LAUNCH(QM_CLS_SMALL, (cudaStream_t)stream,
+              k_expect_ints<<<dim3((unsigned)ceil_div(n, 64), (unsigned)batch), 64, 0, (cudaStream_t)stream>>>(
+                  (const int*)vals, (const int*)expect, n, scalar, (int*)mismatch, stride_vals));
     QM_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int qm_expect_ints(const void* vals, const void* expect, int n, int scalar, void* mismatch, void* stream) {
+    return qm_expect_ints_batch(vals, expect, n, scalar, mismatch, 1, 0, stream);
 }
 
 extern "C" int qm_expect_not_close(const void* f, double tol, void* mismatch, void* stream) {

@@ -18,6 +18,9 @@ namespace {
 
 constexpr int NT = 256;
 
+// element strides between consecutive states of a batch, one per pointer argument (in argument order)
+template <int K> struct BatchStrides { long long s[K]; };
+
 // ---------------------------------------------------------------------------------
 // split + absorb.  Every CTA recomputes the rank (k <= a few thousand values), then copies its share.
 // mode 0: 'rel' cutoff (s_j > cutoff s_0), max_bond, singular values absorbed to the LEFT (left = U S, right = Vh);
@@ -27,7 +30,10 @@ constexpr int NT = 256;
 __global__ void __launch_bounds__(NT)
 k_split_absorb(const cplx* __restrict__ U, long long ldu, const double* __restrict__ S, const cplx* __restrict__ Vh,
                long long ldvh, int m, int n, int k, double cutoff, int mode, int max_bond, int expect,
-               cplx* __restrict__ left, cplx* __restrict__ right, int* __restrict__ mismatch) {
+               cplx* __restrict__ left, cplx* __restrict__ right, int* __restrict__ mismatch, BatchStrides<5> bs) {
+    // state blockIdx.y of a batch of same-shape problems (strides in elements; single problem: grid.y = 1)
+    U += blockIdx.y * bs.s[0]; S += blockIdx.y * bs.s[1]; Vh += blockIdx.y * bs.s[2];
+    left += blockIdx.y * bs.s[3]; right += blockIdx.y * bs.s[4]; mismatch += blockIdx.y;
     __shared__ double red[33];
     __shared__ int s_rank;
     __shared__ double s_f;
@@ -89,7 +95,8 @@ k_split_absorb(const cplx* __restrict__ U, long long ldu, const double* __restri
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT)
 k_theta_small(const cplx* __restrict__ A, const cplx* __restrict__ A2, int l, int b, int r, const cplx* __restrict__ G,
-              int dagger, cplx* __restrict__ X) {
+              int dagger, cplx* __restrict__ X, BatchStrides<4> bs) {
+    A += blockIdx.y * bs.s[0]; A2 += blockIdx.y * bs.s[1]; G += blockIdx.y * bs.s[2]; X += blockIdx.y * bs.s[3];
     __shared__ cplx M[16];
     if (threadIdx.x < 16) {
         const int a = threadIdx.x / 4, c = threadIdx.x % 4;
@@ -125,7 +132,10 @@ k_theta_small(const cplx* __restrict__ A, const cplx* __restrict__ A2, int l, in
 // (Lprev = identity for the first site).  One CTA; Y[p][a][c'] = sum_x Lprev[a][x] B[x,p,c'] staged in shared memory.
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
-k_chi2_env(const cplx* __restrict__ Lprev, const cplx* __restrict__ B, int l, int r, cplx* __restrict__ Lout) {
+k_chi2_env(const cplx* __restrict__ Lprev, const cplx* __restrict__ B, int l, int r, cplx* __restrict__ Lout,
+           BatchStrides<3> bs) {
+    if (Lprev) Lprev += blockIdx.x * bs.s[0];
+    B += blockIdx.x * bs.s[1]; Lout += blockIdx.x * bs.s[2];
     extern __shared__ __align__(16) unsigned char env_smem[];
     cplx* Y = (cplx*)env_smem;                             // [l*2][r]  (row index a*2 + p, as B)
     const int tid = threadIdx.x;
@@ -157,7 +167,9 @@ k_chi2_env(const cplx* __restrict__ Lprev, const cplx* __restrict__ B, int l, in
 __global__ void __launch_bounds__(NT)
 k_chi2_bond(const cplx* __restrict__ L, int b, const cplx* __restrict__ T, const cplx* __restrict__ Bprev, int l0,
             double cutoff, double tie, double amb_rel, cplx* __restrict__ Csite, int* __restrict__ bond,
-            int* __restrict__ ambiguous, cplx* __restrict__ Tout) {
+            int* __restrict__ ambiguous, cplx* __restrict__ Tout, BatchStrides<7> bs) {
+    L += blockIdx.x * bs.s[0]; T += blockIdx.x * bs.s[1]; Bprev += blockIdx.x * bs.s[2]; Csite += blockIdx.x * bs.s[3];
+    bond += blockIdx.x * bs.s[4]; ambiguous += blockIdx.x * bs.s[5]; Tout += blockIdx.x * bs.s[6];
     __shared__ cplx Ts[64 * 4], Ms[64 * 4], Ws[64 * 2], H[16], Vsel[8];
     const int tid = threadIdx.x;
     for (int idx = tid; idx < b * 4; idx += NT) Ts[idx] = T[idx];
@@ -198,7 +210,7 @@ k_chi2_bond(const cplx* __restrict__ L, int b, const cplx* __restrict__ T, const
 // v <- v B_i[:,0,:] over the sites; out = v (re, im); the early-break test |f - 1| <= tol must NOT fire
 // (sequential.py:390) when tol >= 0, else mismatch.
 // ---------------------------------------------------------------------------------
-struct SiteList { const cplx* p[32]; int l[32]; int r[32]; };
+struct SiteList { const cplx* p[32]; int l[32]; int r[32]; long long s[32]; };     // s: batch stride of each site tensor
 
 __global__ void __launch_bounds__(NT)
 k_zero_overlap(SiteList sites, int N, double tol, cplx* __restrict__ out, int* __restrict__ mismatch) {
@@ -208,8 +220,10 @@ k_zero_overlap(SiteList sites, int N, double tol, cplx* __restrict__ out, int* _
     cplx* w = vb;
     if (tid == 0) v[0] = mk(1.0, 0.0);
     __syncthreads();
+    out += blockIdx.x;
+    mismatch += blockIdx.x;
     for (int i = 0; i < N; i++) {
-        const cplx* B = sites.p[i];
+        const cplx* B = sites.p[i] + blockIdx.x * sites.s[i];
         const int l = sites.l[i], r = sites.r[i];
         for (int c = tid; c < r; c += NT) {
             cplx s = mk(0.0, 0.0);
@@ -230,70 +244,117 @@ k_zero_overlap(SiteList sites, int N, double tol, cplx* __restrict__ out, int* _
 
 }  // namespace
 
-extern "C" int qm_split_absorb(const void* U, long long ldu, const void* S, const void* Vh, long long ldvh, int m, int n,
-                               int k, double cutoff, int mode, int max_bond, int expect_rank, void* left, void* right,
-                               void* mismatch, void* stream) {
+namespace {
+template <int K> BatchStrides<K> strides_from(const long long* strides) {
+    BatchStrides<K> bs;
+    for (int i = 0; i < K; i++) bs.s[i] = strides ? strides[i] : 0;
+    return bs;
+}
+}  // namespace
+
+// The *_batch entries run `batch` same-shape problems in ONE launch (the lock-step lanes of graphs.py: W states advance
+// together, so that a CUDA-graph replay has one node per step instead of W).  `strides`: HOST array with the element
+// stride between consecutive problems of every pointer argument, in argument order (the mismatch / flag arguments are
+// int vectors indexed by the problem).  The single-problem entries are batch = 1.
+extern "C" int qm_split_absorb_batch(const void* U, long long ldu, const void* S, const void* Vh, long long ldvh, int m,
+                                     int n, int k, double cutoff, int mode, int max_bond, int expect_rank, void* left,
+                                     void* right, void* mismatch, int batch, const long long* strides, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (m < 1 || n < 1 || k < 1 || expect_rank < 1 || expect_rank > k) return -2;
+    if (m < 1 || n < 1 || k < 1 || expect_rank < 1 || expect_rank > k || batch < 1 || batch > 65535) return -2;
     const long long work = (long long)expect_rank * (m + n);
     long long g = (work + NT - 1) / NT;
     if (g > 148 * 4) g = 148 * 4;
-    QM_LAUNCH(QM_CLS_SMALL, st, k_split_absorb<<<(int)g, NT, 0, st>>>(
+    QM_LAUNCH(QM_CLS_SMALL, st, k_split_absorb<<<dim3((unsigned)g, (unsigned)batch), NT, 0, st>>>(
         (const cplx*)U, ldu, (const double*)S, (const cplx*)Vh, ldvh, m, n, k, cutoff, mode, max_bond, expect_rank,
-        (cplx*)left, (cplx*)right, (int*)mismatch));
+        (cplx*)left, (cplx*)right, (int*)mismatch, strides_from<5>(strides)));
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_split_absorb(const void* U, long long ldu, const void* S, const void* Vh, long long ldvh, int m, int n,
+                               int k, double cutoff, int mode, int max_bond, int expect_rank, void* left, void* right,
+                               void* mismatch, void* stream) {
+    return qm_split_absorb_batch(U, ldu, S, Vh, ldvh, m, n, k, cutoff, mode, max_bond, expect_rank, left, right, mismatch,
+                                 1, nullptr, stream);
+}
+
+extern "C" int qm_theta_small_batch(const void* A, const void* A2, int l, int b, int r, const void* G, int dagger,
+                                    void* X, int batch, const long long* strides, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (batch < 1 || batch > 65535) return -2;
+    QM_LAUNCH(QM_CLS_GEMM, st, k_theta_small<<<dim3((unsigned)ceil_div((long long)l * r, NT), (unsigned)batch), NT, 0, st>>>(
+        (const cplx*)A, (const cplx*)A2, l, b, r, (const cplx*)G, dagger, (cplx*)X, strides_from<4>(strides)));
+    qm_prof_work(QM_CLS_GEMM, 8.0 * (2.0 * l) * b * (2.0 * r) * batch);
     QM_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int qm_theta_small(const void* A, const void* A2, int l, int b, int r, const void* G, int dagger, void* X,
                               void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    QM_LAUNCH(QM_CLS_GEMM, st, k_theta_small<<<ceil_div((long long)l * r, NT), NT, 0, st>>>(
-        (const cplx*)A, (const cplx*)A2, l, b, r, (const cplx*)G, dagger, (cplx*)X));
-    qm_prof_work(QM_CLS_GEMM, 8.0 * (2.0 * l) * b * (2.0 * r));
-    QM_CHECK_LAUNCH();
-    return 0;
+    return qm_theta_small_batch(A, A2, l, b, r, G, dagger, X, 1, nullptr, stream);
 }
 
-extern "C" int qm_chi2_env(const void* Lprev, const void* B, int l, int r, void* Lout, void* stream) {
+extern "C" int qm_chi2_env_batch(const void* Lprev, const void* B, int l, int r, void* Lout, int batch,
+                                 const long long* strides, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)l * 2 * r * sizeof(cplx);
     if (smem > 200 * 1024) return -3;
+    if (batch < 1) return -2;
     static size_t attr_set = 0;
     if (smem > attr_set) {
         QM_CUDA(cudaFuncSetAttribute(k_chi2_env, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = 200 * 1024;
     }
-    QM_LAUNCH(QM_CLS_GEMM, st, k_chi2_env<<<1, 512, smem, st>>>((const cplx*)Lprev, (const cplx*)B, l, r, (cplx*)Lout));
+    QM_LAUNCH(QM_CLS_GEMM, st, k_chi2_env<<<batch, 512, smem, st>>>((const cplx*)Lprev, (const cplx*)B, l, r, (cplx*)Lout,
+                                                                   strides_from<3>(strides)));
+    QM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qm_chi2_env(const void* Lprev, const void* B, int l, int r, void* Lout, void* stream) {
+    return qm_chi2_env_batch(Lprev, B, l, r, Lout, 1, nullptr, stream);
+}
+
+extern "C" int qm_chi2_bond_batch(const void* L, int b, const void* T, const void* Bprev, int l0, double cutoff,
+                                  double tie, double ambiguous_rel, void* Csite, void* bond, void* ambiguous, void* Tout,
+                                  int batch, const long long* strides, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (b < 1 || b > 64) return -3;
+    if (batch < 1) return -2;
+    QM_LAUNCH(QM_CLS_SMALL, st, k_chi2_bond<<<batch, NT, 0, st>>>((const cplx*)L, b, (const cplx*)T, (const cplx*)Bprev, l0,
+                                                                  cutoff, tie, ambiguous_rel, (cplx*)Csite, (int*)bond,
+                                                                  (int*)ambiguous, (cplx*)Tout, strides_from<7>(strides)));
     QM_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int qm_chi2_bond(const void* L, int b, const void* T, const void* Bprev, int l0, double cutoff, double tie,
                             double ambiguous_rel, void* Csite, void* bond, void* ambiguous, void* Tout, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (b < 1 || b > 64) return -3;
-    QM_LAUNCH(QM_CLS_SMALL, st, k_chi2_bond<<<1, NT, 0, st>>>((const cplx*)L, b, (const cplx*)T, (const cplx*)Bprev, l0,
-                                                              cutoff, tie, ambiguous_rel, (cplx*)Csite, (int*)bond,
-                                                              (int*)ambiguous, (cplx*)Tout));
-    QM_CHECK_LAUNCH();
-    return 0;
+    return qm_chi2_bond_batch(L, b, T, Bprev, l0, cutoff, tie, ambiguous_rel, Csite, bond, ambiguous, Tout, 1, nullptr,
+                              stream);
 }
 
 // sites: HOST array of n_sites device pointers to the (l, 2, r) tensors; dims: HOST int[n_sites + 1] bond sizes
-// (dims[0] = dims[n_sites] = 1).  out: cplx[1] = <0..0|psi> (not conjugated); tol < 0 skips the early-break check.
-extern "C" int qm_zero_overlap(const void* const* sites, const int* dims, int n_sites, double tol, void* out,
-                               void* mismatch, void* stream) {
+// (dims[0] = dims[n_sites] = 1).  out: cplx[batch] = <0..0|psi> (not conjugated); tol < 0 skips the early-break check.
+// strides: HOST long long[n_sites], batch stride of every site tensor (NULL for batch = 1); mismatch: int[batch].
+extern "C" int qm_zero_overlap_batch(const void* const* sites, const int* dims, int n_sites, double tol, void* out,
+                                     void* mismatch, int batch, const long long* strides, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_sites < 1 || n_sites > 32) return -3;
+    if (n_sites < 1 || n_sites > 32 || batch < 1) return -3;
     SiteList sl;
     for (int i = 0; i < n_sites; i++) {
         if (dims[i] > 1024 || dims[i + 1] > 1024) return -3;
         sl.p[i] = (const cplx*)sites[i];
         sl.l[i] = dims[i];
         sl.r[i] = dims[i + 1];
+        sl.s[i] = strides ? strides[i] : 0;
     }
-    QM_LAUNCH(QM_CLS_SMALL, st, k_zero_overlap<<<1, NT, 0, st>>>(sl, n_sites, tol, (cplx*)out, (int*)mismatch));
+    QM_LAUNCH(QM_CLS_SMALL, st, k_zero_overlap<<<batch, NT, 0, st>>>(sl, n_sites, tol, (cplx*)out, (int*)mismatch));
     QM_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int qm_zero_overlap(const void* const* sites, const int* dims, int n_sites, double tol, void* out,
+                               void* mismatch, void* stream) {
+    return qm_zero_overlap_batch(sites, dims, n_sites, tol, out, mismatch, 1, nullptr, stream);
 }

@@ -109,15 +109,14 @@ class _BatchLane:
 
         def pipeline():
             K.begin_static()
-            work = [K.scale_copy(self.psi_in[w].reshape(-1, 1)).reshape(-1) for w in range(W)]
-            res = host.prepare_layers_lockstep(K, work, n, chi, L, threshold, self.flags)
-            for w, (gates, kinds, A) in enumerate(res):
-                if len(kinds) != L:
-                    raise RuntimeError("static capture produced an unexpected layer count")
-                self.gates_out[w].copy_(gates)
-                self.target_out[w].copy_(host.to_dense(K, A))         # sequential.py:440 (mps.mps)
+            work = self.psi_in.clone()
+            gates, kinds, A = host.prepare_layers_lockstep(K, work, n, chi, L, threshold, self.flags)
+            if len(kinds) != L:
+                raise RuntimeError("static capture produced an unexpected layer count")
+            self.gates_out.copy_(gates)
+            self.target_out.copy_(host.to_dense_batch(K, A))              # sequential.py:440 (mps.mps)
             K.end_static()
-            return res[0][1]
+            return kinds
 
         with torch.cuda.stream(self.stream):
             for w in range(W):
@@ -163,6 +162,8 @@ class GraphedPreparer:
                       and nq * self.cfg[2] <= CudaKernels.SMALL_SWEEP_MAX_GATES
                       and min(2 ** (nq // 2), self.cfg[1]) <= CudaKernels.FUSED_MAX_BOND)
         self.fallbacks = 0
+        self.time_phases = False             # run_into: record (layers ms, sweeps ms) of the call in self.phase_ms
+        self.phase_ms = None
         self.replays = 0
 
     @property
@@ -225,7 +226,7 @@ class GraphedPreparer:
         tmpl = np.concatenate([np.tile(np.array(kinds_layer, dtype=np.float64), L), [float(L)]])
         rec_dev[:B, ng:ng + nk + 1] = torch.from_numpy(tmpl).to(dev)
         flags = torch.zeros(B, dtype=torch.int32, device=dev)
-        ready = torch.cuda.Event(enable_timing=bool(os.environ.get("QM_BATCH_DEBUG")))
+        ready = torch.cuda.Event(enable_timing=bool(os.environ.get("QM_BATCH_DEBUG")) or self.time_phases)
         ready.record(main)
         if self.defer:
             lanes = self.layer_lanes
@@ -268,7 +269,7 @@ class GraphedPreparer:
         for lane in used:
             lane.done.record(lane.stream)
             main.wait_event(lane.done)
-        debug = bool(os.environ.get("QM_BATCH_DEBUG"))        # phase times of this call on stderr
+        debug = bool(os.environ.get("QM_BATCH_DEBUG")) or self.time_phases     # phase times of this call
         if debug:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record(main)
@@ -282,9 +283,11 @@ class GraphedPreparer:
         if debug:
             ev[1].record(main)
             torch.cuda.synchronize(dev)
-            import sys
-            sys.stderr.write(f"[run_into] B={B}: layers phase ends at +{ready.elapsed_time(ev[0]):.1f} ms, "
-                             f"sweeps phase {ev[0].elapsed_time(ev[1]):.1f} ms\n")
+            self.phase_ms = (ready.elapsed_time(ev[0]), ev[0].elapsed_time(ev[1]))
+            if os.environ.get("QM_BATCH_DEBUG"):
+                import sys
+                sys.stderr.write(f"[run_into] B={B}: layers phase ends at +{self.phase_ms[0]:.1f} ms, "
+                                 f"sweeps phase {self.phase_ms[1]:.1f} ms\n")
         if self.defer:
             gf = gflags.cpu().numpy()
             per_state = (gf[:, :wd] | gf[:, wd:wd + 1]).reshape(-1)[:B]      # own flag or the group's

@@ -431,30 +431,69 @@ def prepare_layers_device(K, psi, n_sites, chi, num_layers, threshold=1 - 1e-6, 
     return gates_all, layer_kinds, overlaps, A
 
 
+def to_dense_batch(K, A):
+    """:func:`to_dense` for W states: A[i] (W, l, 2, r) -> (W, 2^N)."""
+    W = A[0].shape[0]
+    x = A[0].reshape(W, -1, A[0].shape[3])
+    for i in range(1, len(A)):
+        _, l, _, r = A[i].shape
+        x = K.gemm_batch(x, A[i].reshape(W, l, 2 * r)).reshape(W, -1, r)
+    return x.reshape(W, -1)
+
+
+def chi2_layer_lockstep(K, B, flags):
+    """Fast path of :func:`chi2_layer` for W states in ONE launch per step (static mode; B[i]: (W, l, 2, r) with all
+    bonds <= FUSED_MAX_BOND).  Same kernels, same arithmetic per state; an ambiguous truncation, a block structure
+    other than one block spanning all sites or a failed unitarity check sets the state's flag (the state is then redone
+    eagerly, where the accurate path and the error live).  Returns (gates (W, N, 16), kinds of a layer)."""
+    import torch
+    N = len(B)
+    W = B[0].shape[0]
+    facs = [None] * (N - 1)
+    prev = None
+    for i in range(N - 1):
+        prev = facs[i] = K.chi2_env_batch(prev, B[i])
+    C = K.zeros((W, N, 8))
+    bond = K.zeros((W, max(N - 1, 1)), dtype=torch.int32)
+    ambiguous = K.zeros((W,), dtype=torch.int32)
+    b_last = B[N - 1].shape[1]
+    T = K.zeros((W, b_last, 4))
+    T.view(W, b_last * 2, 2)[:, :, 0].copy_(B[N - 1].reshape(W, b_last * 2))
+    for i in range(N - 1, 0, -1):
+        T = K.chi2_bond_batch(facs[i - 1], T, B[i - 1], C, i, bond, i - 1, ambiguous)
+    K.chi2_first_batch(T, C)
+    K.expect_ints_batch(ambiguous.view(W, 1), 1, 0, flags)
+    gates, kinds, bad = K.complete_unitaries_batch(C, bond, N)
+    if N > 1:
+        K.expect_ints_batch(kinds, N - 1, 2, flags)
+    K.expect_ints_batch(kinds[:, N - 1:], 1, 1, flags)
+    K.expect_ints_batch(bad.view(W, 1), 1, 0, flags)
+    return gates, [2] * (N - 1) + [1]
+
+
 def prepare_layers_lockstep(K, psis, n_sites, chi, num_layers, threshold, flags):
     """:func:`prepare_layers_device` for W small states AT ONCE in the static (CUDA-graph) mode of one stream.
-    A graph lane executes its kernels one after the other, and the kernels of a small register are single CTAs:
-    one state per lane keeps one SM busy.  Here the W states advance in lock step -- same shapes by the static
-    assumptions -- so that the dominant kernel, the single-CTA Jacobi SVD, is launched ONCE per split for all W
-    (grid = W); the cheap bookkeeping kernels stay per state.  ``flags``: int32[W + 1] device vector, flags[w] is
-    state w's "an assumption failed" flag, flags[W] the group's (a batched SVD did not converge).
-    Returns [(gates_all, kinds per layer, MPS)] per state; ``psis`` are normalised in place."""
+    A graph lane executes its kernels one after the other, the kernels of a small register are single CTAs, and the
+    front end retires a bounded number of graph nodes per second: one state per lane keeps one SM busy and a batch
+    is bound by its node count.  Here the W states advance in lock step -- same shapes by the static assumptions --
+    and EVERY step is one launch for all of them (grid = W or grid.y = W; the *_batch entries of the C ABI): the
+    single-CTA Jacobi SVDs, the split + absorb, the chi=2 truncation, the contraction + gate, the overlap.
+    ``psis``: (W, 2^N) device tensor, normalised in place.  ``flags``: int32[W + 1], flags[w] = state w's "an
+    assumption failed" flag, flags[W] the group's (a batched SVD did not converge).
+    Returns (gates (W, L*N, 16) in application order, [kinds] * L, A) with A[i] the batched MPS sites (W, l, 2, r)."""
+    import torch
     assert K.static and chi
-    W, N = len(psis), int(n_sites)
+    W, N = int(psis.shape[0]), int(n_sites)
     grp = flags[W:W + 1]
-
-    def per_state(w):
-        K.mismatch = flags[w:w + 1]
-
+    fl = flags[:W]
     for w in range(W):
-        per_state(w)
+        K.mismatch = flags[w:w + 1]
         K.div_sqrt(psis[w], K.vdot(psis[w], psis[w]))                 # quick Ket normalisation
     # ---- A1 + A2: TT-SVD in Schmidt form with max_bond (from_dense_truncated) ----
-    A = [[None] * N for _ in range(W)]
+    A = [None] * N
     r = 1
-    X = K.empty((W, 2 ** (N - 1), 2))
-    for w in range(W):
-        K.scale_copy(psis[w].reshape(-1, 2), out=X[w])
+    X = psis.reshape(W, 2 ** (N - 1), 2)
+    Tl = None
     for i in range(N - 1, 0, -1):
         m, nn = 2 ** i, 2 * r
         k = min(m, nn)
@@ -462,60 +501,35 @@ def prepare_layers_lockstep(K, psis, n_sites, chi, num_layers, threshold, flags)
         U, S, Vh = K.svd_small_batch(X, backmult=True)
         n = min(k, chi)
         Xn = K.empty((W, m // 2, 2 * n)) if i > 1 else None
-        Tl = []
-        for w in range(W):
-            per_state(w)
-            left, right = K.split_absorb(U[w], S[w], Vh[w], CUTOFF, MODE_REL, chi, n, out_left=None if Xn is None else Xn[w])
-            A[w][i] = right.reshape(n, 2, r)
-            Tl.append(left)
+        Tl, right = K.split_absorb_batch(U, S, Vh, CUTOFF, MODE_REL, chi, n, fl, out_left=Xn)
+        A[i] = right.reshape(W, n, 2, r)
         X, r = Xn, n
-    for w in range(W):
-        A[w][0] = Tl[w].reshape(1, 2, r)
+    A[0] = Tl.reshape(W, 1, 2, r)
     # ---- layers (disentangle) ----
-    B = []
+    B = [a.clone() for a in A]
     for w in range(W):
-        per_state(w)
-        Bw = copy_mps(K, A[w])
-        normalize_site0(K, Bw)
-        B.append(Bw)
-    layer_gates = [[] for _ in range(W)]
+        K.mismatch = flags[w:w + 1]
+        a0 = B[0][w]
+        K.div_sqrt(a0, K.vdot(a0, a0))                                # normalize_site0
+    layer_gates = []
     kinds = None
     for _ in range(num_layers):
-        G = []
-        for w in range(W):
-            per_state(w)
-            g, kinds = chi2_layer(K, B[w])                            # mps.py:849-891
-            G.append(g)
-            layer_gates[w].append(g)
+        G, kinds = chi2_layer_lockstep(K, B, fl)                      # mps.py:849-891
+        layer_gates.append(G)
         # inverse layer (mps.py:944-971), one block spanning all sites by the static assumption
-        for w in range(W):
-            per_state(w)
-            l, _, rr = B[w][N - 1].shape
-            K.site_gate(B[w][N - 1], l, rr, G[w][N - 1], dagger=True)
+        K.site_gate_batch(B[N - 1], G[:, N - 1], dagger=True)
         for i in range(N - 2, -1, -1):
-            l, _, b = B[0][i].shape
-            rr = B[0][i + 1].shape[2]
-            Xt = K.empty((W, 2 * l, 2 * rr))
-            for w in range(W):
-                per_state(w)
-                K.theta_small(B[w][i], B[w][i + 1], G[w][i], True, out=Xt[w])
+            l, rr = B[i].shape[1], B[i + 1].shape[3]
+            Xt = K.theta_small_batch(B[i], B[i + 1], G[:, i], True)
             K.mismatch = grp
             U, S, Vh = K.svd_small_batch(Xt, backmult=True)
             k = S.shape[1]
-            for w in range(W):
-                per_state(w)
-                left, right = K.split_absorb(U[w], S[w], Vh[w], CUTOFF, MODE_RSUM2, 0, k)
-                B[w][i] = left.reshape(l, 2, k)
-                B[w][i + 1] = right.reshape(k, 2, rr)
-        for w in range(W):
-            per_state(w)
-            zero_overlap(K, B[w], break_tol=(1 - threshold) + 1e-5)   # sequential.py:390 validated on the device
-    import torch
-    out = []
-    for w in range(W):
-        lg = list(reversed(layer_gates[w]))                           # sequential.py:396
-        out.append((torch.cat(lg, dim=0).contiguous(), [kinds] * num_layers, A[w]))
-    return out
+            left, right = K.split_absorb_batch(U, S, Vh, CUTOFF, MODE_RSUM2, 0, k, fl)
+            B[i] = left.reshape(W, l, 2, k)
+            B[i + 1] = right.reshape(W, k, 2, rr)
+        K.zero_overlap_batch(B, (1 - threshold) + 1e-5, fl)           # sequential.py:390 validated on the device
+    gates_all = torch.cat(list(reversed(layer_gates)), dim=1).contiguous()        # sequential.py:396
+    return gates_all, [kinds] * num_layers, A
 
 
 def prepare_device(K, psi, n_sites, chi, num_layers, num_sweeps, threshold=1 - 1e-6, record=None, fused=True,

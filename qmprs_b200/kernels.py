@@ -388,6 +388,114 @@ class CudaKernels:
                     "qm_zero_overlap")
         return out
 
+    # ---- the same for W same-shape states in one launch (lock-step lanes of graphs.py) --------------------
+    @staticmethod
+    def _strides(*vals):
+        return (ctypes.c_longlong * len(vals))(*[int(v) for v in vals])
+
+    @staticmethod
+    def _bstride(t):
+        """Element stride between the states of a batched tensor whose per-state block is dense."""
+        assert t[0].is_contiguous(), "per-state blocks of a batched tensor must be dense"
+        return t.stride(0) if t.shape[0] > 1 else t[0].numel()
+
+    def gemm_batch(self, A, B):
+        """out[w] = A[w] @ B[w] (W, m, k) x (W, k, n), one launch (qm_zgemm's batch argument)."""
+        W, m, k = A.shape
+        n = B.shape[2]
+        assert B.shape[0] == W and B.shape[1] == k
+        out = self.empty((W, m, n))
+        self._check(self.lib.qm_zgemm(m, n, k, 1.0, 0.0, _p(A), k, _p(B), n, 0.0, 0.0, _p(out), n, W,
+                                      self._bstride(A), self._bstride(B), m * n, 0, self._stream()), "qm_zgemm")
+        return out
+
+    def split_absorb_batch(self, U, S, Vh, cutoff, mode, max_bond, expect, flags, out_left=None):
+        """:meth:`split_absorb` on U (W, m, k), S (W, k), Vh (W, k, n): left (W, m, expect), right (W, expect, n);
+        ``flags``: int32[W], one "assumption failed" flag per state."""
+        W, m, k = U.shape
+        n = Vh.shape[2]
+        left = self.empty((W, m, expect)) if out_left is None else out_left
+        right = self.empty((W, expect, n))
+        assert left.is_contiguous() and left.numel() == W * m * expect
+        self._check(self.lib.qm_split_absorb_batch(
+            _p(U), k, _p(S), _p(Vh), n, m, n, k, float(cutoff), int(mode), int(max_bond or 0), int(expect), _p(left),
+            _p(right), _p(flags), W, self._strides(self._bstride(U), self._bstride(S), self._bstride(Vh), m * expect,
+                                                   expect * n), self._stream()), "qm_split_absorb_batch")
+        return left.reshape(W, m, expect), right
+
+    def theta_small_batch(self, A, A2, G, dagger):
+        """A (W, l, 2, b), A2 (W, b, 2, r), G (W, 16) view (any state stride) -> theta (W, 2l, 2r)."""
+        W, l, _, b = A.shape
+        r = A2.shape[3]
+        X = self.empty((W, 2 * l, 2 * r))
+        self._check(self.lib.qm_theta_small_batch(
+            _p(A), _p(A2), l, b, r, _p(G), 1 if dagger else 0, _p(X), W,
+            self._strides(self._bstride(A), self._bstride(A2), G.stride(0), 4 * l * r), self._stream()),
+            "qm_theta_small_batch")
+        return X
+
+    def chi2_env_batch(self, Lprev, B):
+        W, l, _, r = B.shape
+        out = self.empty((W, r, r))
+        self._check(self.lib.qm_chi2_env_batch(
+            _p(Lprev), _p(B), l, r, _p(out), W,
+            self._strides(0 if Lprev is None else self._bstride(Lprev), self._bstride(B), r * r), self._stream()),
+            "qm_chi2_env_batch")
+        return out
+
+    def chi2_bond_batch(self, L, T, Bprev, C, site, bond, slot, ambiguous):
+        """One bond of the chi=2 truncation for W states: C (W, N, 8) receives site ``site``, bond (W, nb) slot
+        ``slot``, ambiguous int32[W]."""
+        W, b, _ = T.shape
+        l0 = Bprev.shape[1]
+        Tout = self.empty((W, l0, 4))
+        Cs, bs = C[:, site], bond[:, slot]
+        self._check(self.lib.qm_chi2_bond_batch(
+            _p(L), b, _p(T), _p(Bprev), l0, CUTOFF, TIE_REL, CHI2_AMBIGUOUS_REL, _p(Cs), _p(bs), _p(ambiguous), _p(Tout),
+            W, self._strides(self._bstride(L), self._bstride(T), self._bstride(Bprev), C.stride(0), bond.stride(0), 1,
+                             l0 * 4), self._stream()), "qm_chi2_bond_batch")
+        return Tout
+
+    def chi2_first_batch(self, T, C):
+        W = T.shape[0]
+        self._check(self.lib.qm_chi2_first_batch(_p(T), _p(C), W, self._bstride(T), C.stride(0), self._stream()),
+                    "qm_chi2_first_batch")
+
+    def complete_unitaries_batch(self, C, bond, n_sites):
+        W = C.shape[0]
+        assert C.is_contiguous() and C.shape[1] == n_sites
+        gates = self.empty((W, n_sites, 16))
+        kinds = self.empty((W, n_sites), I32)
+        bad = self.zeros((W,), I32)
+        self._check(self.lib.qm_complete_unitaries_batch(_p(C), _p(bond), n_sites, _p(gates), _p(kinds), _p(bad), SIGN_TOL,
+                                                         W, bond.stride(0), self._stream()),
+                    "qm_complete_unitaries_batch")
+        return gates, kinds, bad
+
+    def expect_ints_batch(self, vals, n, scalar, flags):
+        """vals: (W, >= n) int32 view; flags[w] = 1 where one of the first n values of row w is not ``scalar``."""
+        W = vals.shape[0]
+        self._check(self.lib.qm_expect_ints_batch(_p(vals), None, int(n), int(scalar), _p(flags), W, vals.stride(0),
+                                                  self._stream()), "qm_expect_ints_batch")
+
+    def site_gate_batch(self, B, G, dagger):
+        """B (W, l, 2, r) in place, G (W, 16) view (first four entries = the 2x2 gate)."""
+        W, l, _, r = B.shape
+        self._check(self.lib.qm_site_gate_batch(_p(B), l, r, _p(G), 1 if dagger else 0, W, self._bstride(B), G.stride(0),
+                                                self._stream()), "qm_site_gate_batch")
+
+    def zero_overlap_batch(self, B, tol, flags):
+        """<0..0|psi_w> for the W states of the batched sites B[i] (W, l, 2, r); early-break check per state."""
+        n = len(B)
+        W = B[0].shape[0]
+        ptrs = (ctypes.c_void_p * n)(*[b.data_ptr() for b in B])
+        dims = (ctypes.c_int * (n + 1))(*([int(B[0].shape[1])] + [int(b.shape[3]) for b in B]))
+        out = self.empty((W,))
+        self._check(self.lib.qm_zero_overlap_batch(ptrs, dims, n, float(tol), _p(out), _p(flags), W,
+                                                   self._strides(*[self._bstride(b) for b in B]), self._stream()),
+                    "qm_zero_overlap_batch")
+        return out
+
     def reverse3(self, a):
         l, _, r = a.shape
         out = self.empty((r, 2, l))

@@ -597,6 +597,111 @@ def test_svd_small_graded_and_rank_deficient(K):
     K.check_small_svd()
 
 
+def test_small_register_batch_entries_equal_per_state_calls(K):
+    """The *_batch entries (one launch for W same-shape states: lock-step lanes of graphs.py) against W calls of the
+    single-state entries on the same data: bit-identical outputs, flags per state."""
+    import torch
+    from qmprs_b200 import host
+    rng = np.random.default_rng(4242)
+    W, N = 5, 6
+    Cs, bonds = [], []                                      # isometries of real chi=2 layers (eager mode)
+    for w in range(W):
+        psi = crand(rng, 2 ** N)
+        dbg = {}
+        host.chi2_layer(K, host.build_mps(K, K.from_host(psi / np.linalg.norm(psi)), N, 4), debug=dbg)
+        Cs.append(dbg["C"]); bonds.append(dbg["bond"])
+    K.begin_static()
+    try:
+        flags = K.zeros((W,), dtype=torch.int32)
+        # split + absorb (both modes; state 3 gets a spectrum whose rank differs from the assumed one)
+        m, n, k = 12, 20, 12
+        U = K.from_host(np.stack([np.linalg.qr(crand(rng, m, k))[0] for _ in range(W)]))
+        Vh = K.from_host(np.stack([np.linalg.qr(crand(rng, n, k))[0].conj().T for _ in range(W)]))
+        sv = np.stack([np.sort(rng.random(k))[::-1] + 0.1 for _ in range(W)])
+        sv[3, -2:] = 1e-9 * sv[3, 0]
+        S = K.from_host(sv, torch.float64)
+        for mode, mb, expect in ((1, 0, k), (0, 8, 8)):
+            flags.zero_()
+            left, right = K.split_absorb_batch(U, S, Vh, 1e-10, mode, mb, expect, flags)
+            ref_flags = []
+            for w in range(W):
+                K.mismatch.zero_()
+                l1, r1 = K.split_absorb(U[w], S[w], Vh[w], 1e-10, mode, mb, expect)
+                ref_flags.append(int(K.mismatch.item()))
+                assert torch.equal(left[w], l1) and torch.equal(right[w], r1)
+            assert flags.tolist() == ref_flags and (mode == 0 or ref_flags[3] == 1)
+        K.mismatch.zero_()
+        # contraction with the gate; the gates are rows of a (W, N, 16) tensor (strided view)
+        l, b, r = 3, 5, 4
+        A, A2 = K.from_host(crand(rng, W, l, 2, b)), K.from_host(crand(rng, W, b, 2, r))
+        G = K.from_host(crand(rng, W, N, 16))
+        for dag in (False, True):
+            X = K.theta_small_batch(A, A2, G[:, 2], dag)
+            for w in range(W):
+                assert torch.equal(X[w], K.theta_small(A[w], A2[w], G[w, 2], dag))
+        # one-qubit gate on the last site
+        Bs = K.from_host(crand(rng, W, l, 2, 1))
+        ref = Bs.clone()
+        K.site_gate_batch(Bs, G[:, N - 1], True)
+        for w in range(W):
+            K.site_gate(ref[w], l, 1, G[w, N - 1], True)
+        assert torch.equal(Bs, ref)
+        # chi=2 environments, bond step, first site, completion, checks
+        Bt = K.from_host(crand(rng, W, l, 2, r))
+        L0 = K.chi2_env_batch(None, Bt)
+        Lp = K.from_host(crand(rng, W, l, l))
+        L1 = K.chi2_env_batch(Lp, Bt)
+        for w in range(W):
+            assert torch.equal(L0[w], K.chi2_env(None, Bt[w])) and torch.equal(L1[w], K.chi2_env(Lp[w], Bt[w]))
+        bb, l0 = 7, 3
+        Lm = crand(rng, W, bb, bb)
+        Lm = K.from_host(Lm @ np.conj(Lm).transpose(0, 2, 1))
+        T, Bprev = K.from_host(crand(rng, W, bb, 4)), K.from_host(crand(rng, W, l0, 2, bb))
+        C, bond, amb = K.zeros((W, N, 8)), K.zeros((W, N - 1), dtype=torch.int32), K.zeros((W,), dtype=torch.int32)
+        Tout = K.chi2_bond_batch(Lm, T, Bprev, C, 4, bond, 3, amb)
+        for w in range(W):
+            c1, b1, a1 = K.zeros((8,)), K.zeros((1,), dtype=torch.int32), K.zeros((1,), dtype=torch.int32)
+            t1 = K.chi2_bond(Lm[w], T[w], Bprev[w], c1, b1, a1)
+            assert torch.equal(Tout[w], t1) and torch.equal(C[w, 4], c1)
+            assert int(bond[w, 3]) == int(b1) and int(amb[w]) == int(a1)
+        T0 = K.from_host(crand(rng, W, 1, 4))
+        K.chi2_first_batch(T0, C)
+        for w in range(W):
+            c1 = K.zeros((8,))
+            K.chi2_first(T0[w], c1)
+            assert torch.equal(C[w, 0], c1)
+        # completion of isometries into gates: take the C tensors of real chi=2 layers
+        Cb, bondb = torch.stack(Cs).contiguous(), torch.stack(bonds).contiguous()
+        gates, kinds, bad = K.complete_unitaries_batch(Cb, bondb, N)
+        for w in range(W):
+            g1, k1, b1 = K.complete_unitaries(Cs[w], bonds[w], N)
+            assert torch.equal(gates[w], g1) and torch.equal(kinds[w], k1) and int(bad[w]) == int(b1)
+        flags.zero_()
+        kinds2 = kinds.clone(); kinds2[2, 1] = 1
+        K.expect_ints_batch(kinds2, N - 1, 2, flags)
+        assert flags.tolist() == [0, 0, 1, 0, 0]
+        flags.zero_()
+        K.expect_ints_batch(kinds2[:, N - 1:], 1, 1, flags)
+        assert flags.tolist() == [0] * W
+        # <0..0|psi>, early-break check per state
+        sites = [K.from_host(crand(rng, W, 1, 2, 3)), K.from_host(crand(rng, W, 3, 2, 2)), K.from_host(crand(rng, W, 2, 2, 1))]
+        sites[0][1] = 0; sites[0][1, 0, 0, 0] = 1; sites[1][1] = 0; sites[1][1, 0, 0, 0] = 1; sites[2][1] = 0; sites[2][1, 0, 0, 0] = 1
+        flags.zero_()
+        out = K.zero_overlap_batch(sites, 1e-5, flags)
+        for w in range(W):
+            K.mismatch.zero_()
+            o1 = K.zero_overlap_fused([t[w] for t in sites], 1e-5)
+            assert torch.equal(out[w:w + 1], o1) and int(flags[w]) == int(K.mismatch.item())
+        assert flags.tolist() == [0, 1, 0, 0, 0]
+        # batched GEMM of to_dense
+        X, Y = K.from_host(crand(rng, W, 6, 5)), K.from_host(crand(rng, W, 5, 8))
+        Z = K.gemm_batch(X, Y)
+        for w in range(W):
+            assert torch.equal(Z[w], K.gemm(X[w], Y[w]))
+    finally:
+        K.end_static()
+
+
 def test_fused_small_register_kernels(K):
     """csrc/small_mps.cu against the kernel groups they replace (numpy here): split+absorb, theta with the gate,
     chi=2 environment and bond step, zero overlap."""
