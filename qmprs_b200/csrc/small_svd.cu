@@ -13,11 +13,13 @@
 // Deterministic (fixed shuffle trees, no atomics on data).
 #include "common.cuh"
 #include "qmprs_b200.h"
+#include <cstdlib>
 
 namespace {
 
 constexpr int NTS = 512;
 constexpr int MAXNV = 64;
+constexpr int EPL = 4;                                    // row elements a lane keeps in registers across a rotation
 constexpr size_t SMEM_CAP = 200 * 1024;
 
 __device__ __forceinline__ void circle_pair_s(int r, int k, int n, int& a, int& b) {
@@ -41,7 +43,11 @@ __host__ __device__ __forceinline__ size_t small_smem(const Dims& d) {
     return (size_t)d.nv * d.ldw * sizeof(cplx) + (size_t)MAXNV * (sizeof(double) + sizeof(int)) + 64;
 }
 
-__global__ void __launch_bounds__(NTS, 1)
+// 2 CTAs per SM (64 registers): co-resident problems of a batch overlap their shuffle / FP64 / barrier chains; measured
+// on config 5: layer-extraction phase 713 -> 611-638 ms with 3 per SM and no register caching -- the solver is bound by
+// shared-memory traffic (a 64 x 64 round moves 3 x 64 KB), hence the caching below
+template <bool CACHE>
+__global__ void __launch_bounds__(NTS, CACHE ? 2 : 3)
 k_svd_small(int m, int n, const cplx* __restrict__ A_, long long lda, long long sA, cplx* __restrict__ U_, long long ldu,
             long long sU, double* __restrict__ S_, long long sS, cplx* __restrict__ Vh_, long long ldvh, long long sVh,
             double tol2, int max_sweeps, int backmult, int* __restrict__ mismatch) {
@@ -76,6 +82,7 @@ k_svd_small(int m, int n, const cplx* __restrict__ A_, long long lda, long long 
     while (tpp > 1 && npairs * tpp > NTS) tpp >>= 1;
     const int k = tid / tpp, j = tid % tpp;
     const bool has_pair = k < npairs;
+    const bool cached = CACHE && len <= EPL * tpp;
     int converged = nv < 2 ? 1 : 0;
     for (int sweep = 0; sweep < max_sweeps && !converged; sweep++) {
         int any = 0;
@@ -90,12 +97,30 @@ k_svd_small(int m, int n, const cplx* __restrict__ A_, long long lda, long long 
             cplx* wq = W + q * ldw;
             double a = 0.0, b = 0.0;
             cplx g = mk(0.0, 0.0);
+            // a lane's elements of the two rows stay in registers from the dot products to the rotation when they
+            // are at most EPL each (always in config 5): the solver is bound by shared-memory traffic, 3 -> 2 passes
+            cplx xr[EPL], yr[EPL];
             if (valid) {
-                for (int c = j; c < len; c += tpp) {
-                    const cplx x = wp[c], y = wq[c];
-                    a += cabs2(x);
-                    b += cabs2(y);
-                    cfmac(g, x, y);                        // x conj(y)
+                if (cached) {
+#pragma unroll
+                    for (int e = 0; e < EPL; e++) {
+                        const int c = j + e * tpp;
+                        xr[e] = c < len ? wp[c] : mk(0.0, 0.0);
+                        yr[e] = c < len ? wq[c] : mk(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int e = 0; e < EPL; e++) {      // same order of accumulation as the loop below
+                        a += cabs2(xr[e]);
+                        b += cabs2(yr[e]);
+                        cfmac(g, xr[e], yr[e]);
+                    }
+                } else {
+                    for (int c = j; c < len; c += tpp) {
+                        const cplx x = wp[c], y = wq[c];
+                        a += cabs2(x);
+                        b += cabs2(y);
+                        cfmac(g, x, y);                        // x conj(y)
+                    }
                 }
             }
             for (int off = tpp >> 1; off > 0; off >>= 1) {
@@ -114,7 +139,19 @@ k_svd_small(int m, int n, const cplx* __restrict__ A_, long long lda, long long 
                 const double s = copysign(R, dd);
                 const double cc = den * R;
                 const cplx o = mk(-s * g.x, -s * g.y);
-                for (int c = j; c < lenx; c += tpp) {
+                int c0 = j;
+                if (cached) {
+#pragma unroll
+                    for (int e = 0; e < EPL; e++) {
+                        const int c = j + e * tpp;
+                        if (c < len) {
+                            wp[c] = cadd(cscale(xr[e], cc), cmul(o, yr[e]));
+                            wq[c] = csub(cscale(yr[e], cc), cmul(cconj(o), xr[e]));
+                        }
+                    }
+                    c0 = j + ((len - j + tpp - 1) / tpp) * tpp;      // first column >= len of this lane
+                }
+                for (int c = c0; c < lenx; c += tpp) {
                     const cplx x = wp[c], y = wq[c];
                     wp[c] = cadd(cscale(x, cc), cmul(o, y));
                     wq[c] = csub(cscale(y, cc), cmul(cconj(o), x));
@@ -217,14 +254,29 @@ extern "C" int qm_svd_small(int m, int n, const void* A, long long lda, long lon
     if (!qm_svd_small_fits(m, n, flags)) return -3;
     const Dims d = small_dims(m, n, backmult);
     const size_t smem = small_smem(d);
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        QM_CUDA(cudaFuncSetAttribute(k_svd_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
-        attr_set = SMEM_CAP;
+    // QM_SVD_SMALL_CACHE=1: row elements cached in registers across a rotation, 64 registers, 2 CTAs per SM;
+    // 0 (default): 40 registers, 3 CTAs per SM (measured on config 5: profiles/bench_r02_c5_*.json)
+    static const int cache = getenv("QM_SVD_SMALL_CACHE") ? atoi(getenv("QM_SVD_SMALL_CACHE")) : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        // largest shared-memory carve-out for every launch: the batch path interleaves these CTAs with other small
+        // kernels on the same SMs, and CTAs that need different carve-outs cannot share an SM
+        QM_CUDA(cudaFuncSetAttribute(k_svd_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
+        QM_CUDA(cudaFuncSetAttribute(k_svd_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
+        QM_CUDA(cudaFuncSetAttribute(k_svd_small<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+        QM_CUDA(cudaFuncSetAttribute(k_svd_small<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+        attr_set = true;
     }
-    QM_LAUNCH(QM_CLS_SVD_EIG, st, k_svd_small<<<batch, NTS, smem, st>>>(
-        m, n, (const cplx*)A, lda, strideA, (cplx*)U, ldu, strideU, (double*)S, strideS, (cplx*)Vh, ldvh, strideVh,
-        tol * tol, max_sweeps, backmult, (int*)mismatch));
+    if (cache)
+        QM_LAUNCH(QM_CLS_SVD_EIG, st, k_svd_small<true><<<batch, NTS, smem, st>>>(
+            m, n, (const cplx*)A, lda, strideA, (cplx*)U, ldu, strideU, (double*)S, strideS, (cplx*)Vh, ldvh, strideVh,
+            tol * tol, max_sweeps, backmult, (int*)mismatch));
+    else
+        QM_LAUNCH(QM_CLS_SVD_EIG, st, k_svd_small<false><<<batch, NTS, smem, st>>>(
+            m, n, (const cplx*)A, lda, strideA, (cplx*)U, ldu, strideU, (double*)S, strideS, (cplx*)Vh, ldvh, strideVh,
+            tol * tol, max_sweeps, backmult, (int*)mismatch));
     QM_CHECK_LAUNCH();
     return 0;
 }
