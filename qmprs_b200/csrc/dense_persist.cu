@@ -23,6 +23,8 @@
 #include "common.cuh"
 #include "polar.cuh"
 #include "qmprs_b200.h"
+#include <cstdlib>
+#include <cstdio>
 
 namespace {
 
@@ -117,6 +119,12 @@ __device__ __forceinline__ void env_pass(cplx* tbar, const cplx* c, int nbits, i
     }
 }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct Smem {
     double wsum[NTP / 32][32];
     double Ep[NTP];
@@ -146,9 +154,17 @@ __device__ __forceinline__ void reduce_polar(const double* partials, Smem& sm, c
                                              const cplx* vw_in, cplx* vw_out) {
     {
         const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
+        // all of a thread's partials in flight at once (one L2 round trip instead of three), summed in the same order
+        constexpr int NLD = (MAXBLK + NTP / 32 - 1) / (NTP / 32);
+        double v[NLD];
+#pragma unroll
+        for (int k = 0; k < NLD; k++) {
+            const unsigned int b = sl + k * (NTP / 32);
+            v[k] = b < gridDim.x ? __ldcg(partials + (long long)b * 32 + e) : 0.0;
+        }
         double ssum = 0.0;
-#pragma unroll 8
-        for (unsigned int b = sl; b < gridDim.x; b += NTP / 32) ssum += __ldcg(partials + (long long)b * 32 + e);
+#pragma unroll
+        for (int k = 0; k < NLD; k++) ssum += v[k];
         sm.Ep[threadIdx.x] = ssum;
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -178,7 +194,8 @@ __device__ __forceinline__ int low_bit(int nbits, int site, int kind) { return k
 __global__ void __launch_bounds__(NTP, 1)
 k_sweeps_persist(cplx* cs, cplx* tbar, const cplx* __restrict__ target, int nbits, cplx* gates,
                  const int* __restrict__ sites, const int* __restrict__ kinds, int n_gates, int num_sweeps,
-                 double* partials, unsigned int* bar, cplx* vwarm /* [2][n_gates][16] */, cplx* envs) {
+                 double* partials, unsigned int* bar, cplx* vwarm /* [2][n_gates][16] */, cplx* envs, int prefetch,
+                 unsigned long long* dbg) {
     // (no __restrict__ on buffers this kernel both writes and reads across grid barriers: their loads must stay
     // coherent, never ld.global.nc)
     __shared__ Smem sm;
@@ -197,6 +214,8 @@ k_sweeps_persist(cplx* cs, cplx* tbar, const cplx* __restrict__ target, int nbit
             tbar[i] = mk(t.x, -t.y);
         }
         grid_barrier(bar, epoch);
+        const bool timing = dbg && blockIdx.x == 0 && threadIdx.x == 0;       // QM_PERSIST_DEBUG: ns per phase, CTA 0
+        unsigned long long t0 = timing ? gtimer() : 0;
         for (int g = 0; g < n_gates; g++) {
             const int kind = kinds[g], site = sites[g];
             if (threadIdx.x < 16) sm.M[threadIdx.x] = gates[(long long)g * 16 + threadIdx.x];
@@ -207,6 +226,7 @@ k_sweeps_persist(cplx* cs, cplx* tbar, const cplx* __restrict__ target, int nbit
             else stream_gate<2>(xin, xout, nbits, low_bit(nbits, site, 1), sm.M);
             grid_barrier(bar, epoch);
         }
+        if (timing) { const unsigned long long t1 = gtimer(); dbg[0] += t1 - t0; t0 = t1; }
         // ---- backward pass ----
         for (int g = n_gates - 1; g >= 0; g--) {
             const int ck = kinds[g];
@@ -252,14 +272,25 @@ k_sweeps_persist(cplx* cs, cplx* tbar, const cplx* __restrict__ target, int nbit
                     if (ck == 2) env_pass<2, 4, 0>(tbar, c, nbits, cb, sm.M, acc);
                     else env_pass<1, 2, 0>(tbar, c, nbits, cb, sm.M, acc);
             }
+            if (timing) { const unsigned long long t1 = gtimer(); dbg[1] += t1 - t0; t0 = t1; }
             double* part = partials + (long long)par * MAXBLK * 32;
             cta_partial(acc, sm, part);
+            if (prefetch && g > 0) {
+                // HBM idles during the barrier + reduction + polar that follow: pull the next step's stored circuit
+                // state (read once, last touched a whole forward pass ago) into L2 meanwhile
+                const char* nxt = (const char*)(cs + (long long)(g - 1) * n);
+                const long long lines = (n * (long long)sizeof(cplx)) >> 7;
+                for (long long i = gtid; i < lines; i += gthreads)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (i << 7)));
+            }
             grid_barrier(bar, epoch);
+            if (timing) { const unsigned long long t1 = gtimer(); dbg[2] += t1 - t0; t0 = t1; }
             cplx* G = gates + (long long)g * 16;
             cplx* env = envs ? envs + (long long)g * 16 : nullptr;
             if (ck == 2) reduce_polar<4>(part, sm, G, env, vw_in + (long long)g * 16, vw_out + (long long)g * 16);
             else reduce_polar<2>(part, sm, G, env, vw_in + (long long)g * 16, vw_out + (long long)g * 16);
             par ^= 1;
+            if (timing) { const unsigned long long t1 = gtimer(); dbg[3] += t1 - t0; t0 = t1; }
         }
         grid_barrier(bar, epoch);          // gates of this sweep (written by CTA 0) visible to every CTA's forward pass
     }
@@ -301,11 +332,28 @@ extern "C" int qm_sweeps_persist(void* cs, void* tbar, const void* target, int n
     QM_CUDA(cudaMemsetAsync(vwarm, 0, 2LL * n_gates * 16 * sizeof(cplx), st));
     cplx* cs_ = (cplx*)cs; cplx* tbar_ = (cplx*)tbar; const cplx* target_ = (const cplx*)target;
     cplx* gates_ = (cplx*)gates; cplx* envs_ = (cplx*)envs;
+    static int prefetch = getenv("QM_PERSIST_PREFETCH") ? atoi(getenv("QM_PERSIST_PREFETCH")) : 1;
+    static const int debug = getenv("QM_PERSIST_DEBUG") ? atoi(getenv("QM_PERSIST_DEBUG")) : 0;
+    unsigned long long* dbg = nullptr;
+    if (debug) {
+        QM_CUDA(cudaMalloc(&dbg, 4 * sizeof(unsigned long long)));
+        QM_CUDA(cudaMemsetAsync(dbg, 0, 4 * sizeof(unsigned long long), st));
+    }
     void* args[] = {&cs_, &tbar_, &target_, &n_sites, &gates_, &sites_dev, &kinds_dev, &n_gates, &num_sweeps,
-                    &partials, &bar, &vwarm, &envs_};
+                    &partials, &bar, &vwarm, &envs_, &prefetch, &dbg};
     // forward: read c_k, write c_{k+1} (32 B per amplitude and gate); backward: tbar read + write, c_k read (48 B)
     qm_prof_work(QM_CLS_ENV, 80.0 * (double)(1LL << n_sites) * n_gates * num_sweeps);
     QM_LAUNCH(QM_CLS_ENV, st, cudaLaunchCooperativeKernel((void*)k_sweeps_persist, dim3(grid), dim3(NTP), args, 0, st));
     QM_CHECK_LAUNCH();
+    if (dbg) {
+        unsigned long long h[4];
+        QM_CUDA(cudaStreamSynchronize(st));
+        QM_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        QM_CUDA(cudaFree(dbg));
+        const double steps = (double)n_gates * num_sweeps;
+        fprintf(stderr, "[qm_sweeps_persist] us per gate-step (CTA 0): forward %.2f, backward pass %.2f, partial + barrier "
+                        "%.2f, reduce + polar %.2f\n", h[0] / steps / 1e3, h[1] / steps / 1e3, h[2] / steps / 1e3,
+                h[3] / steps / 1e3);
+    }
     return 0;
 }
