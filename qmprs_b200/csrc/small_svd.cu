@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int NTS = 512;
+constexpr int NTS = 256;                                  // threads per CTA (max; see qm_svd_small)
 constexpr int MAXNV = 64;
 constexpr int EPL = 4;                                    // row elements a lane keeps in registers across a rotation
 constexpr size_t SMEM_CAP = 200 * 1024;
@@ -57,21 +57,21 @@ k_svd_small(int m, int n, const cplx* __restrict__ A_, long long lda, long long 
     cplx* W = (cplx*)ss_smem;
     double* sig = (double*)(W + (size_t)nv * ldw);
     int* perm = (int*)(sig + MAXNV);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, nts = blockDim.x;     // 256 or 512 threads (host choice)
     const cplx* A = A_ + (long long)blockIdx.x * sA;
     // ---- load W = A (m < n) or A^T, identity extension ----
     if (m < n) {
-        for (int idx = tid; idx < m * n; idx += NTS) {
+        for (int idx = tid; idx < m * n; idx += nts) {
             const int i = idx / n, c = idx % n;
             W[i * ldw + c] = A[(long long)i * lda + c];
         }
     } else {
-        for (int idx = tid; idx < m * n; idx += NTS) {
+        for (int idx = tid; idx < m * n; idx += nts) {
             const int a = idx / n, j = idx % n;
             W[j * ldw + a] = A[(long long)a * lda + j];
         }
     }
-    for (int idx = tid; idx < nv * ext; idx += NTS) {
+    for (int idx = tid; idx < nv * ext; idx += nts) {
         const int i = idx / ext, c = idx % ext;
         W[i * ldw + len + c] = mk(i == c ? 1.0 : 0.0, 0.0);
     }
@@ -79,7 +79,7 @@ k_svd_small(int m, int n, const cplx* __restrict__ A_, long long lda, long long 
     // ---- sweeps ----
     const int ne = nv + (nv & 1), npairs = ne / 2;
     int tpp = 32;                                          // lanes per pair (power of two, a pair never spans warps)
-    while (tpp > 1 && npairs * tpp > NTS) tpp >>= 1;
+    while (tpp > 1 && npairs * tpp > nts) tpp >>= 1;
     const int k = tid / tpp, j = tid % tpp;
     const bool has_pair = k < npairs;
     const bool cached = CACHE && len <= EPL * tpp;
@@ -164,7 +164,7 @@ k_svd_small(int m, int n, const cplx* __restrict__ A_, long long lda, long long 
     }
     if (!converged && mismatch && tid == 0) mismatch[0] = 1;
     // ---- singular values, sorted descending by counting rank ----
-    for (int i = tid >> 5; i < nv; i += NTS / 32) {
+    for (int i = tid >> 5; i < nv; i += nts / 32) {
         double s2 = 0.0;
         for (int c = lane; c < len; c += 32) s2 += cabs2(W[i * ldw + c]);
         s2 = warp_sum(s2);
@@ -189,13 +189,13 @@ k_svd_small(int m, int n, const cplx* __restrict__ A_, long long lda, long long 
     if (m < n) {
         // rows of W are sigma_j z_j:  Vh[j][c] = W[perm[j]][c] / sigma_j ;  U = J^H  or  A Z^H Sigma^-1
         if (Vh)
-            for (int idx = tid; idx < kk * n; idx += NTS) {
+            for (int idx = tid; idx < kk * n; idx += nts) {
                 const int jj = idx / n, c = idx % n, src = perm[jj];
                 const double s2 = sig[src];
                 Vh[(long long)jj * ldvh + c] = cscale(W[src * ldw + c], s2 > 0.0 ? rsqrt(s2) : 0.0);
             }
         if (U)
-            for (int idx = tid; idx < m * kk; idx += NTS) {
+            for (int idx = tid; idx < m * kk; idx += nts) {
                 const int a = idx / kk, jj = idx % kk, src = perm[jj];
                 cplx v;
                 if (ext) v = cconj(W[src * ldw + len + a]);
@@ -211,13 +211,13 @@ k_svd_small(int m, int n, const cplx* __restrict__ A_, long long lda, long long 
     } else {
         // rows of W are sigma_j u_j^T:  U[a][j] = W[perm[j]][a] / sigma_j ;  Vh = conj(J)  or  Sigma^-1 U^H A
         if (U)
-            for (int idx = tid; idx < m * kk; idx += NTS) {
+            for (int idx = tid; idx < m * kk; idx += nts) {
                 const int a = idx / kk, jj = idx % kk, src = perm[jj];
                 const double s2 = sig[src];
                 U[(long long)a * ldu + jj] = cscale(W[src * ldw + a], s2 > 0.0 ? rsqrt(s2) : 0.0);
             }
         if (Vh)
-            for (int idx = tid; idx < kk * n; idx += NTS) {
+            for (int idx = tid; idx < kk * n; idx += nts) {
                 const int jj = idx / n, c = idx % n, src = perm[jj];
                 cplx v;
                 if (ext) v = cconj(W[src * ldw + len + c]);
@@ -269,12 +269,17 @@ extern "C" int qm_svd_small(int m, int n, const void* A, long long lda, long lon
                                      cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
+    // threads per CTA: 256 -- a row pair of a 64-row problem gets 8 lanes instead of 16 (one shuffle stage less, the
+    // rotation formula evaluated by half as many lanes) and three CTAs of a batch share an SM.  Measured on config 5
+    // (layer-extraction phase of 4096 states): 512 threads 637 ms, 256: 499 ms, 128: 608 ms.  QM_SVD_SMALL_THREADS overrides.
+    static const int thr_env = getenv("QM_SVD_SMALL_THREADS") ? atoi(getenv("QM_SVD_SMALL_THREADS")) : 0;
+    const int nthreads = (thr_env >= 64 && thr_env <= NTS && thr_env % 32 == 0) ? thr_env : 256;
     if (cache)
-        QM_LAUNCH(QM_CLS_SVD_EIG, st, k_svd_small<true><<<batch, NTS, smem, st>>>(
+        QM_LAUNCH(QM_CLS_SVD_EIG, st, k_svd_small<true><<<batch, nthreads, smem, st>>>(
             m, n, (const cplx*)A, lda, strideA, (cplx*)U, ldu, strideU, (double*)S, strideS, (cplx*)Vh, ldvh, strideVh,
             tol * tol, max_sweeps, backmult, (int*)mismatch));
     else
-        QM_LAUNCH(QM_CLS_SVD_EIG, st, k_svd_small<false><<<batch, NTS, smem, st>>>(
+        QM_LAUNCH(QM_CLS_SVD_EIG, st, k_svd_small<false><<<batch, nthreads, smem, st>>>(
             m, n, (const cplx*)A, lda, strideA, (cplx*)U, ldu, strideU, (double*)S, strideS, (cplx*)Vh, ldvh, strideVh,
             tol * tol, max_sweeps, backmult, (int*)mismatch));
     QM_CHECK_LAUNCH();
