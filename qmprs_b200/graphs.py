@@ -210,16 +210,39 @@ class GraphedPreparer:
             return 0
         main = torch.cuda.current_stream(dev)
         host_states = None
+        stage = None                                       # staged host->device copy: (chunk of states, events)
         if hasattr(states, "data_ptr") and states.is_cuda:
             sdev = states.contiguous()
         else:
-            host_states = np.ascontiguousarray(np.asarray(states, dtype=np.complex128))
+            host_states = np.asarray(states, dtype=np.complex128)      # any row stride (a rank's shard is states[r::w])
+            dim = host_states.shape[1]
             # one pinned staging buffer per preparer, grown on demand (pinning 256 MB per call costs ~0.1 s)
             pin = getattr(self, "_pin_in", None)
-            if pin is None or pin.shape[0] < B or pin.shape[1] != host_states.shape[1]:
-                pin = self._pin_in = torch.empty(host_states.shape, dtype=torch.complex128).pin_memory()
-            pin[:B].copy_(torch.from_numpy(host_states))
-            sdev = pin[:B].to(dev, non_blocking=True)
+            if pin is None or pin.shape[0] < B or pin.shape[1] != dim:
+                pin = self._pin_in = torch.empty((B, dim), dtype=torch.complex128).pin_memory()
+            sdev = torch.empty((B, dim), dtype=torch.complex128, device=dev)
+            # the copy goes in chunks, each with its own event: the lanes start on the first chunk while the host is
+            # still staging the later ones (memcpy into pinned memory + DMA of 256 MB would otherwise sit in front of
+            # the whole batch)
+            chunk = max(self.width, min(B, max(1, (16 << 20) // (16 * dim))))
+            chunk = ((chunk + self.width - 1) // self.width) * self.width
+            stage = (chunk, {})
+
+        def staged(upto):
+            """Make sure the states [0, upto) are on their way to the device; returns the event to wait for."""
+            ck, evs = stage
+            last = None
+            c0 = len(evs) * ck
+            while c0 < min(upto, B):
+                c1 = min(c0 + ck, B)
+                pin[c0:c1].copy_(torch.from_numpy(host_states[c0:c1]))
+                sdev[c0:c1].copy_(pin[c0:c1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                evs[c0 // ck] = ev
+                c0 = c1
+            return evs[(min(upto, B) - 1) // ck]
+
         ng, nk = L * n * 32, L * n
         # constant part of the records of the static pipeline: one block per layer, all layers used
         kinds_layer = [2] * (n - 1) + [1]
@@ -241,6 +264,8 @@ class GraphedPreparer:
             for gi, g0 in enumerate(range(0, B, wd)):
                 lane = lanes[gi % nl]
                 w = min(wd, B - g0)
+                if stage is not None:
+                    lane.stream.wait_event(staged(g0 + w))
                 with torch.cuda.stream(lane.stream):
                     lane.psi_in[:w].copy_(sdev[g0:g0 + w], non_blocking=True)
                     if w < wd:                             # ragged tail: idle slots redo the last state
@@ -258,6 +283,8 @@ class GraphedPreparer:
                 lane.stream.wait_event(ready)
             for s in range(B):
                 lane = lanes[s % nl]
+                if stage is not None:
+                    lane.stream.wait_event(staged(s + 1))
                 with torch.cuda.stream(lane.stream):
                     lane.psi_in.copy_(sdev[s], non_blocking=True)
                     lane.mismatch.zero_()
