@@ -535,6 +535,16 @@ def measure_batch(args, wl, env, steps, warmup, main_line):
     sync_all()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e = steps * B / (ms_e2e * 1e-3)
+    phases = None
+    if main_line and prep is not None and prep.defer:
+        # one more pass with events between the two phases of the batch path -- on EVERY rank: the pass ends with the
+        # all-gather (a collective entered by rank 0 alone would never complete)
+        prep.time_phases = True
+        qb.prepare_state_batch(sdev, chi, L, S, kernels=K, preparer=prep, return_device=True)
+        torch.cuda.synchronize(dev)
+        prep.time_phases = False
+        phases = prep.phase_ms
+    sync_all()
     if rank != 0:
         return None
     rl = qb.record_len(n, L)
@@ -549,19 +559,16 @@ def measure_batch(args, wl, env, steps, warmup, main_line):
             host.prepare(K, sdev[s], n, chi, L, S)
         eager = roofline_from_profile(K.prof_end(), peak_tf)
         roof = None
-        if prep is not None and prep.defer:
-            # the batch path proper: one more pass with events between its two phases.  Its dominant single kernel is
-            # the whole-shard sweeps launch (k_sweeps_small: every sweep of every state, one CTA per state, vectors in
-            # shared memory); algorithmic bytes = those of the unfused kernels it replaces, 96 B per amplitude and
-            # gate-step (32 forward + 64 backward), so "achieved" is the HBM traffic the launch AVOIDS per second.
-            prep.time_phases = True
-            qb.prepare_state_batch(sdev, chi, L, S, kernels=K, preparer=prep, return_device=True)
-            torch.cuda.synchronize(dev)
-            prep.time_phases = False
-            layers_ms, sweeps_ms = prep.phase_ms
+        if phases is not None:
+            # the batch path proper (pass above).  Its dominant single kernel is the whole-shard sweeps launch
+            # (k_sweeps_small: every sweep of every state of the rank's shard, one CTA per state, vectors in shared
+            # memory); algorithmic bytes = those of the unfused kernels it replaces, 96 B per amplitude and gate-step
+            # (32 forward + 64 backward), so "achieved" is the HBM traffic the launch AVOIDS per second.
+            layers_ms, sweeps_ms = phases
             peaks = load_peaks()
             hbm = peaks.get("hbm_gbs", 6650.0)
-            work = float(sdev.shape[0]) * S * (L * n) * 96.0 * float(2 ** n)
+            shard = (sdev.shape[0] + world - 1) // world               # states of this rank (the launch is per rank)
+            work = float(shard) * S * (L * n) * 96.0 * float(2 ** n)
             ach = work / (sweeps_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",

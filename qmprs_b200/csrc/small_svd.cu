@@ -156,7 +156,9 @@ k_svd_small(int m, int n, const cplx* __restrict__ A_, long long lda, long long 
                     wp[c] = cadd(cscale(x, cc), cmul(o, y));
                     wq[c] = csub(cscale(y, cc), cmul(cconj(o), x));
                 }
-                any = 1;
+                // a sweep whose rotations all had |cos| <= 1e-8 leaves cosines of ~1e-16 n (quadratic convergence of the
+                // cyclic Jacobi iteration): it ends the iteration, no verification sweep (40 % of a sweep's cost)
+                if (mag2 > 1e-16 * a * b) any = 1;
             }
             __syncthreads();
         }

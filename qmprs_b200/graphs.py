@@ -94,7 +94,9 @@ class _BatchLane:
     hardware runs at most 32 lanes side by side (work queues).  Measured on config 5 (profiles/bench_r02_c5_*.json):
     cutting the kernel nodes per state from 1814 to 691 moved the throughput by 10 %, and forking a graph into
     parallel per-state branches by nothing: the bound was the per-lane chain of single-CTA SVDs (23 of the ~28 ms of
-    kernel time of a state).  In lock step the SVD of every split is ONE launch with grid = width."""
+    kernel time of a state).  In lock step EVERY step is one launch for the ``width`` states (the SVD of a split with
+    grid = width, the bookkeeping kernels through their ``*_batch`` entries): 46 graph nodes per state instead of 578,
+    and the layer phase of a 4096-state batch is the SM time of its single-CTA SVDs."""
 
     def __init__(self, device, n, chi, L, threshold, sample_state, width=8):
         self.n, self.L, self.width = n, L, int(width)
