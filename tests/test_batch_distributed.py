@@ -26,6 +26,27 @@ def test_shard_and_record_roundtrip():
     assert np.array_equal(back["gates"], res["gates"])
 
 
+def test_unpack_records_bulk_ragged_layers():
+    """Bulk unpacking of a (B, record_len) block: ragged layer counts, odd record length (views into unaligned
+    rows), same content as the per-record form."""
+    rng = np.random.default_rng(0)
+    n, L = 3, 4
+    recs = []
+    for nl in (4, 1, 3, 2, 4):
+        recs.append({"gates": rng.standard_normal((nl, n, 16)) + 1j * rng.standard_normal((nl, n, 16)),
+                     "kinds": [[2, 2, 1]] * nl, "n_layers": nl, "fidelity": 0.0,
+                     "overlap": (float(rng.standard_normal()), float(rng.standard_normal()))})
+    block = np.stack([batch.pack_record(r, n, L) for r in recs])
+    assert block.shape[1] % 2 == 1                       # odd row length: every second row starts on an 8-byte boundary
+    out = batch.unpack_records(block, n, L)
+    assert len(out) == len(recs)
+    for got, ref in zip(out, recs):
+        assert got["n_layers"] == ref["n_layers"] and got["kinds"] == ref["kinds"] and got["overlap"] == ref["overlap"]
+        assert got["gates"].shape == ref["gates"].shape and np.array_equal(got["gates"], ref["gates"])
+        assert abs(got["fidelity"] - np.hypot(*ref["overlap"])) < 1e-15
+        assert np.array_equal(np.conj(got["gates"]).T @ np.ones(got["gates"].shape[0]), np.conj(ref["gates"]).T @ np.ones(ref["gates"].shape[0]))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
