@@ -1080,54 +1080,83 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 template <bool CG>
 __device__ __forceinline__ cplx ldw_(const cplx* p) { return CG ? __ldcg(p) : *p; }
 
+// One 8 x 8 tile (mt, nt) of W_pair W_pair^H accumulated over the columns [k0, k1) (operands past k1 are zero).
 template <bool CG>
-__device__ __forceinline__ void gram_mma_part(const cplx* W, long long ldw, int bi, int bj, long long c0,
-                                              long long c1, double* __restrict__ Gp, int warp, int lane) {
-    const int g = lane >> 2, t = lane & 3;
-    const int mt = warp >> 1, nt0 = (warp & 1) * 2;
-    auto rowptr = [&](int r) { return W + (long long)(r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ)) * ldw; };
-    const cplx* pa = rowptr(mt * 8 + g);
-    const cplx* pb0 = rowptr(nt0 * 8 + g);
-    const cplx* pb1 = rowptr(nt0 * 8 + 8 + g);
-    double cr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, ci[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+__device__ __forceinline__ void gram_tile_acc(const cplx* pa, const cplx* pb, long long k0, long long k1, int t,
+                                              double (&cr)[2], double (&ci)[2]) {
     // register double-buffering, prefetch distance PF k-steps (operands come from L2)
     constexpr int PF = 4;
-    cplx fa[PF], fb0[PF], fb1[PF];
+    cplx fa[PF], fb[PF];
 #pragma unroll
     for (int s = 0; s < PF; s++) {
-        const long long col = c0 + 4 * s + t;
-        const bool ok = col < c1;
+        const long long col = k0 + 4 * s + t;
+        const bool ok = col < k1;
         fa[s] = ok ? ldw_<CG>(pa + col) : mk(0.0, 0.0);
-        fb0[s] = ok ? ldw_<CG>(pb0 + col) : mk(0.0, 0.0);
-        fb1[s] = ok ? ldw_<CG>(pb1 + col) : mk(0.0, 0.0);
+        fb[s] = ok ? ldw_<CG>(pb + col) : mk(0.0, 0.0);
     }
-    for (long long k0 = c0; k0 < c1; k0 += 4 * PF) {
+    for (long long k = k0; k < k1; k += 4 * PF) {
 #pragma unroll
         for (int s = 0; s < PF; s++) {
-            const cplx wa = fa[s], wb0 = fb0[s], wb1 = fb1[s];
-            const long long col = k0 + 4 * (PF + s) + t;          // same slot, PF steps ahead
-            const bool ok = col < c1;
-            fa[s] = ok ? pa[col] : mk(0.0, 0.0);
-            fb0[s] = ok ? pb0[col] : mk(0.0, 0.0);
-            fb1[s] = ok ? pb1[col] : mk(0.0, 0.0);
-            // W_m conj(W_n): re = ar*br + ai*bi ; im = ai*br - ar*bi   (zero operands past c1 add nothing)
-            // (four independent accumulators back to back, then their second products: same order per accumulator)
-            dmma884(cr[0][0], cr[0][1], wa.x, wb0.x);
-            dmma884(ci[0][0], ci[0][1], wa.y, wb0.x);
-            dmma884(cr[1][0], cr[1][1], wa.x, wb1.x);
-            dmma884(ci[1][0], ci[1][1], wa.y, wb1.x);
-            dmma884(cr[0][0], cr[0][1], wa.y, wb0.y);
-            dmma884(ci[0][0], ci[0][1], -wa.x, wb0.y);
-            dmma884(cr[1][0], cr[1][1], wa.y, wb1.y);
-            dmma884(ci[1][0], ci[1][1], -wa.x, wb1.y);
+            const cplx wa = fa[s], wb = fb[s];
+            const long long col = k + 4 * (PF + s) + t;           // same slot, PF steps ahead
+            const bool ok = col < k1;
+            fa[s] = ok ? ldw_<CG>(pa + col) : mk(0.0, 0.0);
+            fb[s] = ok ? ldw_<CG>(pb + col) : mk(0.0, 0.0);
+            // W_m conj(W_n): re = ar*br + ai*bi ; im = ai*br - ar*bi   (zero operands past k1 add nothing)
+            dmma884(cr[0], cr[1], wa.x, wb.x);
+            dmma884(ci[0], ci[1], wa.y, wb.x);
+            dmma884(cr[0], cr[1], wa.y, wb.y);
+            dmma884(ci[0], ci[1], -wa.x, wb.y);
         }
     }
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const int row = mt * 8 + g, col = (nt0 + j) * 8 + 2 * t;
-        double* dst = Gp + ((long long)row * PMAX + col) * 2;
-        *(double4*)dst = make_double4(cr[j][0], ci[j][0], cr[j][1], ci[j][1]);
+}
+
+// Partial Gram matrix of a pair over the columns [c0, c1) by ONE 8-warp team, Hermitian symmetry used: only the 10
+// upper 8 x 8 tiles are computed (37.5 % fewer DMMAs than the 16 tiles of round 1).  Balance: the 10 tiles x 4 column
+// quarters = 40 units go to the warps five at a time in tile-major order, so a warp accumulates the tail quarters
+// [s, 4) of tile A = 5w/4 and the head quarters [0, s] of tile A + 1 (s = 5w mod 4).  A tile shared by two warps is
+// finished by the warp that holds its tail: the other one deposits its partial sum in shared memory (`dep`, 8 x 64
+// complex per team; fixed order own + deposit).  The finished tile and its conjugate mirror are stored into the slab,
+// so the eigen-solvers read a full 32 x 32 matrix as before.  Contains one __syncthreads(): every thread of the CTA
+// must call it.
+template <bool CG>
+__device__ __forceinline__ void gram_mma_part(const cplx* W, long long ldw, int bi, int bj, long long c0,
+                                              long long c1, double* __restrict__ Gp, int warp, int lane, cplx* dep) {
+    const int g = lane >> 2, t = lane & 3;
+    auto rowptr = [&](int r) { return W + (long long)(r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ)) * ldw; };
+    auto tile_mn = [](int ti, int& m, int& n) {           // upper tiles, row-major: (0,0) (0,1) (0,2) (0,3) (1,1) ...
+        m = ti < 4 ? 0 : (ti < 7 ? 1 : (ti < 9 ? 2 : 3));
+        n = ti < 4 ? ti : (ti < 7 ? ti - 3 : (ti < 9 ? ti - 5 : 3));
+    };
+    long long qlen = ((c1 - c0 + 3) / 4 + 3) / 4 * 4;      // quarter length, a multiple of the k-step
+    if (qlen < 4) qlen = 4;
+    auto qcol = [&](int qd) { const long long c = c0 + qd * qlen; return c < c1 ? c : c1; };
+    const int sq = (5 * warp) & 3, ta = (5 * warp) >> 2, tb = ta + 1;
+    int ma, na, mb, nb;
+    tile_mn(ta, ma, na);
+    tile_mn(tb < 10 ? tb : 9, mb, nb);
+    double ar[2] = {0.0, 0.0}, ai[2] = {0.0, 0.0}, br[2] = {0.0, 0.0}, bim[2] = {0.0, 0.0};
+    gram_tile_acc<CG>(rowptr(ma * 8 + g), rowptr(na * 8 + g), qcol(sq), qcol(4), t, ar, ai);
+    gram_tile_acc<CG>(rowptr(mb * 8 + g), rowptr(nb * 8 + g), qcol(0), qcol(sq + 1), t, br, bim);
+    auto store_tile = [&](int m, int n, const double* xr, const double* xi) {
+        const int row = m * 8 + g, col = n * 8 + 2 * t;
+        *(double4*)(Gp + ((long long)row * PMAX + col) * 2) = make_double4(xr[0], xi[0], xr[1], xi[1]);
+        if (m != n) {                                      // mirror: G[col][row] = conj(G[row][col])
+            *(double2*)(Gp + ((long long)col * PMAX + row) * 2) = make_double2(xr[0], -xi[0]);
+            *(double2*)(Gp + ((long long)(col + 1) * PMAX + row) * 2) = make_double2(xr[1], -xi[1]);
+        }
+    };
+    if (sq == 3) store_tile(mb, nb, br, bim);              // the head quarters were all four: tile B is complete
+    else {
+        dep[warp * 64 + 2 * lane] = mk(br[0], bim[0]);
+        dep[warp * 64 + 2 * lane + 1] = mk(br[1], bim[1]);
     }
+    __syncthreads();
+    if (sq != 0) {                                         // tile A's head quarters came from the previous warp
+        const cplx d0 = dep[(warp - 1) * 64 + 2 * lane], d1 = dep[(warp - 1) * 64 + 2 * lane + 1];
+        ar[0] += d0.x; ai[0] += d0.y; ar[1] += d1.x; ai[1] += d1.y;
+    }
+    store_tile(ma, na, ar, ai);
 }
 
 // G = W_pair W_pair^H over a column chunk.  Each of the 8 warps owns two of the sixteen 8x8 output
@@ -1145,8 +1174,9 @@ k_gram_mma(const cplx* __restrict__ W, long long ldw, int len, int chunk, PairSp
     get_pair(ps, blockIdx.y, bi, bj);
     const long long c0 = (long long)blockIdx.x * chunk;
     const long long c1 = (c0 + chunk < len) ? c0 + chunk : len;
+    __shared__ cplx dep[8 * 64];
     gram_mma_part<false>(W, ldw, bi, bj, c0, c1, G + ((long long)pair * gridDim.x + blockIdx.x) * PMAX * PMAX * 2,
-                         tid >> 5, tid & 31);
+                         tid >> 5, tid & 31, dep);
 }
 
 // One 8-warp team: rows <- Q rows over columns [c0, c1): each warp owns 8-column strips (stride 64), loads the 32x8
@@ -1265,6 +1295,7 @@ struct RoundSmem {
         Eig3Smem e;
         Eig4Smem e4;
         struct { double qr[PMAX * QS], qi[PMAX * QS]; } a;
+        cplx dep[2 * 8 * 64];                                 // Gram phase: tile partials passed between warps
     };
     int s_last;
 };
@@ -1334,7 +1365,8 @@ k_round(cplx* W, long long ldw, int len, long long lenx, int chunk, int nbp, int
         {
             const long long c0 = cc0 < len ? cc0 : len;
             const long long c1 = cc1 < len ? cc1 : len;
-            gram_mma_part<true>(W, ldw, bi, bj, c0, c1 > c0 ? c1 : c0, Gp + (long long)sub * PMAX * PMAX * 2, w8, lane);
+            gram_mma_part<true>(W, ldw, bi, bj, c0, c1 > c0 ? c1 : c0, Gp + (long long)sub * PMAX * PMAX * 2, w8, lane,
+                                sm.dep + team * 8 * 64);
         }
         __syncthreads();
         if (DBG && tid == 0) tt[1] = gtimer();
