@@ -1975,7 +1975,9 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
                         sizeof(RoundSmem), st));
                 }
             }
-            qm_prof_work(QM_CLS_SVD_ROUND, 8.0 * g.nrows * g.nrows * ((double)g.len + (double)lenx) * g.npairs * g.rounds);
+            // algorithmic flops: Hermitian Gram = the 10 upper tiles of 16 (a ZHERK), full 32 x 32 update
+            qm_prof_work(QM_CLS_SVD_ROUND,
+                         8.0 * g.nrows * g.nrows * (0.625 * (double)g.len + (double)lenx) * g.npairs * g.rounds);
         } else if (grouped) {
             for (int ph = 0; ph < nphases; ph++) {
                 const Phase& P = phases[ph];
@@ -2035,7 +2037,7 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
         }
         // complex MAC = 8 flops: Gram nrows^2 x len, update nrows^2 x lenx, per pair and round
         if (!fused) {
-            qm_prof_work(QM_CLS_SVD_GRAM, 8.0 * g.nrows * g.nrows * (double)g.len * g.npairs * g.rounds);
+            qm_prof_work(QM_CLS_SVD_GRAM, 0.625 * 8.0 * g.nrows * g.nrows * (double)g.len * g.npairs * g.rounds);
             qm_prof_work(QM_CLS_SVD_APPLY, 8.0 * g.nrows * g.nrows * (double)lenx * g.npairs * g.rounds);
         }
         QM_CHECK_LAUNCH();
