@@ -483,7 +483,7 @@ def sweep(target, layers, n_sites, gauge="verbatim"):
 # top level                           (base.py:96-104, sequential.py:330-398, 509-600)
 # --------------------------------------------------------------------------------------
 def prepare(psi, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 - 1e-6,
-            gauge="canonical", record=None):
+            gauge="canonical", record=None, schedule="DallOall"):
     """Restatement of ``Sequential.prepare_state``.  Returns a dict with
 
     ``layers``      list (application order) of [(start, end, [G...])],
@@ -505,14 +505,27 @@ def prepare(psi, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 - 1e-6,
     rec.setdefault("chi2", [])
 
     A = compress_right(from_dense(psi, N, rec["tt_svd"]), max_bond=chi, spectra=rec["truncate"])
-    return prepare_mps(A, num_layers, num_sweeps, threshold, gauge, rec)
+    return prepare_mps(A, num_layers, num_sweeps, threshold, gauge, rec, schedule)
 
 
-def prepare_mps(A, num_layers=1, num_sweeps=0, threshold=1 - 1e-6, gauge="canonical", record=None):
+SCHEDULES = ("DallOall", "IterDiOall", "IterDiOi")
+
+
+def prepare_mps(A, num_layers=1, num_sweeps=0, threshold=1 - 1e-6, gauge="canonical", record=None,
+                schedule="DallOall"):
     """Restatement of ``Sequential.prepare_mps`` (sequential.py:588-600 -> :543-586) for an MPS given as
-    site tensors (l, 2, r) in ANY gauge; same result dict as :func:`prepare`."""
+    site tensors (l, 2, r) in ANY gauge; same result dict as :func:`prepare`.
+
+    ``schedule``: "DallOall" is what the reference runs (all layers by disentangling, then ``num_sweeps`` sweeps
+    over all of them).  "IterDiOall" / "IterDiOi" are the two schedules the reference only names as future work
+    (notebook cell at :459, docstring sequential.py:410, 428-432; Rudolph et al. 2022, the reference's [2]) --
+    see :func:`prepare_mps_iterative`."""
     if not isinstance(num_layers, int) or num_layers < 1:
         raise ValueError("The number of layers must be a positive integer.")
+    if schedule not in SCHEDULES:
+        raise ValueError("`schedule` must be one of %s." % (SCHEDULES,))
+    if schedule != "DallOall":
+        return prepare_mps_iterative(A, num_layers, num_sweeps, threshold, gauge, record, schedule)
     rec = record if record is not None else {}
     rec.setdefault("gate_split", [])
     rec.setdefault("chi2", [])
@@ -550,6 +563,68 @@ def prepare_mps(A, num_layers=1, num_sweeps=0, threshold=1 - 1e-6, gauge="canoni
         sweep(target, layers, N, gauge)
 
     return {"layers": layers, "n_layers": n_used, "mps": A, "target": target,
+            "overlaps": overlaps, "n_sites": N}
+
+
+def prepare_mps_iterative(A, num_layers, num_sweeps, threshold, gauge, record, schedule):
+    """The two iterative schedules of Rudolph et al. 2022 that the reference lists as future work (notebook :459:
+    "Iter DiOi, where we perform optimization on each layer as we generate them, or Iter DiOall, where we generate
+    a layer and optimize that and its predecessors").  There is no reference code to follow; the building blocks
+    are the reference's own (chi=2 truncation mps.py:849-891, inverse application :933-971, sweep
+    sequential.py:400-507) composed as the paper describes:
+
+    IterDiOi    layer k is generated from the residual |psi_k> (chi=2 truncation), then optimised ALONE for
+                ``num_sweeps`` sweeps -- the rest of the circuit is fixed, so its environment is the one-layer
+                circuit against |psi_k> -- and the optimised layer is taken out: |psi_{k+1}> = V_k^H |psi_k>.
+    IterDiOall  layer k is generated from the residual, ALL layers generated so far are optimised for
+                ``num_sweeps`` sweeps against the target, and the residual is rebuilt from the target with the
+                optimised circuit: |psi_{k+1}> = V_k^H ... V_1^H |psi>.
+
+    Same pre-conditioning, early break and result record as the default schedule; with ``num_sweeps = 0`` both
+    reduce to it exactly."""
+    rec = record if record is not None else {}
+    rec.setdefault("gate_split", [])
+    rec.setdefault("chi2", [])
+    A = [np.asarray(a, dtype=np.complex128) for a in A]
+    N = len(A)
+    target = to_dense(A)
+    B0 = [a.copy() for a in A]
+    nrm = mps_norm(B0)
+    if not np.isclose(nrm, 1.0):
+        B0[-1] = B0[-1] / nrm
+    B0 = right_canon(compress_right(B0), normalize=True)
+
+    B = [a.copy() for a in B0]
+    layers = []                                                        # application order: newest layer first
+    overlaps = []
+    for _ in range(num_layers):
+        sp4, sp6 = [], []
+        layer = generate_unitary_layer(chi2_truncate(B, gauge, sp4), gauge)
+        rec["chi2"].append(sp4)
+        if schedule == "IterDiOi":
+            residual = to_dense(B)
+            single = [layer]
+            for _ in range(num_sweeps):
+                sweep(residual, single, N, gauge)
+            layers.insert(0, layer)
+            apply_inverse_layer(B, layer, sp6)
+        else:
+            layers.insert(0, layer)
+            for _ in range(num_sweeps):
+                sweep(target, layers, N, gauge)
+            if num_sweeps > 0:
+                B = [a.copy() for a in B0]
+                for lay in reversed(layers):                           # the layer applied last comes off first
+                    sp6 = []
+                    apply_inverse_layer(B, lay, sp6)
+            else:
+                apply_inverse_layer(B, layer, sp6)
+        rec["gate_split"].append(sp6)
+        f = zero_overlap(B)
+        overlaps.append(f)
+        if np.isclose(f, 1 + 0j, atol=1 - threshold):
+            break
+    return {"layers": layers, "n_layers": len(layers), "mps": A, "target": target,
             "overlaps": overlaps, "n_sites": N}
 
 

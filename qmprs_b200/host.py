@@ -421,6 +421,65 @@ def disentangle(K, A, num_layers, threshold, record=None, split="svd", precondit
     return gates_all, layer_kinds, overlaps
 
 
+SCHEDULES = ("DallOall", "IterDiOall", "IterDiOi")
+
+
+def disentangle_iterative(K, A, num_layers, num_sweeps, threshold, schedule, record=None, split="svd",
+                          preconditioned=True):
+    """The two schedules the reference names as future work (notebook :459; docstring sequential.py:410,
+    428-432; Rudolph et al. 2022), composed from the same stages as the default one:
+
+    ``IterDiOi``    generate layer k from the residual MPS (A4/A5), optimise it ALONE for ``num_sweeps`` sweeps --
+                    the rest of the circuit is fixed, so its environments are those of the one-layer circuit
+                    against the dense residual -- then take the optimised layer out of the residual (A6).
+    ``IterDiOall``  generate layer k from the residual, optimise ALL layers so far against the target (A8/A9),
+                    rebuild the residual from the pre-conditioned MPS with the optimised circuit (k x A6).
+
+    Returns what :func:`disentangle` returns, sweeps already done.  With ``num_sweeps = 0`` both are the default
+    schedule, launch for launch."""
+    import torch
+    if schedule not in SCHEDULES[1:]:
+        raise ValueError("`schedule` must be one of %s." % (SCHEDULES,))
+    rec = record if record is not None else {}
+    N = len(A)
+    B0 = copy_mps(K, A) if preconditioned else canonicalize_truncate(K, A)
+    normalize_site0(K, B0)
+    rebuild = schedule == "IterDiOall" and num_sweeps > 0
+    B = copy_mps(K, B0) if rebuild else B0
+    target = to_dense(K, A) if rebuild else None                     # sequential.py:440 (mps.mps, not normalised)
+    layer_gates, layer_kinds, overlaps = [], [], []                   # application order: newest layer first
+    for _ in range(num_layers):
+        gates, kinds = chi2_layer(K, B)
+        sp = []
+        if schedule == "IterDiOi":
+            if num_sweeps > 0:
+                gates = gates.contiguous()
+                optimize_layers(K, to_dense(K, B), gates, [kinds], N, num_sweeps)
+            layer_gates.insert(0, gates)
+            layer_kinds.insert(0, kinds)
+            apply_inverse_layer(K, B, gates, kinds, sp, split=split)
+        else:
+            layer_gates.insert(0, gates)
+            layer_kinds.insert(0, kinds)
+            if rebuild:
+                gates_all = torch.cat(layer_gates, dim=0).contiguous()
+                optimize_layers(K, target, gates_all, layer_kinds, N, num_sweeps)
+                layer_gates = [gates_all[j * N:(j + 1) * N] for j in range(len(layer_kinds))]
+                B = copy_mps(K, B0)
+                for g, kd in zip(reversed(layer_gates), reversed(layer_kinds)):   # the layer applied last comes off first
+                    sp = []
+                    apply_inverse_layer(K, B, g, kd, sp, split=split)
+            else:
+                apply_inverse_layer(K, B, gates, kinds, sp, split=split)
+        rec.setdefault("gate_split", []).append(sp)
+        f = zero_overlap(K, B, break_tol=(1 - threshold) + 1e-5)
+        overlaps.append(f)
+        if f is not None and np.isclose(f, 1 + 0j, atol=1 - threshold):
+            break
+    gates_all = torch.cat(layer_gates, dim=0).contiguous()
+    return gates_all, layer_kinds, overlaps
+
+
 def prepare_layers_device(K, psi, n_sites, chi, num_layers, threshold=1 - 1e-6, record=None, fused=True, split="svd"):
     """First half of :func:`prepare_device`: normalise ``psi`` in place, build the MPS and extract the layers.
     Returns (gates_all, kinds per layer, overlaps, MPS).  graphs.py captures this much per state and leaves the
@@ -549,7 +608,7 @@ def prepare_device(K, psi, n_sites, chi, num_layers, num_sweeps, threshold=1 - 1
 
 
 def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 - 1e-6, record=None,
-            mps=None, fused=True, split="svd", mps_preconditioned=False):
+            mps=None, fused=True, split="svd", mps_preconditioned=False, schedule="DallOall"):
     """Whole path on the device.  ``psi_host``: complex128 numpy vector or device tensor.
     Returns dict(gates [L,N,16] numpy, kinds [L][N], n_layers, overlaps, fidelity).
     ``mps``: start from these site tensors instead of building them (``prepare_mps``); any gauge unless
@@ -559,15 +618,26 @@ def prepare(K, psi_host, n_sites, chi, num_layers=1, num_sweeps=0, threshold=1 -
         psi = K.scale_copy(psi_host.reshape(-1, 1)).reshape(-1)
     else:
         psi = K.from_host(np.asarray(psi_host, dtype=np.complex128).reshape(-1))
-    if mps is None:
+    if schedule not in SCHEDULES:
+        raise ValueError("`schedule` must be one of %s." % (SCHEDULES,))
+    if mps is None and schedule == "DallOall":
         gates_all, layer_kinds, ovt, overlaps, A = prepare_device(K, psi, N, chi, num_layers, num_sweeps,
                                                                   threshold, record, fused, split)
     else:
-        A = mps
-        gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record, split,
-                                                       preconditioned=mps_preconditioned)
-        if num_sweeps > 0:
-            optimize_layers(K, to_dense(K, A), gates_all, layer_kinds, N, num_sweeps)
+        if mps is None:
+            K.div_sqrt(psi, K.vdot(psi, psi))                         # quick Ket normalisation
+            A = build_mps(K, psi, N, chi, record, fused)
+            mps_preconditioned = True
+        else:
+            A = mps
+        if schedule == "DallOall":
+            gates_all, layer_kinds, overlaps = disentangle(K, A, num_layers, threshold, record, split,
+                                                           preconditioned=mps_preconditioned)
+            if num_sweeps > 0:
+                optimize_layers(K, to_dense(K, A), gates_all, layer_kinds, N, num_sweeps)
+        else:
+            gates_all, layer_kinds, overlaps = disentangle_iterative(K, A, num_layers, num_sweeps, threshold,
+                                                                     schedule, record, split, mps_preconditioned)
         sites, kinds = flat_schedule(layer_kinds, N)
         ovt = K.vdot(psi, K.circuit_state(N, gates_all, sites, kinds))
     ov = K.to_host(ovt)

@@ -25,6 +25,10 @@ class Sequential(MPSEncoder):
         # (mps.py:968-971).  "exact": gauge-free trivial re-split, identical circuit, no SVD
         # (qmprs_b200.host.apply_inverse_layer); opt-in.
         self.gate_split = "svd"
+        # "DallOall": what the reference runs (sequential.py:543-586).  "IterDiOall" / "IterDiOi": the two schedules
+        # it names as future work (notebook :459, docstring :410, 428-432) -- qmprs_b200.host.disentangle_iterative.
+        # Also accepted per call as the keyword ``schedule=`` of prepare_state / prepare_mps.
+        self.schedule = "DallOall"
         # CUDA-graph replay for small registers (qmprs_b200.graphs), OPT-IN: False (default) always runs the
         # eager path; "auto" captures the pipeline the second time the same (n, chi, layers, sweeps) is
         # requested with n <= 16; True forces it.  The replayed pipeline uses fixed Jacobi sweep budgets and
@@ -62,8 +66,11 @@ class Sequential(MPSEncoder):
             Sequential._apply_unitary_layer_to_circuit(circuit, layer_gates, kinds)
         return circuit
 
-    def _sequential_unitary_circuit(self, mps: MPS, num_layers: int, num_sweeps: int = 0):
+    def _sequential_unitary_circuit(self, mps: MPS, num_layers: int, num_sweeps: int = 0, schedule=None):
         """sequential.py:543-586."""
+        schedule = self.schedule if schedule is None else schedule
+        if schedule not in host.SCHEDULES:
+            raise ValueError("`schedule` must be one of %s." % (host.SCHEDULES,))
         K = mps.mps.K
         A = mps.mps.tensors
         N = mps.num_sites
@@ -74,8 +81,14 @@ class Sequential(MPSEncoder):
         # the reference's cutoff (what MPS.from_statevector / MPS.compress return); any other gauge
         # (left-canonical, after apply_unitary_layer, built from raw arrays) is pre-conditioned in full
         pre = mps.mps.form == "right" and getattr(mps.mps, "trimmed", False)
-        gates_all, layer_kinds, overlaps = host.disentangle(K, A, num_layers, self._fidelity_threshold, record,
-                                                            split=self.gate_split, preconditioned=pre)
+        if schedule != "DallOall":
+            gates_all, layer_kinds, overlaps = host.disentangle_iterative(
+                K, A, num_layers, num_sweeps, self._fidelity_threshold, schedule, record, split=self.gate_split,
+                preconditioned=pre)
+            num_sweeps = 0                                 # done inside, per layer
+        else:
+            gates_all, layer_kinds, overlaps = host.disentangle(K, A, num_layers, self._fidelity_threshold, record,
+                                                                split=self.gate_split, preconditioned=pre)
         if num_sweeps > 0:
             target = host.to_dense(K, A)
             host.optimize_layers(K, target, gates_all, layer_kinds, N, num_sweeps)
@@ -98,7 +111,8 @@ class Sequential(MPSEncoder):
         n = statevector.num_qubits
         key = (n, int(bond_dimension), num_layers, int(num_sweeps), float(self._fidelity_threshold), self.gate_split)
         want = self.use_cuda_graphs
-        plain = compression_percentage == 0.0 and index_type == "row" and n >= 2
+        plain = (compression_percentage == 0.0 and index_type == "row" and n >= 2
+                 and kwargs.get("schedule", self.schedule) == "DallOall")
         if want and plain and (want is True or (n <= 16 and self._graph_seen.get(key, 0) >= 1)):
             prep = self._graph_cache.get(key)
             if prep is None:
@@ -124,4 +138,4 @@ class Sequential(MPSEncoder):
         num_sweeps = kwargs.get("num_sweeps", 0)
         if not isinstance(num_layers, int) or num_layers < 1:
             raise ValueError("The number of layers must be a positive integer.")
-        return self._sequential_unitary_circuit(mps, num_layers, num_sweeps)
+        return self._sequential_unitary_circuit(mps, num_layers, num_sweeps, kwargs.get("schedule"))

@@ -169,3 +169,35 @@ def test_reference_inequalities_through_public_api(K):
         f = abs(np.vdot(psi, enc.prepare_state(psi, 64, num_layers=6, num_sweeps=S).get_statevector()))
         assert f >= prev - 1e-9
         prev = f
+
+
+@pytest.mark.parametrize("schedule", ["IterDiOall", "IterDiOi"])
+@pytest.mark.parametrize("n,chi,L,S,seed", [(8, 32, 4, 3, 2), (10, 32, 3, 2, 5), (13, 64, 3, 2, 1)])
+def test_iterative_schedules_vs_oracle(K, schedule, n, chi, L, S, seed):
+    """SURVEY 8(f) rank 4 (reference: notebook :459, sequential.py:410, 428-432 -- named, not implemented): the
+    CUDA stages composed as Iter DiOall / Iter DiOi against the oracle's composition.  8-10 qubits run the
+    one-CTA sweeps kernel, 13 qubits the persistent multi-CTA one (one-layer circuits included)."""
+    from qmprs.synthesis.mps_encoding import Sequential
+    from qmprs_b200 import GateListCircuit
+    psi = O.random_state(n, seed)
+    ref = O.prepare(psi, n, chi, L, S, gauge="canonical", schedule=schedule)
+    enc = Sequential(GateListCircuit)
+    circ = enc.prepare_state(psi, chi, num_layers=L, num_sweeps=S, schedule=schedule)
+    res = enc.last_result
+    assert res["n_layers"] == ref["n_layers"]
+    g = res["gates"].reshape(-1, 16)
+    for idx, (_, _, _, site, G) in enumerate(O.flatten_layers(ref["layers"])):
+        assert np.abs(g[idx][: G.size] - G.reshape(-1)).max() < 1e-5
+    f_ref = O.circuit_fidelity(psi, ref["layers"], n)
+    sv = circ.get_statevector()
+    assert abs(abs(np.vdot(psi, sv)) - f_ref) <= 1e-6                              # north_star fidelity bar
+    assert np.abs(sv - O.circuit_state(ref["layers"], n)).max() <= 1e-6
+    for a, b in zip(res["overlaps"], ref["overlaps"]):
+        assert abs(a - b) < 1e-6
+    # attribute form, and the default schedule is untouched by it
+    enc2 = Sequential(GateListCircuit)
+    enc2.schedule = schedule
+    enc2.prepare_state(psi, chi, num_layers=L, num_sweeps=S)
+    assert np.array_equal(enc2.last_result["gates"], res["gates"])
+    with pytest.raises(ValueError):
+        enc.prepare_state(psi, chi, num_layers=L, schedule="nope")

@@ -131,3 +131,42 @@ def test_prepare_mps_any_gauge_matches_reference_preconditioning(kind):
     g = out["gates"].reshape(-1, 16)
     for idx, (_, _, _, site, G) in enumerate(gate_table(ref)):
         assert np.abs(g[idx][: G.size] - G.reshape(-1)).max() < 1e-7
+
+
+@pytest.mark.parametrize("schedule", ["IterDiOall", "IterDiOi"])
+@pytest.mark.parametrize("n,chi,L,S,seed", [(6, 64, 3, 2, 1), (8, 32, 4, 3, 2), (8, 4, 4, 2, 3)])
+def test_iterative_schedules_match_oracle(schedule, n, chi, L, S, seed):
+    """the schedules the reference names as future work (notebook :459, sequential.py:410,
+    428-432), composed on the host from the same stages; checked against the oracle's composition of its own."""
+    psi = O.random_state(n, seed)
+    ref = O.prepare(psi, n, chi, L, S, gauge="canonical", schedule=schedule)
+    out = host.prepare(FakeKernels(svd_phase_seed=seed + 10), psi, n, chi, L, S, schedule=schedule)
+    assert out["n_layers"] == ref["n_layers"]
+    g = out["gates"].reshape(-1, 16)
+    for idx, (_, _, _, site, G) in enumerate(gate_table(ref)):
+        assert np.abs(g[idx][: G.size] - G.reshape(-1)).max() < 1e-7
+    assert abs(out["fidelity"] - O.circuit_fidelity(psi, ref["layers"], n)) < 1e-9
+    for a, b in zip(out["overlaps"], ref["overlaps"]):
+        assert abs(a - b) < 1e-8
+
+
+def test_iterative_schedules_without_sweeps_are_the_default_schedule():
+    psi = O.random_state(7, 6)
+    base = host.prepare(FakeKernels(), psi, 7, 16, 4, 0)
+    for schedule in ("IterDiOall", "IterDiOi"):
+        out = host.prepare(FakeKernels(), psi, 7, 16, 4, 0, schedule=schedule)
+        assert out["kinds"] == base["kinds"]
+        assert np.array_equal(out["gates"], base["gates"])
+    with pytest.raises(ValueError):
+        host.prepare(FakeKernels(), psi, 7, 16, 4, 0, schedule="IterDallOi")
+
+
+def test_iterative_schedule_early_break_and_blocks():
+    """A product of two-qubit blocks is disentangled by the first layer whatever the schedule."""
+    bell = np.zeros(4, dtype=complex); bell[0] = bell[3] = 1 / np.sqrt(2)
+    psi = np.array([1.0 + 0j])
+    for v in (bell, bell, bell):
+        psi = np.kron(psi, v)
+    for schedule in ("IterDiOall", "IterDiOi"):
+        out = host.prepare(FakeKernels(), psi, 6, 8, 4, 2, schedule=schedule)
+        assert out["n_layers"] == 1 and out["fidelity"] > 1 - 1e-12

@@ -174,3 +174,29 @@ def test_golden_fixture():
         assert res["n_layers"] == L
         assert abs(fid(psi, res, n) - float(z[key + "_fidelity"])) < 1e-9
         assert np.abs(O.circuit_state(res["layers"], n) - z[key + "_state"]).max() < 1e-6
+
+
+def test_iterative_schedules_properties():
+    """Iter DiOall / Iter DiOi (reference: named only, notebook :459).  No sweeps: the default schedule exactly;
+    with sweeps: the residual's |0..0> overlap IS the circuit fidelity (the residual is rebuilt from / updated with
+    the optimised gates), every schedule at least as good as plain disentangling, and DiOall -- every gate
+    re-optimised after every new layer -- not worse than the one-shot DallOall with the same sweeps per stage."""
+    n, chi, L, S = 8, 32, 4, 3
+    psi = O.random_state(n, 0)
+    plain = O.prepare(psi, n, chi, L, 0)
+    f_plain = fid(psi, plain, n)
+    for schedule in ("IterDiOall", "IterDiOi"):
+        same = O.prepare(psi, n, chi, L, 0, schedule=schedule)
+        for (_, _, _, _, g0), (_, _, _, _, g1) in zip(O.flatten_layers(plain["layers"]), O.flatten_layers(same["layers"])):
+            assert np.array_equal(g0, g1)
+        res = O.prepare(psi, n, chi, L, S, schedule=schedule)
+        f = fid(psi, res, n)
+        assert abs(abs(res["overlaps"][-1]) - f) < 1e-9
+        assert f > f_plain
+        for lay in res["layers"]:
+            for _, _, gates in lay:
+                assert all(O.is_unitary(g) for g in gates)
+    f_all = fid(psi, O.prepare(psi, n, chi, L, S), n)
+    assert fid(psi, O.prepare(psi, n, chi, L, S, schedule="IterDiOall"), n) >= f_all - 1e-9
+    with pytest.raises(ValueError):
+        O.prepare(psi, n, chi, L, S, schedule="other")
