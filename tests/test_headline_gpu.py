@@ -70,6 +70,33 @@ def test_headline_20q_chi512_two_layers_one_sweep(K):
     assert abs(rf["fidelity"] - fo) <= 1e-6
 
 
+def test_config2_16q_chi256_15_layers(K):
+    """BASELINE config 2 at its own size (16 qubits, chi=256, 15 layers) against the canonical oracle: layer count,
+    gate structure, overlaps after every layer, the first four extracted layers at the 1e-8 bar, and -- continuing
+    both sides with 5 optimisation sweeps (the persistent multi-CTA sweep kernel; 50 sweeps would be ~70 s of oracle
+    time) -- the fidelity at the 1e-6 bar."""
+    n, chi, L, S = 16, 256, 15, 5
+    psi = O.random_state(n, 0)
+    ro = O.prepare(psi, n, chi, L, 0, gauge="canonical")
+    rd = host.prepare(K, psi, n, chi, L, 0, fused=False)
+    assert rd["n_layers"] == ro["n_layers"] == L
+    assert host.bond_dims(rd["mps"]) == O.bond_dims(ro["mps"])
+    assert np.abs(np.array(rd["overlaps"]) - np.array(ro["overlaps"])).max() <= 1e-9
+    flat = O.flatten_layers(ro["layers"])
+    g = rd["gates"].reshape(-1, 16)
+    kinds = [k for kl in rd["kinds"] for k in kl]
+    assert len(flat) == g.shape[0] == L * n
+    for idx, (li, _, _, _, G) in enumerate(flat):
+        assert kinds[idx] == (2 if G.shape[0] == 4 else 1)
+        if L - 1 - li < 4:                                   # application order is the reverse of extraction order
+            assert np.abs(g[idx][: G.size] - G.reshape(-1)).max() <= 1e-8
+    assert abs(rd["fidelity"] - O.circuit_fidelity(psi, ro["layers"], n)) <= 1e-6
+    for _ in range(S):
+        O.sweep(ro["target"], ro["layers"], n, "canonical")
+    rs = host.prepare(K, psi, n, chi, L, S)                  # default (fused) build + sweeps
+    assert abs(rs["fidelity"] - O.circuit_fidelity(psi, ro["layers"], n)) <= 1e-6
+
+
 def test_config4_tt_svd_spectra_21q(K):
     """BASELINE config 4 (24-qubit TT-SVD) one size down, spectra of EVERY split against numpy's LAPACK SVD
     (the 24-qubit case itself is covered through properties in test_pipeline_gpu and scripts/tt_svd_c4.py)."""
