@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqmprs_b200.so")
+# QM_B200_LIB: another build of the same library (A/B runs of kernel variants on one box); the default is the in-tree one
+LIB_PATH = os.environ.get("QM_B200_LIB") or os.path.join(_HERE, "libqmprs_b200.so")
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

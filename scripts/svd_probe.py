@@ -19,4 +19,9 @@ for m, n in zip(args[0::2], args[1::2]):
         torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
     s = K.to_host(S)
     sref = np.linalg.svd(a, compute_uv=False)
-    print(f"svd {m}x{n}: {1e3*best:.2f} ms, sweeps {K.svd_sweeps}, max|s-sref|/s0 {np.abs(s-sref).max()/sref[0]:.2e}", flush=True)
+    u, vh = K.to_host(U), K.to_host(Vh)
+    k = s.shape[0]
+    rec = np.abs((u[:, :k] * s[None, :]) @ vh[:k] - a).max() / sref[0]
+    orth = max(np.abs(u[:, :k].conj().T @ u[:, :k] - np.eye(k)).max(), np.abs(vh[:k] @ vh[:k].conj().T - np.eye(k)).max())
+    print(f"svd {m}x{n}: {1e3*best:.2f} ms, sweeps {K.svd_sweeps}, max|s-sref|/s0 {np.abs(s-sref).max()/sref[0]:.2e}, "
+          f"|USV-A|/s0 {rec:.1e}, orth {orth:.1e}", flush=True)
