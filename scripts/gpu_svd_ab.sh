@@ -1,6 +1,11 @@
 #!/bin/bash
 # A/B of k_round Gram-phase variants on ONE box, SM clocks sampled during each run.
 # ctl = library built from the previous commit's svd.cu (qmprs_b200/libqmprs_b200_ctl.so), new = in-tree library.
+# Control build (here, before the gpurun call):
+#   git show HEAD:qmprs_b200/csrc/svd.cu > /tmp/ctl/svd.cu
+#   nvcc <FLAGS of qmprs_b200/build.py> <the other csrc/*.cu> /tmp/ctl/svd.cu -o qmprs_b200/libqmprs_b200_ctl.so
+# The default probe accumulates V in the identity extension (update over 2 x len columns); QM_PROBE_BACKMULT=1 is the
+# mode the pipeline uses (V by back-multiplication): 1024 x 1024 takes 56 ms in the former, 44-46 ms in the latter.
 mkdir -p gpurun_out
 run() {  # name lib gram2 [extra env]
   nvidia-smi --query-gpu=clocks.sm,power.draw,clocks_throttle_reasons.active --format=csv,noheader,nounits -lms 100 > /tmp/smi_$1.txt &
