@@ -201,3 +201,24 @@ def test_iterative_schedules_vs_oracle(K, schedule, n, chi, L, S, seed):
     assert np.array_equal(enc2.last_result["gates"], res["gates"])
     with pytest.raises(ValueError):
         enc.prepare_state(psi, chi, num_layers=L, schedule="nope")
+
+
+def test_two_pass_build_switch(K):
+    """MPS.two_pass_build = True: the reference's literal from_dense + compress (mps.py:242-247) instead of the
+    one-pass Schmidt-form build; same bonds, same state up to the 1e-10 cut, same circuit here (12 qubits)."""
+    from qmprs.primitives import MPS
+    from qmprs.synthesis.mps_encoding import Sequential
+    from qmprs_b200 import GateListCircuit
+    psi = O.random_state(12, 3)
+    enc = Sequential(GateListCircuit)
+    a = enc.prepare_state(psi, 16, num_layers=3, num_sweeps=2).get_statevector()
+    try:
+        MPS.two_pass_build = True
+        m = MPS(statevector=psi, bond_dimension=16)
+        b = enc.prepare_state(psi, 16, num_layers=3, num_sweeps=2).get_statevector()
+    finally:
+        MPS.two_pass_build = False
+    ref = O.prepare(psi, 12, 16, 3, 2, gauge="canonical")
+    assert [int(t.shape[2]) for t in m.mps.tensors[:-1]] == O.bond_dims(ref["mps"])
+    assert np.abs(b - O.circuit_state(ref["layers"], 12)).max() <= 1e-6
+    assert np.abs(a - b).max() <= 1e-6
