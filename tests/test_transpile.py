@@ -72,20 +72,32 @@ def test_two_qubit_lowering_matches_dense_and_uses_fewest_cx():
         assert len(two_qubit_ops(u)[0]) == 3 * ncx + 2
 
 
-@pytest.mark.parametrize("n,layers,depth", [(5, 5, 73), (6, 8, 115), (9, 8, 133), (10, 15, 223)])
-def test_published_depths_and_op_counts(n, layers, depth):
-    # notebook cell 28: depths [.., 73, 115, 121, 127, 133, 223, ..] for 5..10 qubits = 6N + 12L - 17;
-    # README.md:70 depth 223; notebook cell 27 op counts at 10 qubits: 405 CX, 1095 U3
+# notebook cell 27 (config: 5 layers below 6 qubits, 8 below 10, 15 below 14; bond dimension 2^n) prints count_ops()
+# per register size and cell 28 the depths [7, 13, 65, 73, 115, 121, 127, 133, 223, 229, 235] for 2..12 qubits: outputs
+# of the REAL reference (quimb + quick) on unseeded random states.  For generic states they depend on the structure
+# only (layers used, blocks, CX per Weyl class), so every row can be reproduced exactly -- except 4 qubits, where the
+# early break and the CX count of the last gates depend on the state (the notebook's own second run, cell 29, has
+# depth 53 there instead of 65).
+NOTEBOOK_TABLE = [  # n, layers asked, depth, U3, CX
+    (2, 5, 7, 9, 3), (3, 5, 13, 17, 6), (5, 5, 73, 165, 60), (6, 8, 115, 328, 120), (7, 8, 121, 392, 144),
+    (8, 8, 127, 456, 168), (9, 8, 133, 520, 192), (10, 15, 223, 1095, 405), (11, 15, 229, 1215, 450),
+    (12, 15, 235, 1335, 495)]
+
+
+@pytest.mark.parametrize("n,layers,depth,u3,cx", NOTEBOOK_TABLE)
+def test_published_depths_and_op_counts(n, layers, depth, u3, cx):
+    # README.md:70 depth 223; notebook cell 27 op counts, cell 28 depths
     psi = O.random_state(n, 0)
     res = O.prepare(psi, n, 2 ** n, layers, 0, gauge="canonical")
-    assert len(res["layers"]) == layers
+    used = len(res["layers"])
+    assert used == (layers if n >= 5 else 1)              # 2 and 3 qubits: exact after one layer (sequential.py:390)
     c1, c2 = both(n, lambda c: [c.unitary(g, q) for g, q in O.emit_gates(res["layers"], n)])
-    assert c1.get_depth() == depth == 6 * n + 12 * layers - 17
+    assert c1.get_depth() == depth
+    if n >= 5:
+        assert depth == 6 * n + 12 * layers - 17
     ops = c1.count_ops()
     n2, n1 = O.count_gates(res["layers"])
-    assert (ops["CX"], ops["U3"]) == (3 * n2, 8 * n2 + n1)
-    if n == 10:
-        assert (ops["CX"], ops["U3"]) == (405, 1095)
+    assert (ops["CX"], ops["U3"]) == (3 * n2, 8 * n2 + n1) == (cx, u3)
     assert np.abs(c1.get_statevector() - c2.get_statevector()).max() < 1e-9
     assert abs(abs(np.vdot(psi, c1.get_statevector())) - O.circuit_fidelity(psi, res["layers"], n)) < 1e-9
 
