@@ -222,3 +222,25 @@ def test_two_pass_build_switch(K):
     assert [int(t.shape[2]) for t in m.mps.tensors[:-1]] == O.bond_dims(ref["mps"])
     assert np.abs(b - O.circuit_state(ref["layers"], 12)).max() <= 1e-6
     assert np.abs(a - b).max() <= 1e-6
+
+
+@pytest.mark.parametrize("n,layers,published", [(7, 8, 0.9999999999998372), (8, 8, 0.9993833081918707),
+                                                (9, 8, 0.9856561882831156), (10, 15, 0.990348166799249),
+                                                (11, 15, 0.9625191328840889), (12, 15, 0.9318239807292739)])
+def test_notebook_fidelity_table_on_the_gpu(K, n, layers, published):
+    """Notebook cells 27-28: what the REAL reference printed for unseeded random states (bond dimension 2^n,
+    num_sweeps = 15 n, 8 layers below 10 qubits, 15 from 10 on), against the CUDA path on two seeds of the same
+    distribution through the public API; gate counts as published (cell 27: CX = 3 x two-qubit gates)."""
+    from qmprs.synthesis.mps_encoding import Sequential
+    from qmprs_b200 import GateListCircuit
+    enc = Sequential(GateListCircuit)
+    fs = []
+    for seed in (0, 1):
+        psi = O.random_state(n, seed)
+        circ = enc.prepare_state(psi, 2 ** n, num_layers=layers, num_sweeps=15 * n)
+        fs.append(abs(np.vdot(psi, circ.get_statevector())))
+        assert circ.count_ops() == {"unitary2": layers * (n - 1), "unitary1": layers}
+    if n == 7:
+        assert all(1 - f < 1e-8 for f in fs), fs
+    else:
+        assert abs(np.mean(fs) - published) < 2.5e-3, (fs, published)
