@@ -16,7 +16,11 @@ algorithm of those dependencies (quimb 1.10.0: ``MatrixProductState.from_dense``
 ``right_canonize``, ``right_compress`` / ``tensor_compress_bond``, ``gate_split``;
 quick: ``_get_submps_indices``; scipy ``null_space``) and follows the reference's own
 call sites line by line.  It is anchored on the reference's test inequalities and
-published statistics (README.md:59-70; tests/test_oracle.py).
+on the outputs the real reference stack published: the README statistic (README.md:59-70),
+the notebook's table of depths / U3 / CX counts for 2..12 qubits (30 integers, reproduced
+exactly) and its fidelities for 7..12 qubits (each bracketed by two seeds of the same
+distribution) -- tests/test_oracle.py, tests/test_transpile.py.  No fixture of the reference
+pins a vector or a matrix, hence "unpinned" at that level.
 
 Two gauge modes:
 
