@@ -418,10 +418,14 @@ extern "C" int qm_zgemm(int m, int n, int k, double alpha_re, double alpha_im, c
                                        : (long long)ceil_div(m, BM) * ceil_div(n, BN);
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cap);
-        if (batch == 1 && tiles < 64 && k >= 512 && (long long)m * n >= 4096 && cap == cudaStreamCaptureStatusNone) {
+        // k from 256 up, slices of >= 64 (round 2: k >= 512, slices >= 128 -- a 256^3 product then ran on 16 CTAs, 6.6x
+        // behind cuBLAS; QM_GEMM_SPLITK_MINK=512 restores that rule for A/B runs)
+        static const int splitk_mink = getenv("QM_GEMM_SPLITK_MINK") ? atoi(getenv("QM_GEMM_SPLITK_MINK")) : 256;
+        const int min_slice = splitk_mink >= 512 ? 128 : 64;
+        if (batch == 1 && tiles < 64 && k >= splitk_mink && (long long)m * n >= 4096 && cap == cudaStreamCaptureStatusNone) {
             int splits = (int)((148 + tiles - 1) / tiles);
             if (splits > 16) splits = 16;
-            if (splits > k / 128) splits = k / 128;
+            if (splits > k / min_slice) splits = k / min_slice;
             int kc = ((k + splits - 1) / splits + 15) / 16 * 16;
             splits = (k + kc - 1) / kc;
             if (splits >= 2) {

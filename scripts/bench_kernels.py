@@ -2,7 +2,7 @@
   * ZGEMM (this library vs cuBLAS through torch.matmul) at the contraction shapes of SURVEY section 8 A6;
   * SVD (qm_svd vs cuSOLVER through torch.linalg.svd, drivers gesvdj and gesvd) at the gate-split shapes of the
     16- and 20-qubit configurations -- the library bar for the Jacobi SVD.
-usage: python scripts/bench_kernels.py [out.json] [--no-gemm]"""
+usage: python scripts/bench_kernels.py [out.json] [--no-gemm] [--no-svd]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -28,7 +28,8 @@ out = {"zgemm": [], "svd": []}
 argv = [a for a in sys.argv[1:] if not a.startswith("--")]
 for (m, n, k, ta) in [] if "--no-gemm" in sys.argv else [(1024, 1024, 1024, 0), (512, 2048, 1024, 0), (2048, 512, 1024, 0), (1024, 1024, 2048, 0),
                       (2048, 2048, 2048, 0), (4096, 4096, 4096, 0), (8192, 2048, 2048, 0), (2048, 2048, 8192, 1),
-                      (256, 256, 256, 0), (512, 512, 512, 0)]:
+                      (256, 256, 256, 0), (512, 512, 512, 0), (512, 512, 256, 0), (256, 512, 256, 0), (128, 128, 256, 0),
+                      (512, 1024, 256, 0), (256, 256, 512, 0)]:
     A = torch.randn((k, m) if ta else (m, k), dtype=torch.complex128, device=dev)
     B = torch.randn(k, n, dtype=torch.complex128, device=dev)
     C = torch.empty(m, n, dtype=torch.complex128, device=dev)
@@ -42,7 +43,7 @@ for (m, n, k, ta) in [] if "--no-gemm" in sys.argv else [(1024, 1024, 1024, 0), 
     out["zgemm"].append(row)
 import numpy as np
 rng = np.random.default_rng(0)
-for (m, n) in [(64, 64), (128, 512), (256, 256), (256, 1024), (512, 512), (512, 2048), (2048, 512), (1024, 1024)]:
+for (m, n) in [] if "--no-svd" in sys.argv else [(64, 64), (128, 512), (256, 256), (256, 1024), (512, 512), (512, 2048), (2048, 512), (1024, 1024)]:
     a = rng.random((m, n)) + 1j * rng.random((m, n))
     A = K.from_host(a)
     s0 = K.svd_sweeps
