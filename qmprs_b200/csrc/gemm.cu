@@ -423,7 +423,7 @@ extern "C" int qm_zgemm(int m, int n, int k, double alpha_re, double alpha_im, c
         static const int splitk_mink = getenv("QM_GEMM_SPLITK_MINK") ? atoi(getenv("QM_GEMM_SPLITK_MINK")) : 256;
         const int min_slice = splitk_mink >= 512 ? 128 : 64;
         if (batch == 1 && tiles < 64 && k >= splitk_mink && (long long)m * n >= 4096 && cap == cudaStreamCaptureStatusNone) {
-            int splits = (int)((148 + tiles - 1) / tiles);
+            int splits = (int)(148 / tiles);               // one wave: tiles x splits <= 148 CTAs (512^3: 5 x 32 = 160 CTAs measured slower than 4 x 32)
             if (splits > 16) splits = 16;
             if (splits > k / min_slice) splits = k / min_slice;
             int kc = ((k + splits - 1) / splits + 15) / 16 * 16;
