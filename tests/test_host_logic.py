@@ -170,3 +170,22 @@ def test_iterative_schedule_early_break_and_blocks():
     for schedule in ("IterDiOall", "IterDiOi"):
         out = host.prepare(FakeKernels(), psi, 6, 8, 4, 2, schedule=schedule)
         assert out["n_layers"] == 1 and out["fidelity"] > 1 - 1e-12
+
+
+@pytest.mark.parametrize("schedule", ["IterDiOall", "IterDiOi"])
+def test_iterative_schedules_on_an_mps_in_any_gauge(schedule):
+    """prepare_mps(schedule=...) on a left-canonical, un-normalised MPS: the pre-conditioning of sequential.py:360-376
+    comes first, as in the default schedule, and the residual of Iter DiOall is rebuilt from the PRE-CONDITIONED MPS."""
+    n, chi, L, S = 7, 8, 3, 2
+    psi = O.random_state(n, 22)
+    A0 = O.compress_right(O.from_dense(psi, n), max_bond=chi)
+    A = O.left_canon([a.copy() for a in A0])
+    A[2] = 1.7 * A[2]
+    ref = O.prepare_mps(A, L, S, gauge="canonical", schedule=schedule)
+    K = FakeKernels(svd_phase_seed=6)
+    out = host.prepare(K, psi, n, chi, L, S, mps=[K.from_host(a) for a in A], schedule=schedule)
+    assert out["n_layers"] == ref["n_layers"]
+    assert np.abs(np.array(out["overlaps"]) - np.array(ref["overlaps"])).max() < 1e-9
+    g = out["gates"].reshape(-1, 16)
+    for idx, (_, _, _, site, G) in enumerate(gate_table(ref)):
+        assert np.abs(g[idx][: G.size] - G.reshape(-1)).max() < 1e-7
