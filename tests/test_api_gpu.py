@@ -194,6 +194,14 @@ def test_iterative_schedules_vs_oracle(K, schedule, n, chi, L, S, seed):
     assert np.abs(sv - O.circuit_state(ref["layers"], n)).max() <= 1e-6
     for a, b in zip(res["overlaps"], ref["overlaps"]):
         assert abs(a - b) < 1e-6
+    # committed fixture of the same configuration (tests/golden/make_golden_schedules.py)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_schedules.npz"))
+    tag = {(8, 32, 4, 3, 2): "s8", (10, 32, 3, 2, 5): "s10"}.get((n, chi, L, S, seed))
+    if tag is not None:
+        tag = f"{tag}_{schedule}"
+        assert np.abs(res["gates"] - z[tag + "_gates"]).max() < 1e-5
+        assert np.abs(sv - z[tag + "_state"]).max() <= 1e-6
+        assert abs(abs(np.vdot(psi, sv)) - float(z[tag + "_fidelity"])) <= 1e-6
     # attribute form, and the default schedule is untouched by it
     enc2 = Sequential(GateListCircuit)
     enc2.schedule = schedule

@@ -223,3 +223,18 @@ def test_iterative_schedules_properties():
     assert fid(psi, O.prepare(psi, n, chi, L, S, schedule="IterDiOall"), n) >= f_all - 1e-9
     with pytest.raises(ValueError):
         O.prepare(psi, n, chi, L, S, schedule="other")
+
+
+def test_golden_fixture_schedules():
+    """Fixtures written by tests/golden/make_golden_schedules.py (Iter DiOall / Iter DiOi, canonical gauge)."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_schedules.npz"))
+    for key in ("s8", "s10"):
+        for schedule in ("IterDiOall", "IterDiOi"):
+            tag = f"{key}_{schedule}"
+            n, chi, L, S, seed = [int(x) for x in z[tag + "_cfg"]]
+            psi = O.random_state(n, seed)
+            res = O.prepare(psi, n, chi, L, S, gauge="canonical", schedule=schedule)
+            assert res["n_layers"] == L
+            assert abs(fid(psi, res, n) - float(z[tag + "_fidelity"])) < 1e-9
+            assert np.abs(np.array(res["overlaps"]) - z[tag + "_overlaps"]).max() < 1e-9
+            assert np.abs(O.circuit_state(res["layers"], n) - z[tag + "_state"]).max() < 1e-6
