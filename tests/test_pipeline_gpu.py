@@ -206,3 +206,30 @@ def test_repeat_runs_are_bit_identical(K, pdl):
                 assert a["kinds"] == b["kinds"] and a["fidelity"] == b["fidelity"]
     finally:
         K.set_pdl(old)
+
+
+def test_edge_case_states_bonds_and_schedules_on_the_gpu(K):
+    """The seeded edge-case sweep of tests/test_host_logic.py through the CUDA kernels: 2..8 qubits, bond dimension
+    1..64, product / basis / GHZ / sparse / block-product / dense states, every schedule.  Layer count (early break),
+    block structure and fidelity equal the oracle's; gates too where the Schmidt spectrum is non-degenerate."""
+    from tests.test_host_logic import _edge_state
+    rng = np.random.default_rng(123)
+    kinds_all = ["random", "haar", "product", "ghz", "sparse", "basis", "blocks"]
+    for trial in range(70):
+        n = int(rng.integers(2, 9)); chi = int(rng.choice([1, 2, 3, 4, 8, 64]))
+        L = int(rng.integers(1, 5)); S = int(rng.integers(0, 3))
+        kind = str(rng.choice(kinds_all))
+        sched = str(rng.choice(["DallOall", "DallOall", "IterDiOall", "IterDiOi"]))
+        psi = _edge_state(rng, n, kind)
+        ref = O.prepare(psi, n, chi, L, S, gauge="canonical", schedule=sched)
+        out = host.prepare(K, psi, n, chi, L, S, schedule=sched)
+        ctx = (trial, n, chi, L, S, kind, sched)
+        assert out["n_layers"] == ref["n_layers"], ctx
+        flat = O.flatten_layers(ref["layers"])
+        kinds = [k for kl in out["kinds"] for k in kl]
+        assert kinds == [2 if G.shape[0] == 4 else 1 for (_, _, _, _, G) in flat], ctx
+        assert abs(out["fidelity"] - O.circuit_fidelity(psi, ref["layers"], n)) < 1e-6, ctx
+        if kind in ("random", "haar"):
+            g = out["gates"].reshape(-1, 16)
+            for idx, (_, _, _, _, G) in enumerate(flat):
+                assert np.abs(g[idx][: G.size] - G.reshape(-1)).max() < 1e-5, ctx
