@@ -56,7 +56,9 @@ int qm_svd_static(int m, int n, const void* A, long long lda, void* U, long long
  * iteration inside the kernel -- no workspace, no host synchronisation, CUDA-graph capturable.  Same outputs and
  * flags as qm_svd; strides in elements between consecutive problems (0 for batch = 1); U / Vh may be NULL.
  * mismatch (optional int[1]) is set to 1 if a problem has not converged after max_sweeps sweeps.
- * qm_svd_small_fits: 1 if the shape is supported (else qm_svd_small returns -3). */
+ * qm_svd_small_fits: 1 if the shape is supported (else qm_svd_small returns -3).
+ * Same reference call sites as qm_svd (numpy.linalg.svd behind quimb tensor_split: mps.py:242, :451-453, :881,
+ * :928-931, :968-971) wherever min(m, n) <= 64. */
 int qm_svd_small_fits(int m, int n, int flags);
 int qm_svd_small(int m, int n, const void* A, long long lda, long long strideA, void* U, long long ldu,
                  long long strideU, void* S, long long strideS, void* Vh, long long ldvh, long long strideVh,
@@ -85,12 +87,14 @@ int qm_qr_finish(int m, int n, const void* A, long long lda, void* R, long long 
 
 /* ---- MPS bookkeeping ----------------------------------------------------------- */
 
-/* Rank selection of quimb _trim_and_renorm_svd_result: mode 0 'rel', 1 'rsum2' (+renorm).
+/* Rank selection of quimb _trim_and_renorm_svd_result: mode 0 'rel' (compress: mps.py:247, :451-453, :881),
+ * 1 'rsum2' (+renorm; from_dense mps.py:242, gate_split_ mps.py:928-931, :968-971).
  * out_rank: int[1], out_f: double[1] (renormalisation factor). */
 int qm_trim(const void* S, int k, double cutoff, int mode, int max_bond, void* out_rank, void* out_f, void* stream);
 
 /* out = in with rows (mode 1) or columns (mode 2) scaled by (S*f)^(half_power ? 1/2 : 1);
- * mode 0 copies.  absorb='both' / 'left' of tensor_split.  f may be NULL. */
+ * mode 0 copies.  absorb='both' (mps.py:242, :968-971) / 'left' (mps.py:451-453, :881) of tensor_split.
+ * f may be NULL. */
 int qm_scale_copy(void* out, long long ldo, const void* in, long long ldi, int rows, int cols, const void* S,
                   const void* f, int mode, int half_power, void* stream);
 
@@ -187,7 +191,9 @@ int qm_expect_not_close(const void* f, double tol, void* mismatch, void* stream)
 /* ---- vectors ------------------------------------------------------------------- */
 int qm_conj_scale_copy(void* out, const void* in, long long n, int conj, double scale, void* stream);
 /* out[0..1] = sum conj(a_i) b_i (re, im).  Reproducible: per-CTA partials are kept in out[2..] and added in
- * fixed order by a second kernel, so `out` must hold qm_vdot_out_doubles() doubles. */
+ * fixed order by a second kernel, so `out` must hold qm_vdot_out_doubles() doubles.
+ * mps.norm() / mps.normalize() (mps.py:285, :302-310), the Ket normalisation (base.py:96-97) and the final
+ * <psi|circuit> (README.md:66); qm_div_sqrt: x <- x / sqrt(nrm2[0]). */
 int qm_vdot_out_doubles(void);
 int qm_vdot(const void* a, const void* b, long long n, void* out /* double[qm_vdot_out_doubles()] */, void* stream);
 int qm_div_sqrt(void* x, long long n, const void* nrm2 /* double[1] */, void* stream);
